@@ -357,8 +357,8 @@ static inline CV clip_lerp(const CV& in, const CV& out, float din, float dout) {
 }
 static inline int snap(float v) {
 	float s = v * 256.0f;
-	if (s > 1073741824.0f) s = 1073741824.0f;
-	if (s < -1073741824.0f) s = -1073741824.0f;
+	if (s > 536870912.0f) s = 536870912.0f;       // +-2^29 keeps coordinate differences inside int32
+	if (s < -536870912.0f) s = -536870912.0f;
 	return (int)lrintf(s);
 }
 static inline int64_t edge_fn(int ax, int ay, int bx, int by, int cx, int cy) {

@@ -1,0 +1,561 @@
+// C ABI of librad_cuda.so (include/rad_cuda.h): context, memory, the staged S1..S6 calls, the
+// device-resident shooting loop (CUDA graph), kernel benchmarks, and the NCCL plumbing of the
+// batched multi-GPU mode.  Kernels live in raster.cu / process.cu / select_update.cu.
+#include "rad_internal.cuh"
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <dlfcn.h>
+
+static std::string g_create_err;
+
+// ---- NCCL through dlopen: the same library instance torch already loaded when there is one -----
+namespace {
+struct NcclId { char internal[128]; };
+typedef int (*fn_ncclGetUniqueId)(NcclId*);
+typedef int (*fn_ncclCommInitRank)(void**, int, NcclId, int);
+typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(void*);
+typedef const char* (*fn_ncclGetErrorString)(int);
+struct NcclApi {
+	void* lib = nullptr;
+	fn_ncclGetUniqueId GetUniqueId = nullptr; fn_ncclCommInitRank CommInitRank = nullptr;
+	fn_ncclAllReduce AllReduce = nullptr; fn_ncclCommDestroy CommDestroy = nullptr; fn_ncclGetErrorString GetErrorString = nullptr;
+	bool load(std::string& err) {
+		if (lib) return true;
+		const char* names[] = { "libnccl.so.2", "libnccl.so" };
+		for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+		if (!lib) { err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+		GetUniqueId = (fn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+		CommInitRank = (fn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
+		AllReduce = (fn_ncclAllReduce)dlsym(lib, "ncclAllReduce");
+		CommDestroy = (fn_ncclCommDestroy)dlsym(lib, "ncclCommDestroy");
+		GetErrorString = (fn_ncclGetErrorString)dlsym(lib, "ncclGetErrorString");
+		if (!GetUniqueId || !CommInitRank || !AllReduce) { err = "libnccl: missing symbols"; lib = nullptr; return false; }
+		return true;
+	}
+};
+NcclApi g_nccl;
+const int kNcclFloat32 = 7, kNcclSum = 0;
+
+template <typename T> cudaError_t dalloc(T*& p, size_t n) { return cudaMalloc((void**)&p, n * sizeof(T)); }
+} // namespace
+
+extern "C" {
+
+const char* rad_version(void) { return "radiosity_b200 0.1 (sm_100a)"; }
+
+const char* rad_last_error(const rad_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+uint32_t rad_patch_count(const rad_ctx* c) { return c ? c->d.P : 0; }
+uint32_t rad_atlas_width(const rad_ctx* c) { return c ? c->d.W : 0; }
+uint32_t rad_atlas_height(const rad_ctx* c) { return c ? c->d.H : 0; }
+
+int rad_create(rad_ctx** out, const rad_config* cfg) {
+	if (!out || !cfg) { g_create_err = "rad_create: null argument"; return RAD_E_ARG; }
+	*out = nullptr;
+	if (cfg->hemicube_side < 16 || cfg->hemicube_side > 2048 || cfg->hemicube_side % 16) { g_create_err = "rad_create: hemicube_side must be a multiple of 16 in [16, 2048]"; return RAD_E_ARG; }
+	if (cfg->hemicubes < 1 || cfg->hemicubes > 64) { g_create_err = "rad_create: hemicubes must be in [1, 64]"; return RAD_E_ARG; }
+	if (cfg->max_patches < 1) { g_create_err = "rad_create: max_patches must be >= 1"; return RAD_E_ARG; }
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) { g_create_err = std::string("rad_create: no CUDA device (") + cudaGetErrorString(e) + ") — there is no CPU fallback"; return RAD_E_CUDA; }
+	if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "rad_create: bad device ordinal"; return RAD_E_ARG; }
+	if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return RAD_E_CUDA; }
+
+	rad_ctx* c = new rad_ctx();
+	c->cfg = *cfg;
+	c->have_ff = c->have_scene = c->emitters_ready = c->rendered = c->processed = c->keys_dirty = false;
+	c->parity = 0; c->selkey_valid = false;
+	c->graph_exec = nullptr; c->graph_batches = 0; c->graph_keep_items = false;
+	c->h_stage = nullptr; c->h_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
+	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
+	c->launches = 0;
+	RadDev& D = c->d;
+	memset(&D, 0, sizeof(D));
+	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
+	D.P = 0; D.h0 = 0; D.h1 = D.k;
+	D.reflectivity = cfg->reflectivity;
+	D.q_tri_cap = 1u << 16; D.q_ent_cap = 1u << 21;
+	const size_t Pm = cfg->max_patches;
+	float4 *v0, *v1, *v2; float *color, *ff, *proj;
+	bool ok = true;
+	#define A(expr) do { if (ok && (expr) != cudaSuccess) ok = false; } while (0)
+	A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	A(cudaEventCreate(&c->ev0)); A(cudaEventCreate(&c->ev1));
+	A(dalloc(v0, Pm)); A(dalloc(v1, Pm)); A(dalloc(v2, Pm));
+	A(dalloc(color, 3 * Pm)); A(dalloc(D.rad, 3 * Pm)); A(dalloc(D.illum, 3 * Pm));
+	A(dalloc(ff, (size_t)D.RES));
+	A(dalloc(D.keys, (size_t)D.k * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
+	A(dalloc(D.F, (size_t)D.k * Pm)); A(dalloc(D.dB, 3 * Pm));
+	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.ctl, 1));
+	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap));
+	A(dalloc(D.ework, Pm < 64 ? (size_t)64 : Pm)); A(dalloc(D.topkey, (size_t)D.k)); A(dalloc(proj, 16));
+	#undef A
+	if (!ok) {
+		g_create_err = std::string("rad_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+		delete c; return RAD_E_CUDA;
+	}
+	D.v0 = v0; D.v1 = v1; D.v2 = v2; D.color = color; D.ff = ff; D.proj = proj;
+	cudaMemcpyAsync(proj, cfg->projection, 64, cudaMemcpyHostToDevice, c->stream);
+	cudaMemsetAsync(D.keys, 0xFF, (size_t)D.k * D.RES * 8, c->stream);
+	cudaMemsetAsync(D.items, 0, (size_t)D.k * D.RES * 4, c->stream);
+	cudaMemsetAsync(D.F, 0, (size_t)D.k * Pm * 4, c->stream);
+	cudaMemsetAsync(D.dB, 0, 3 * Pm * 4, c->stream);
+	cudaMemsetAsync(D.em, 0, (size_t)D.k * sizeof(RadEmitter), c->stream);
+	cudaMemsetAsync(D.ctl, 0, sizeof(RadControl), c->stream);
+	cudaMemsetAsync(D.topkey, 0, (size_t)D.k * 8, c->stream);
+	if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete c; return RAD_E_CUDA; }
+	*out = c;
+	return RAD_OK;
+}
+
+static void drop_graph(rad_ctx* c) {
+	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_batches = 0; }
+}
+
+int rad_destroy(rad_ctx* c) {
+	if (!c) return RAD_OK;
+	cudaSetDevice(c->cfg.device);
+	cudaStreamSynchronize(c->stream);
+	drop_graph(c);
+	if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+	RadDev& D = c->d;
+	cudaFree((void*)D.v0); cudaFree((void*)D.v1); cudaFree((void*)D.v2); cudaFree((void*)D.color);
+	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
+	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.ctl);
+	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.ework); cudaFree(D.topkey); cudaFree((void*)D.proj);
+	if (c->h_stage) cudaFreeHost(c->h_stage);
+	if (c->saved) cudaFree(c->saved);
+	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+	cudaStreamDestroy(c->stream);
+	delete c;
+	return RAD_OK;
+}
+
+static int stage(rad_ctx* c, size_t bytes) {
+	if (c->h_stage_bytes >= bytes) return RAD_OK;
+	if (c->h_stage) cudaFreeHost(c->h_stage);
+	c->h_stage = nullptr; c->h_stage_bytes = 0;
+	RAD_CUDA_TRY(c, cudaMallocHost((void**)&c->h_stage, bytes));
+	c->h_stage_bytes = bytes;
+	return RAD_OK;
+}
+
+int rad_set_formfactors(rad_ctx* c, const float* ff, uint32_t n) {
+	if (!c || !ff) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	if (n != c->d.RES) { c->err = "rad_set_formfactors: n must be 3*N*N (one hemicube)"; return RAD_E_ARG; }
+	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.ff, ff, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	c->have_ff = true;
+	return RAD_OK;
+}
+
+// AoS float[P*3] -> three planes
+static void to_planes(const float* src, float* dst, size_t P) {
+	for (size_t i = 0; i < P; i++) { dst[i] = src[3 * i]; dst[P + i] = src[3 * i + 1]; dst[2 * P + i] = src[3 * i + 2]; }
+}
+static void from_planes(const float* src, float* dst, size_t P) {
+	for (size_t i = 0; i < P; i++) { dst[3 * i] = src[i]; dst[3 * i + 1] = src[P + i]; dst[3 * i + 2] = src[2 * P + i]; }
+}
+
+int rad_upload_state(rad_ctx* c, const float* rad3, const float* illum3) {
+	if (!c || !rad3 || !illum3) return RAD_E_ARG;
+	if (!c->have_scene) { c->err = "rad_upload_state: no scene"; return RAD_E_STATE; }
+	cudaSetDevice(c->cfg.device);
+	const size_t P = c->d.P;
+	int r = stage(c, 6 * P * 4); if (r) return r;
+	to_planes(rad3, c->h_stage, P); to_planes(illum3, c->h_stage + 3 * P, P);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.rad, c->h_stage, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.illum, c->h_stage + 3 * P, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.ctl, 0, sizeof(RadControl), c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	c->selkey_valid = false; c->emitters_ready = c->rendered = c->processed = false;
+	return RAD_OK;
+}
+
+int rad_upload_scene(rad_ctx* c, const float* verts12, const float* color3, const float* rad3, const float* illum3, uint32_t P) {
+	if (!c || !verts12 || !color3 || !rad3 || !illum3) return RAD_E_ARG;
+	if (P < 1 || P > c->cfg.max_patches) { c->err = "rad_upload_scene: P out of range (max_patches)"; return RAD_E_ARG; }
+	cudaSetDevice(c->cfg.device);
+	drop_graph(c);
+	int r = stage(c, (size_t)P * 12 * 4); if (r) return r;
+	float* s = c->h_stage;
+	// 48-byte quad records -> three float4 streams (coalesced 16 B loads per lane in the rasteriser)
+	for (size_t i = 0; i < P; i++) {
+		memcpy(s + 4 * i, verts12 + 12 * i, 16);
+		memcpy(s + 4 * (size_t)P + 4 * i, verts12 + 12 * i + 4, 16);
+		memcpy(s + 8 * (size_t)P + 4 * i, verts12 + 12 * i + 8, 16);
+	}
+	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.v0, s, (size_t)P * 16, cudaMemcpyHostToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.v1, s + 4 * (size_t)P, (size_t)P * 16, cudaMemcpyHostToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.v2, s + 8 * (size_t)P, (size_t)P * 16, cudaMemcpyHostToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	to_planes(color3, s, P);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.color, s, (size_t)P * 12, cudaMemcpyHostToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.F, 0, (size_t)c->d.k * P * 4, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	c->d.P = P;
+	c->have_scene = true;
+	return rad_upload_state(c, rad3, illum3);
+}
+
+int rad_download_state(rad_ctx* c, float* rad3, float* illum3) {
+	if (!c || !rad3 || !illum3) return RAD_E_ARG;
+	if (!c->have_scene) { c->err = "rad_download_state: no scene"; return RAD_E_STATE; }
+	cudaSetDevice(c->cfg.device);
+	const size_t P = c->d.P;
+	int r = stage(c, 6 * P * 4); if (r) return r;
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d.rad, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage + 3 * P, c->d.illum, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	from_planes(c->h_stage, rad3, P); from_planes(c->h_stage + 3 * P, illum3, P);
+	return RAD_OK;
+}
+
+static int need_ready(rad_ctx* c, const char* who) {
+	if (!c) return RAD_E_ARG;
+	if (!c->have_scene || !c->have_ff) { c->err = std::string(who) + ": upload the scene and the form factors first"; return RAD_E_STATE; }
+	cudaSetDevice(c->cfg.device);
+	return RAD_OK;
+}
+static int sync_check(rad_ctx* c) {
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	RAD_CUDA_TRY(c, cudaGetLastError());
+	return RAD_OK;
+}
+
+static int read_emitters(rad_ctx* c, uint32_t* ids_out, uint32_t* valid_out) {
+	std::vector<RadEmitter> em(c->d.k);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(em.data(), c->d.em, em.size() * sizeof(RadEmitter), cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	for (uint32_t h = 0; h < c->d.k; h++) { if (ids_out) ids_out[h] = em[h].id; if (valid_out) valid_out[h] = em[h].valid; }
+	return RAD_OK;
+}
+
+int rad_select(rad_ctx* c, uint32_t* ids_out, uint32_t* valid_out) {
+	int r = need_ready(c, "rad_select"); if (r) return r;
+	rad_launch_select(c);
+	if ((r = sync_check(c))) return r;
+	c->emitters_ready = true; c->rendered = c->processed = false;
+	if (ids_out || valid_out) return read_emitters(c, ids_out, valid_out);
+	return RAD_OK;
+}
+
+int rad_set_emitters(rad_ctx* c, const uint32_t* ids, uint32_t n) {
+	int r = need_ready(c, "rad_set_emitters"); if (r) return r;
+	if (!ids || n > c->d.k) { c->err = "rad_set_emitters: n must be <= hemicubes"; return RAD_E_ARG; }
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.ework, ids, n * 4, cudaMemcpyHostToDevice, c->stream));   // ework doubles as staging
+	rad_launch_set_emitters(c, c->d.ework, n);
+	if ((r = sync_check(c))) return r;
+	c->emitters_ready = true; c->rendered = c->processed = false;
+	c->selkey_valid = false;
+	return RAD_OK;
+}
+
+int rad_render_hemicubes(rad_ctx* c) {
+	int r = need_ready(c, "rad_render_hemicubes"); if (r) return r;
+	if (!c->emitters_ready) { c->err = "rad_render_hemicubes: call rad_select / rad_set_emitters first"; return RAD_E_STATE; }
+	rad_launch_clear_keys(c);
+	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.items, 0, (size_t)c->d.k * c->d.RES * 4, c->stream));   // glClear: NULL emitters stay black
+	rad_launch_raster(c);
+	rad_launch_resolve(c, /*reset=*/false);       // keys stay readable for rad_read_depthbuffer
+	if ((r = sync_check(c))) return r;
+	c->rendered = true; c->processed = false;
+	return RAD_OK;
+}
+
+int rad_process_hemicubes(rad_ctx* c) {
+	int r = need_ready(c, "rad_process_hemicubes"); if (r) return r;
+	if (!c->emitters_ready) { c->err = "rad_process_hemicubes: no emitters"; return RAD_E_STATE; }
+	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.F, 0, (size_t)c->d.k * c->d.P * 4, c->stream));
+	rad_launch_process(c);
+	if ((r = sync_check(c))) return r;
+	c->processed = true;
+	return RAD_OK;
+}
+
+static int read_ctl(rad_ctx* c, RadControl* out) {
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(out, c->d.ctl, sizeof(RadControl), cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	return RAD_OK;
+}
+
+int rad_apply(rad_ctx* c, float* last_energy_len) {
+	int r = need_ready(c, "rad_apply"); if (r) return r;
+	if (!c->processed) { c->err = "rad_apply: call rad_process_hemicubes first"; return RAD_E_STATE; }
+	rad_launch_apply(c, false);
+	if ((r = sync_check(c))) return r;
+	c->processed = c->rendered = c->emitters_ready = false;
+	c->selkey_valid = false;
+	RadControl ctl; if ((r = read_ctl(c, &ctl))) return r;
+	if (last_energy_len) *last_energy_len = ctl.last_energy_len;
+	return RAD_OK;
+}
+
+// one steady-state batch on the stream (single GPU): select -> camera -> raster -> fused resolve+process -> apply
+static void enqueue_batch(rad_ctx* c, bool keep_items) {
+	rad_launch_select(c);
+	rad_launch_raster(c);
+	rad_launch_resolve_process(c, keep_items);
+	const bool fuse = c->d.k == 1;
+	rad_launch_apply(c, fuse);
+	if (fuse) { c->parity ^= 1; c->selkey_valid = true; }
+}
+
+static int enqueue_batch_multi(rad_ctx* c, bool keep_items) {
+	rad_launch_select(c);
+	rad_launch_raster(c);
+	rad_launch_resolve_process(c, keep_items);
+	rad_launch_delta(c);
+	if (c->nccl_comm) {
+		int rc = g_nccl.AllReduce(c->d.dB, c->d.dB, (size_t)3 * c->d.P, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream);
+		if (rc != 0) { c->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return RAD_E_NCCL; }
+	}
+	rad_launch_finish(c, false);
+	c->selkey_valid = false;
+	return RAD_OK;
+}
+
+int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
+	int r = need_ready(c, "rad_shoot"); if (r) return r;
+	const bool keep = (c->cfg.flags & RAD_FLAG_KEEP_ITEMBUFFER) != 0;
+	RadControl ctl0; if ((r = read_ctl(c, &ctl0))) return r;
+	c->launches = 0;
+	uint64_t launches = 0;
+	if (c->keys_dirty) rad_launch_clear_keys(c);
+	RAD_CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+	uint32_t done = 0; bool stopped = false;
+	if (c->world > 1) {
+		for (; done < n_batches && !stopped; done++) {
+			if ((r = enqueue_batch_multi(c, keep))) return r;
+			if (stop_test) { RadControl t; if ((r = read_ctl(c, &t))) return r; stopped = t.stopped != 0; }
+		}
+		launches = c->launches;
+	} else {
+		if (c->d.k == 1 && !c->selkey_valid) rad_launch_argmax(c);
+		// steady state: a CUDA graph of GB batches (even, so that the k==1 key ping-pong returns to its start)
+		const uint32_t GB = 16;
+		if (n_batches >= GB) {
+			if (!c->graph_exec || c->graph_batches != GB || c->graph_keep_items != keep || c->graph_parity0 != c->parity) {
+				drop_graph(c);
+				cudaGraph_t g = nullptr;
+				const uint32_t parity0 = c->parity; const bool sk0 = c->selkey_valid; const uint32_t l0 = c->launches;
+				RAD_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+				for (uint32_t b = 0; b < GB; b++) enqueue_batch(c, keep);
+				RAD_CUDA_TRY(c, cudaStreamEndCapture(c->stream, &g));
+				RAD_CUDA_TRY(c, cudaGraphInstantiate(&c->graph_exec, g, 0));
+				cudaGraphDestroy(g);
+				c->graph_batches = GB; c->graph_keep_items = keep;
+				c->graph_launches = c->launches - l0;
+				c->parity = parity0; c->selkey_valid = sk0; c->launches = l0;   // capture did not execute anything
+				c->graph_parity0 = parity0;
+			}
+			while (n_batches - done >= GB && !stopped && c->parity == c->graph_parity0) {
+				RAD_CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
+				launches += c->graph_launches;
+				done += GB;
+				if (c->d.k == 1) c->selkey_valid = true;
+				if (stop_test) { RadControl t; if ((r = read_ctl(c, &t))) return r; stopped = t.stopped != 0; }
+			}
+		}
+		for (; done < n_batches && !stopped; done++) {
+			enqueue_batch(c, keep);
+			if (stop_test) { RadControl t; if ((r = read_ctl(c, &t))) return r; stopped = t.stopped != 0; }
+		}
+		launches += c->launches;
+	}
+	RAD_CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+	if ((r = sync_check(c))) return r;
+	c->emitters_ready = c->rendered = c->processed = false;
+	RadControl ctl; if ((r = read_ctl(c, &ctl))) return r;
+	if (out) {
+		out->batches_done = ctl.batches_done - ctl0.batches_done;
+		out->shots_done = ctl.shots_done - ctl0.shots_done;
+		out->stopped = ctl.stopped;
+		out->last_energy_len = ctl.last_energy_len;
+		cudaEventElapsedTime(&out->gpu_ms, c->ev0, c->ev1);
+		out->kernel_launches = (uint32_t)launches;
+		out->big_triangles = ctl.pad;
+		out->queue_overflow = ctl.q_overflow;
+	}
+	if (ctl.q_overflow) { c->err = "rad_shoot: tile queue overflow"; return RAD_E_CUDA; }
+	return RAD_OK;
+}
+
+int rad_read_itembuffer(rad_ctx* c, uint32_t hi, uint32_t* ids_out) {
+	if (!c || !ids_out || hi >= c->d.k) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(ids_out, c->d.items + (size_t)hi * c->d.RES, (size_t)c->d.RES * 4, cudaMemcpyDeviceToHost, c->stream));
+	return sync_check(c);
+}
+int rad_write_itembuffer(rad_ctx* c, uint32_t hi, const uint32_t* ids) {
+	if (!c || !ids || hi >= c->d.k) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.items + (size_t)hi * c->d.RES, ids, (size_t)c->d.RES * 4, cudaMemcpyHostToDevice, c->stream));
+	return sync_check(c);
+}
+int rad_read_depthbuffer(rad_ctx* c, uint32_t hi, uint32_t* depth_out) {
+	if (!c || !depth_out || hi >= c->d.k) return RAD_E_ARG;
+	if (!c->rendered) { c->err = "rad_read_depthbuffer: only valid right after rad_render_hemicubes"; return RAD_E_STATE; }
+	cudaSetDevice(c->cfg.device);
+	uint32_t* tmp = nullptr;
+	RAD_CUDA_TRY(c, cudaMalloc((void**)&tmp, (size_t)c->d.RES * 4));
+	rad_launch_read_depth(c, hi, tmp);
+	cudaError_t e = cudaMemcpyAsync(depth_out, tmp, (size_t)c->d.RES * 4, cudaMemcpyDeviceToHost, c->stream);
+	cudaStreamSynchronize(c->stream);
+	cudaFree(tmp);
+	if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return RAD_E_CUDA; }
+	return sync_check(c);
+}
+int rad_read_formfactors(rad_ctx* c, uint32_t hi, float* F) {
+	if (!c || !F || hi >= c->d.k) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(F, c->d.F + (size_t)hi * c->d.P, (size_t)c->d.P * 4, cudaMemcpyDeviceToHost, c->stream));
+	return sync_check(c);
+}
+int rad_read_mvp(rad_ctx* c, uint32_t hi, uint32_t face, float* out16) {
+	if (!c || !out16 || hi >= c->d.k || face >= RAD_NFACES) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(out16, c->d.mvp + ((size_t)hi * RAD_NFACES + face) * 16, 64, cudaMemcpyDeviceToHost, c->stream));
+	return sync_check(c);
+}
+
+int rad_bench_process(rad_ctx* c, uint32_t repeat, float* ms_per_launch) {
+	int r = need_ready(c, "rad_bench_process"); if (r) return r;
+	if (!c->emitters_ready) { c->err = "rad_bench_process: no emitters"; return RAD_E_STATE; }
+	if (repeat < 1) repeat = 1;
+	rad_launch_process(c);                         // warm-up
+	RAD_CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+	for (uint32_t i = 0; i < repeat; i++) rad_launch_process(c);
+	RAD_CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.F, 0, (size_t)c->d.k * c->d.P * 4, c->stream));
+	if ((r = sync_check(c))) return r;
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+	if (ms_per_launch) *ms_per_launch = ms / repeat;
+	c->processed = false;
+	return RAD_OK;
+}
+
+int rad_profile_batch(rad_ctx* c, float* ms6) {
+	int r = need_ready(c, "rad_profile_batch"); if (r) return r;
+	if (!ms6) return RAD_E_ARG;
+	cudaEvent_t ev[7];
+	for (int i = 0; i < 7; i++) cudaEventCreate(&ev[i]);
+	const bool keep = (c->cfg.flags & RAD_FLAG_KEEP_ITEMBUFFER) != 0;
+	if (c->d.k == 1 && !c->selkey_valid) rad_launch_argmax(c);
+	cudaEventRecord(ev[0], c->stream);
+	rad_launch_select(c);
+	cudaEventRecord(ev[1], c->stream);
+	{   // raster split in two for the report
+		rad_launch_raster_setup_only(c);
+		cudaEventRecord(ev[2], c->stream);
+		rad_launch_raster_tiles_only(c);
+	}
+	cudaEventRecord(ev[3], c->stream);
+	cudaEventRecord(ev[4], c->stream);            // resolve is fused into process in the steady state
+	rad_launch_resolve_process(c, keep);
+	cudaEventRecord(ev[5], c->stream);
+	const bool fuse = c->d.k == 1;
+	rad_launch_apply(c, fuse);
+	if (fuse) { c->parity ^= 1; c->selkey_valid = true; }
+	cudaEventRecord(ev[6], c->stream);
+	r = sync_check(c);
+	for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ms6[i], ev[i], ev[i + 1]);
+	for (int i = 0; i < 7; i++) cudaEventDestroy(ev[i]);
+	c->emitters_ready = c->rendered = c->processed = false;
+	return r;
+}
+
+// ---- device-side state snapshot (benchmarks restart from the same state without host traffic) ----
+int rad_save_state(rad_ctx* c) {
+	int r = need_ready(c, "rad_save_state"); if (r) return r;
+	const size_t P = c->d.P;
+	if (!c->saved) RAD_CUDA_TRY(c, cudaMalloc((void**)&c->saved, 6 * (size_t)c->cfg.max_patches * 4));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->saved, c->d.rad, 3 * P * 4, cudaMemcpyDeviceToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->saved + 3 * P, c->d.illum, 3 * P * 4, cudaMemcpyDeviceToDevice, c->stream));
+	return sync_check(c);
+}
+int rad_restore_state(rad_ctx* c) {
+	int r = need_ready(c, "rad_restore_state"); if (r) return r;
+	if (!c->saved) { c->err = "rad_restore_state: nothing saved"; return RAD_E_STATE; }
+	const size_t P = c->d.P;
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.rad, c->saved, 3 * P * 4, cudaMemcpyDeviceToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.illum, c->saved + 3 * P, 3 * P * 4, cudaMemcpyDeviceToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.ctl, 0, sizeof(RadControl), c->stream));
+	c->selkey_valid = false; c->emitters_ready = c->rendered = c->processed = false;
+	return sync_check(c);
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------
+int rad_nccl_unique_id(void* id_out128) {
+	if (!id_out128) return RAD_E_ARG;
+	if (!g_nccl.load(g_create_err)) return RAD_E_NCCL;
+	NcclId id; memset(&id, 0, sizeof(id));
+	if (g_nccl.GetUniqueId(&id) != 0) { g_create_err = "ncclGetUniqueId failed"; return RAD_E_NCCL; }
+	memcpy(id_out128, &id, 128);
+	return RAD_OK;
+}
+
+int rad_set_partition(rad_ctx* c, int rank, int world) {
+	if (!c || world < 1 || rank < 0 || rank >= world) return RAD_E_ARG;
+	drop_graph(c);
+	c->rank = rank; c->world = world;
+	c->d.h0 = (uint32_t)((uint64_t)c->d.k * rank / world);
+	c->d.h1 = (uint32_t)((uint64_t)c->d.k * (rank + 1) / world);
+	c->partition_only = c->nccl_comm == nullptr;
+	return RAD_OK;
+}
+
+int rad_comm_init(rad_ctx* c, int rank, int world, const void* id128) {
+	if (!c || !id128) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	if (!g_nccl.load(c->err)) return RAD_E_NCCL;
+	NcclId id; memcpy(&id, id128, 128);
+	int rc = g_nccl.CommInitRank(&c->nccl_comm, world, id, rank);
+	if (rc != 0) { c->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); c->nccl_comm = nullptr; return RAD_E_NCCL; }
+	int r = rad_set_partition(c, rank, world);
+	c->partition_only = false;
+	return r;
+}
+
+int rad_batch_partial(rad_ctx* c) {
+	int r = need_ready(c, "rad_batch_partial"); if (r) return r;
+	const bool keep = (c->cfg.flags & RAD_FLAG_KEEP_ITEMBUFFER) != 0;
+	rad_launch_select(c);
+	rad_launch_raster(c);
+	rad_launch_resolve_process(c, keep);
+	rad_launch_delta(c);
+	return sync_check(c);
+}
+int rad_read_delta(rad_ctx* c, float* dB3) {
+	if (!c || !dB3) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	const size_t P = c->d.P;
+	int r = stage(c, 3 * P * 4); if (r) return r;
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d.dB, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	from_planes(c->h_stage, dB3, P);
+	return RAD_OK;
+}
+int rad_write_delta(rad_ctx* c, const float* dB3) {
+	if (!c || !dB3) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	const size_t P = c->d.P;
+	int r = stage(c, 3 * P * 4); if (r) return r;
+	to_planes(dB3, c->h_stage, P);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.dB, c->h_stage, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
+	return sync_check(c);
+}
+int rad_batch_finish(rad_ctx* c, float* last_energy_len) {
+	int r = need_ready(c, "rad_batch_finish"); if (r) return r;
+	rad_launch_finish(c, false);
+	c->selkey_valid = false;
+	if ((r = sync_check(c))) return r;
+	RadControl ctl; if ((r = read_ctl(c, &ctl))) return r;
+	if (last_energy_len) *last_energy_len = ctl.last_energy_len;
+	return RAD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,105 @@
+// Internal declarations shared by the CUDA translation units of librad_cuda.so.
+// Public surface: include/rad_cuda.h.  All device float math is compiled with --fmad=false and
+// IEEE div/sqrt so that it reproduces, operation for operation, the float32 evaluation order of
+// the reference's host code (Vector.h / Transform.cpp / Camera.cpp) and of the CPU oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/rad_cuda.h"
+
+#define RAD_NFACES 5
+#define RAD_CLEAR_KEY 0xFFFFFFFFFFFFFFFFull
+#define RAD_TILE 64               // big-triangle tile edge in pixels
+#define RAD_BIG_AREA 4096         // bbox area (px) above which a triangle goes through the tile queue
+#define RAD_INLINE_AREA 32        // bbox area (px) up to which the owning lane rasterises alone
+
+struct RadBigTri {                // one screen-space triangle parked for tile processing (64 B)
+	int X0, Y0, X1, Y1, X2, Y2;   // snapped window coordinates, 8 sub-pixel bits
+	float z0, dz1, dz2, inv_area; // depth plane in barycentric form
+	uint32_t id1;                 // patch id + 1
+	uint32_t slot;                // hemicube slot (atlas index)
+	int px0, py0, px1, py1;       // pixel bbox already clipped to the face scissor
+};
+struct RadQueueEntry { uint32_t tri; uint16_t tx, ty; };
+
+struct RadControl {               // small device-resident control block
+	unsigned long long selkey[2]; // k==1 selection: (E bits << 32 | id), ping-pong by batch parity
+	uint32_t q_tris;              // tile queue: triangles parked
+	uint32_t q_entries;           // tile queue: (triangle, tile) entries
+	uint32_t q_overflow;
+	uint32_t stopped;             // |lastEnergy| < 0.1 seen
+	float last_energy_len;
+	uint32_t batches_done;
+	uint32_t shots_done;
+	uint32_t pad;
+};
+
+struct RadEmitter {               // per hemicube slot
+	uint32_t id;
+	uint32_t valid;               // 0 == the reference's NULL emitter
+	float S[3];                   // radiosity snapshot (Main.cpp:1161)
+	float color[3];               // emitter colour (Main.cpp:1274)
+};
+
+struct RadDev {                   // device pointers + sizes, passed by value to kernels
+	uint32_t P, N, W, H, RES, k;
+	uint32_t h0, h1;              // hemicube slots this rank renders/processes
+	float reflectivity;
+	const float4* v0; const float4* v1; const float4* v2;   // verts: (v1.xyz,v2.x) (v2.yz,v3.xy) (v3.z,v4.xyz)
+	const float* color;           // [3][P] planes
+	float* rad;                   // [3][P] planes  (B, unshot)
+	float* illum;                 // [3][P] planes  (I, shot)
+	const float* ff;              // [RES]
+	unsigned long long* keys;     // [k][RES] (depth24 << 32 | id+1), RAD_CLEAR_KEY when empty
+	uint32_t* items;              // [k][RES] id+1
+	float* F;                     // [k][P]
+	float* dB;                    // [3][P] partial received energy (multi-GPU)
+	float* mvp;                   // [k][5][16] column-major
+	RadEmitter* em;               // [k]
+	RadControl* ctl;
+	RadBigTri* q_tri; RadQueueEntry* q_ent;
+	uint32_t q_tri_cap, q_ent_cap;
+	uint32_t* ework;              // [P] scratch energies for top-k rounds
+	unsigned long long* topkey;   // [k] winners of the top-k rounds
+	const float* proj;            // [16]
+};
+
+struct rad_ctx {
+	rad_config cfg;
+	RadDev d;
+	cudaStream_t stream;
+	cudaEvent_t ev0, ev1;
+	std::string err;
+	bool have_ff, have_scene, emitters_ready, rendered, processed, keys_dirty;
+	uint32_t parity;              // selkey ping-pong for k==1
+	bool selkey_valid;            // selkey[parity] holds the argmax of the current B
+	// CUDA graph of the steady-state loop
+	cudaGraphExec_t graph_exec; uint32_t graph_batches; bool graph_keep_items; uint32_t graph_launches, graph_parity0;
+	float* saved;                 // device snapshot of (B, I) for rad_save_state / rad_restore_state
+	// host staging
+	float* h_stage; size_t h_stage_bytes;
+	// multi-GPU
+	int rank, world; void* nccl_comm; bool partition_only;
+	uint32_t launches;            // kernels launched since last reset
+};
+
+// ---- launchers (each enqueues on ctx->stream and bumps ctx->launches) -------------------------
+void rad_launch_select(rad_ctx* c);                 // S1 + camera/snapshots (all modes)
+void rad_launch_camera(rad_ctx* c);                 // camera/snapshots only (emitters already set)
+void rad_launch_raster(rad_ctx* c);                 // setup + inline/warp raster, then tile queue
+void rad_launch_raster_setup_only(rad_ctx* c);
+void rad_launch_raster_tiles_only(rad_ctx* c);
+void rad_launch_set_emitters(rad_ctx* c, const uint32_t* d_ids, uint32_t n);
+void rad_launch_resolve(rad_ctx* c, bool reset);    // keys -> items (+ keys reset)
+void rad_launch_clear_keys(rad_ctx* c);
+void rad_launch_process(rad_ctx* c);                // items -> F
+void rad_launch_resolve_process(rad_ctx* c, bool keep_items);   // fused
+void rad_launch_apply(rad_ctx* c, bool fuse_select); // S4..S6 (+ argmax of the new B for k==1)
+void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB
+void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update
+void rad_launch_argmax(rad_ctx* c);                 // k==1: prime selkey[parity] from the current B
+void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out);
+
+#define RAD_CUDA_TRY(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+	(c)->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return RAD_E_CUDA; } } while (0)

@@ -1,0 +1,419 @@
+// K1 — five-face hemicube item-buffer rasteriser (replaces the OpenGL render of the reference:
+// Shaders.cpp:235-260 patch-view program, DrawPatchLook Main.cpp:689-725, GL state Main.cpp:12,1104,
+// 1148-1200, atlas/FBO Main.cpp:271-294) and the per-emitter camera set-up done on the CPU in
+// OnIdle (Main.cpp:1161,1172-1183 -> Camera.cpp:19-52,97-103, Transform.cpp:26-46,70-80,127-156).
+//
+// Pipeline per batch (all on the context's stream):
+//   camera_kernel        k x 5 lanes: radiosity snapshot, emitter colour, the five MVPs
+//   raster_setup_kernel  one lane per (patch[,face]): vertex transform, near-plane clip, viewport,
+//                        8-bit sub-pixel snap, back-face cull, scissored bbox; then three tiers:
+//                          tiny  bbox  -> the owning lane walks it alone
+//                          medium bbox -> the warp walks it cooperatively in 8x4 pixel blocks
+//                          big   bbox  -> parked in the tile queue (64x64 pixel tiles)
+//   raster_tiles_kernel  persistent warps drain the tile queue
+//   resolve_kernel       64-bit keys -> uint32 item buffer (id+1), keys reset for the next batch
+// Visibility is a deterministic 64-bit atomicMin of (depth24 << 32 | id+1) per pixel: equal to GL_LESS
+// with patches drawn in id order (Main.cpp:715-720), independent of thread scheduling.
+//
+// Raster rules (identical, operation for operation, to oracle/oracle.cpp): clip = MVP*(p,1) with
+// row r = ((m0r*x + m1r*y) + m2r*z) + m3r; near clip z+w>=0 with new vertices interpolated from the
+// inside vertex; xw = x/w*(N/2) + (vx+N/2); RNE snap to 1/256 px; keep signed area > 0 (CCW front,
+// GL_CULL_FACE back); pixel centres, exact int64 edge functions, top-left tie rule; depth =
+// barycentric interpolation of z/w*0.5+0.5, RNE-quantised to 24 bit, d >= 0xFFFFFF fails (LESS vs 1.0).
+#include "rad_internal.cuh"
+
+namespace {
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 vneg(V3 a) { return mk(-a.x, -a.y, -a.z); }
+// the reference's v_Cross: a.v_Cross(b) == b x a   (Vector.h:534-537)
+__device__ __forceinline__ V3 rcross(V3 a, V3 b) {
+	return mk(b.y * a.z - b.z * a.y, b.z * a.x - b.x * a.z, b.x * a.y - b.y * a.x);
+}
+__device__ __forceinline__ V3 vnormalize(V3 a) {   // Vector.h:390-400: t = 1/len, then scale
+	float t = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+	if (t != 0) { t = 1 / t; a.x *= t; a.y *= t; a.z *= t; }
+	return a;
+}
+
+// out = a * b, column-major m[c*4+r], term order of Matrix4f::ProductOf (Vector.cpp:445-458)
+__device__ __forceinline__ void mat_product(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b) {
+	for (int c = 0; c < 4; c++)
+		for (int r = 0; r < 4; r++)
+			out[c * 4 + r] = a[r] * b[c * 4] + a[4 + r] * b[c * 4 + 1] + a[8 + r] * b[c * 4 + 2] + a[12 + r] * b[c * 4 + 3];
+}
+
+struct Quad { V3 a, b, c, d; };
+__device__ __forceinline__ Quad load_quad(const RadDev& D, uint32_t p) {
+	float4 q0 = __ldg(D.v0 + p), q1 = __ldg(D.v1 + p), q2 = __ldg(D.v2 + p);
+	Quad q;
+	q.a = mk(q0.x, q0.y, q0.z); q.b = mk(q0.w, q1.x, q1.y); q.c = mk(q1.z, q1.w, q2.x); q.d = mk(q2.y, q2.z, q2.w);
+	return q;
+}
+
+// face order in the atlas = p_patchlook_perm (Main.h:210-211): UP, DOWN, LEFT, RIGHT, FRONT
+// MVP = Perspective * LookAt(eye, target + eye, up), column-major m[c*4+r]
+__device__ void build_mvp(const Quad& q, int face, const float* __restrict__ proj, float* __restrict__ out) {
+	V3 eye = mk((q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f, (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f, (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f);
+	V3 normal = rcross(vsub(q.b, q.a), vsub(q.d, q.a));   // Patch::getNormal, Patch.cpp:272-276
+	V3 pup = vsub(q.d, q.a);                              // Patch::getUp, Patch.cpp:253-255
+	V3 target, up;
+	switch (face) {                                       // Camera::lookFromPatch, Camera.cpp:19-52
+	case 0: target = pup; up = vneg(normal); break;                       // UP
+	case 1: target = vneg(pup); up = normal; break;                       // DOWN
+	case 2: target = vneg(rcross(normal, pup)); up = pup; break;          // LEFT
+	case 3: target = rcross(normal, pup); up = pup; break;                // RIGHT
+	default: target = normal; up = pup; break;                            // FRONT
+	}
+	// CGLTransform::LookAt(eye, target + eye, up)
+	V3 dir = vnormalize(vsub(vadd(target, eye), eye));
+	V3 right = vnormalize(rcross(dir, up));
+	up = rcross(right, dir);
+	float la[16], tr[16], mv[16];
+	la[0] = right.x; la[4] = right.y; la[8] = right.z;
+	la[1] = up.x; la[5] = up.y; la[9] = up.z;
+	la[2] = -dir.x; la[6] = -dir.y; la[10] = -dir.z;
+	la[3] = 0; la[7] = 0; la[11] = 0; la[12] = 0; la[13] = 0; la[14] = 0; la[15] = 1;
+	// Translate(-eye): (*this) *= Translation  (Vector.cpp:325-330,478-527) — full products so that signed
+	// zeros come out exactly as in the reference
+	for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) tr[c * 4 + r] = (c < 3) ? (float)(c == r) : 0.0f;
+	tr[12] = -eye.x; tr[13] = -eye.y; tr[14] = -eye.z; tr[15] = 1;
+	mat_product(mv, la, tr);
+	mat_product(out, proj, mv);     // t_projection * t_modelview (Main.cpp:1183)
+}
+
+// one block per hemicube slot: lanes 0..4 build the face matrices, lane 0 takes the snapshot
+__global__ void camera_kernel(RadDev D) {
+	uint32_t h = blockIdx.x;
+	RadEmitter e = D.em[h];
+	if (!e.valid || e.id >= D.P) return;
+	if (threadIdx.x < RAD_NFACES) {
+		Quad q = load_quad(D, e.id);
+		build_mvp(q, threadIdx.x, D.proj, D.mvp + ((size_t)h * RAD_NFACES + threadIdx.x) * 16);
+	}
+	if (threadIdx.x == 0) {
+		for (int c = 0; c < 3; c++) {
+			D.em[h].S[c] = D.rad[(size_t)c * D.P + e.id];          // p_tmp_radiosities[hi] (Main.cpp:1161)
+			D.em[h].color[c] = D.color[(size_t)c * D.P + e.id];
+		}
+	}
+}
+
+struct CV { float x, y, z, w; };
+__device__ __forceinline__ CV xform(const float* __restrict__ m, V3 p) {
+	CV c;
+	c.x = ((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12];
+	c.y = ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13];
+	c.z = ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14];
+	c.w = ((m[3] * p.x + m[7] * p.y) + m[11] * p.z) + m[15];
+	return c;
+}
+__device__ __forceinline__ CV clip_lerp(const CV& in, const CV& out, float din, float dout) {
+	float t = din / (din - dout);
+	CV r;
+	r.x = in.x + t * (out.x - in.x);
+	r.y = in.y + t * (out.y - in.y);
+	r.z = in.z + t * (out.z - in.z);
+	r.w = in.w + t * (out.w - in.w);
+	return r;
+}
+__device__ __forceinline__ int snap256(float v) {
+	float s = v * 256.0f;
+	s = fminf(fmaxf(s, -536870912.0f), 536870912.0f);
+	return __float2int_rn(s);
+}
+__device__ __forceinline__ long long edge_fn(int ax, int ay, int bx, int by, int cx, int cy) {
+	return (long long)(bx - ax) * (long long)(cy - ay) - (long long)(by - ay) * (long long)(cx - ax);
+}
+__device__ __forceinline__ int edge_bias(int ax, int ay, int bx, int by) {
+	int dx = bx - ax, dy = by - ay;
+	return (dy < 0 || (dy == 0 && dx < 0)) ? 0 : -1;
+}
+
+struct Tri {                 // screen-space triangle ready for coverage
+	int X0, Y0, X1, Y1, X2, Y2;
+	float z0, dz1, dz2, inv_area;
+	int bx;                  // px0 | px1 << 16
+	int by;                  // py0 | py1 << 16
+};
+
+// coverage + depth + visibility for one pixel
+__device__ __forceinline__ void shade_pixel(const Tri& t, int b0, int b1, int b2, int px, int py, uint32_t id1,
+                                            unsigned long long* __restrict__ keys, uint32_t W) {
+	int cx = px * 256 + 128, cy = py * 256 + 128;
+	long long e0 = edge_fn(t.X1, t.Y1, t.X2, t.Y2, cx, cy);
+	long long e1 = edge_fn(t.X2, t.Y2, t.X0, t.Y0, cx, cy);
+	long long e2 = edge_fn(t.X0, t.Y0, t.X1, t.Y1, cx, cy);
+	if (((e0 + b0) | (e1 + b1) | (e2 + b2)) < 0) return;
+	float l1 = (float)e1 * t.inv_area, l2 = (float)e2 * t.inv_area;
+	float z = (t.z0 + l1 * t.dz1) + l2 * t.dz2;
+	z = fminf(fmaxf(z, 0.0f), 1.0f);
+	uint32_t dq = __float2uint_rn(z * 16777215.0f);
+	if (dq >= 0xFFFFFFu) return;
+	unsigned long long key = ((unsigned long long)dq << 32) | id1;
+	unsigned long long* a = keys + (size_t)py * W + px;
+	if (key < __ldcg(a)) atomicMin(a, key);   // the stale read only skips atomics that cannot win
+}
+
+// project + snap + cull + bbox.  Returns bbox area in pixels (0 = nothing to draw).
+__device__ __forceinline__ int setup_tri(const CV& a, const CV& b, const CV& c, int vpx, int vpy, int N,
+                                         int scx, int scy, int scw, int sch, Tri& t) {
+	// exact trivial reject (w > 0 after the near clip): wholly beyond one viewport edge
+	if ((a.x > a.w && b.x > b.w && c.x > c.w) || (a.x < -a.w && b.x < -b.w && c.x < -c.w) ||
+	    (a.y > a.w && b.y > b.w && c.y > c.w) || (a.y < -a.w && b.y < -b.w && c.y < -c.w)) return 0;
+	float hw = (float)N * 0.5f;
+	float ox = (float)vpx + hw, oy = (float)vpy + hw;
+	t.X0 = snap256((a.x / a.w) * hw + ox); t.Y0 = snap256((a.y / a.w) * hw + oy);
+	t.X1 = snap256((b.x / b.w) * hw + ox); t.Y1 = snap256((b.y / b.w) * hw + oy);
+	t.X2 = snap256((c.x / c.w) * hw + ox); t.Y2 = snap256((c.y / c.w) * hw + oy);
+	long long area2 = edge_fn(t.X0, t.Y0, t.X1, t.Y1, t.X2, t.Y2);
+	if (area2 <= 0) return 0;
+	int minx = min(t.X0, min(t.X1, t.X2)), maxx = max(t.X0, max(t.X1, t.X2));
+	int miny = min(t.Y0, min(t.Y1, t.Y2)), maxy = max(t.Y0, max(t.Y1, t.Y2));
+	int px0 = max((minx - 128 + 255) >> 8, scx), px1 = min((maxx - 128) >> 8, scx + scw - 1);
+	int py0 = max((miny - 128 + 255) >> 8, scy), py1 = min((maxy - 128) >> 8, scy + sch - 1);
+	if (px0 > px1 || py0 > py1) return 0;
+	float za = (a.z / a.w) * 0.5f + 0.5f, zb = (b.z / b.w) * 0.5f + 0.5f, zc = (c.z / c.w) * 0.5f + 0.5f;
+	t.z0 = za; t.dz1 = zb - za; t.dz2 = zc - za;
+	t.inv_area = 1.0f / (float)area2;
+	t.bx = px0 | (px1 << 16); t.by = py0 | (py1 << 16);
+	return (px1 - px0 + 1) * (py1 - py0 + 1);
+}
+
+__device__ __forceinline__ void park_big(const RadDev& D, const Tri& t, uint32_t id1, uint32_t slot) {
+	uint32_t ti = atomicAdd(&D.ctl->q_tris, 1u);
+	if (ti >= D.q_tri_cap) { D.ctl->q_overflow = 1; return; }
+	RadBigTri r;
+	r.X0 = t.X0; r.Y0 = t.Y0; r.X1 = t.X1; r.Y1 = t.Y1; r.X2 = t.X2; r.Y2 = t.Y2;
+	r.z0 = t.z0; r.dz1 = t.dz1; r.dz2 = t.dz2; r.inv_area = t.inv_area;
+	r.id1 = id1; r.slot = slot;
+	r.px0 = t.bx & 0xFFFF; r.px1 = t.bx >> 16; r.py0 = t.by & 0xFFFF; r.py1 = t.by >> 16;
+	D.q_tri[ti] = r;
+	int tx0 = r.px0 / RAD_TILE, tx1 = r.px1 / RAD_TILE, ty0 = r.py0 / RAD_TILE, ty1 = r.py1 / RAD_TILE;
+	uint32_t n = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
+	uint32_t e = atomicAdd(&D.ctl->q_entries, n);
+	if (e + n > D.q_ent_cap) { D.ctl->q_overflow = 1; return; }
+	for (int ty = ty0; ty <= ty1; ty++)
+		for (int tx = tx0; tx <= tx1; tx++) {
+			RadQueueEntry q; q.tri = ti; q.tx = (uint16_t)tx; q.ty = (uint16_t)ty;
+			D.q_ent[e++] = q;
+		}
+}
+
+#define FULL 0xFFFFFFFFu
+
+// grid: x = patch chunk, y = face (SPLIT) or 1, z = local hemicube slot
+template <bool SPLIT_FACES>
+__global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
+	__shared__ float s_mvp[RAD_NFACES][16];
+	const uint32_t slot = D.h0 + blockIdx.z;
+	const RadEmitter em = D.em[slot];
+	if (!em.valid) return;
+	const int f_begin = SPLIT_FACES ? blockIdx.y : 0, f_end = SPLIT_FACES ? blockIdx.y + 1 : RAD_NFACES;
+	if (threadIdx.x < RAD_NFACES * 16) (&s_mvp[0][0])[threadIdx.x] = D.mvp[(size_t)slot * RAD_NFACES * 16 + threadIdx.x];
+	__syncthreads();
+
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = p < D.P;
+	const int lane = threadIdx.x & 31;
+	const int N = (int)D.N;
+	unsigned long long* __restrict__ keys = D.keys + (size_t)slot * D.RES;
+	Quad q;
+	if (live) q = load_quad(D, p);
+	const uint32_t id1 = p + 1;
+
+	for (int f = f_begin; f < f_end; f++) {
+		// viewport origin and scissor of this face (Main.cpp:314-389)
+		int vpx, vpy, scx, scy, scw, sch;
+		switch (f) {
+		case 0: vpx = 0; vpy = N; scx = 0; scy = N; scw = N; sch = N / 2; break;
+		case 1: vpx = N; vpy = N / 2; scx = N; scy = N; scw = N; sch = N / 2; break;
+		case 2: vpx = -(N / 2); vpy = 0; scx = 0; scy = 0; scw = N / 2; sch = N; break;
+		case 3: vpx = N + N / 2; vpy = 0; scx = N + N / 2; scy = 0; scw = N / 2; sch = N; break;
+		default: vpx = N / 2; vpy = 0; scx = N / 2; scy = 0; scw = N; sch = N; break;
+		}
+		CV c[4]; float dn[4]; int nin = 0;
+		if (live) {
+			c[0] = xform(s_mvp[f], q.a); c[1] = xform(s_mvp[f], q.b); c[2] = xform(s_mvp[f], q.c); c[3] = xform(s_mvp[f], q.d);
+			#pragma unroll
+			for (int i = 0; i < 4; i++) { dn[i] = c[i].z + c[i].w; nin += dn[i] >= 0.0f; }
+		}
+		if (!__any_sync(FULL, nin > 0)) continue;
+
+		#pragma unroll
+		for (int t = 0; t < 2; t++) {          // triangles (0,1,2) and (0,2,3), ModelContainer.cpp:112-117
+			CV p0, p1, p2, p3; int n = 0;
+			if (live && nin > 0) {
+				const CV in0 = c[0], in1 = c[t + 1], in2 = c[t + 2];
+				const float d0 = dn[0], d1 = dn[t + 1], d2 = dn[t + 2];
+				// near-plane clip; vertex order as produced by walking the edges 0-1, 1-2, 2-0
+				switch ((d0 >= 0.0f ? 1 : 0) | (d1 >= 0.0f ? 2 : 0) | (d2 >= 0.0f ? 4 : 0)) {
+				case 7: p0 = in0; p1 = in1; p2 = in2; n = 3; break;
+				case 1: p0 = in0; p1 = clip_lerp(in0, in1, d0, d1); p2 = clip_lerp(in0, in2, d0, d2); n = 3; break;
+				case 2: p0 = clip_lerp(in1, in0, d1, d0); p1 = in1; p2 = clip_lerp(in1, in2, d1, d2); n = 3; break;
+				case 4: p0 = clip_lerp(in2, in1, d2, d1); p1 = in2; p2 = clip_lerp(in2, in0, d2, d0); n = 3; break;
+				case 3: p0 = in0; p1 = in1; p2 = clip_lerp(in1, in2, d1, d2); p3 = clip_lerp(in0, in2, d0, d2); n = 4; break;
+				case 6: p0 = clip_lerp(in1, in0, d1, d0); p1 = in1; p2 = in2; p3 = clip_lerp(in2, in0, d2, d0); n = 4; break;
+				case 5: p0 = in0; p1 = clip_lerp(in0, in1, d0, d1); p2 = clip_lerp(in2, in1, d2, d1); p3 = in2; n = 4; break;
+				default: break;
+				}
+			}
+			for (int sub = 0; sub < 2; sub++) {
+				if (!__any_sync(FULL, n >= 3 + sub)) break;
+				Tri tr; int area = 0;
+				if (n >= 3 + sub) area = setup_tri(p0, sub ? p2 : p1, sub ? p3 : p2, vpx, vpy, N, scx, scy, scw, sch, tr);
+				int b0 = 0, b1 = 0, b2 = 0;
+				if (area > 0) { b0 = edge_bias(tr.X1, tr.Y1, tr.X2, tr.Y2); b1 = edge_bias(tr.X2, tr.Y2, tr.X0, tr.Y0); b2 = edge_bias(tr.X0, tr.Y0, tr.X1, tr.Y1); }
+				// tier 1: tiny bbox, the owning lane walks it alone
+				if (area > 0 && area <= RAD_INLINE_AREA) {
+					const int px0 = tr.bx & 0xFFFF, px1 = tr.bx >> 16, py0 = tr.by & 0xFFFF, py1 = tr.by >> 16;
+					for (int py = py0; py <= py1; py++)
+						for (int px = px0; px <= px1; px++)
+							shade_pixel(tr, b0, b1, b2, px, py, id1, keys, D.W);
+				}
+				// tier 3: big bbox, parked for the tile pass
+				if (area > RAD_BIG_AREA) park_big(D, tr, id1, slot);
+				// tier 2: medium bbox, the warp walks it together in 8x4 blocks
+				unsigned m = __ballot_sync(FULL, area > RAD_INLINE_AREA && area <= RAD_BIG_AREA);
+				while (m) {
+					const int src = __ffs(m) - 1;
+					m &= m - 1;
+					Tri w;
+					w.X0 = __shfl_sync(FULL, tr.X0, src); w.Y0 = __shfl_sync(FULL, tr.Y0, src);
+					w.X1 = __shfl_sync(FULL, tr.X1, src); w.Y1 = __shfl_sync(FULL, tr.Y1, src);
+					w.X2 = __shfl_sync(FULL, tr.X2, src); w.Y2 = __shfl_sync(FULL, tr.Y2, src);
+					w.z0 = __shfl_sync(FULL, tr.z0, src); w.dz1 = __shfl_sync(FULL, tr.dz1, src);
+					w.dz2 = __shfl_sync(FULL, tr.dz2, src); w.inv_area = __shfl_sync(FULL, tr.inv_area, src);
+					w.bx = __shfl_sync(FULL, tr.bx, src); w.by = __shfl_sync(FULL, tr.by, src);
+					const uint32_t wid = __shfl_sync(FULL, id1, src);
+					const int wb0 = edge_bias(w.X1, w.Y1, w.X2, w.Y2), wb1 = edge_bias(w.X2, w.Y2, w.X0, w.Y0), wb2 = edge_bias(w.X0, w.Y0, w.X1, w.Y1);
+					const int px0 = w.bx & 0xFFFF, px1 = w.bx >> 16, py0 = w.by & 0xFFFF, py1 = w.by >> 16;
+					for (int by = py0; by <= py1; by += 4)
+						for (int bx = px0; bx <= px1; bx += 8) {
+							const int px = bx + (lane & 7), py = by + (lane >> 3);
+							if (px <= px1 && py <= py1) shade_pixel(w, wb0, wb1, wb2, px, py, wid, keys, D.W);
+						}
+				}
+			}
+		}
+	}
+}
+
+// persistent warps drain the (triangle, tile) queue
+__global__ void __launch_bounds__(128) raster_tiles_kernel(RadDev D) {
+	const uint32_t nent = min(D.ctl->q_entries, D.q_ent_cap);
+	const int lane = threadIdx.x & 31;
+	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t i = gw; i < nent; i += nw) {
+		const RadQueueEntry e = D.q_ent[i];
+		if (e.tri >= D.q_tri_cap) continue;
+		const RadBigTri r = D.q_tri[e.tri];
+		Tri w;
+		w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
+		w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
+		const int b0 = edge_bias(w.X1, w.Y1, w.X2, w.Y2), b1 = edge_bias(w.X2, w.Y2, w.X0, w.Y0), b2 = edge_bias(w.X0, w.Y0, w.X1, w.Y1);
+		const int px0 = max(r.px0, (int)e.tx * RAD_TILE), px1 = min(r.px1, (int)e.tx * RAD_TILE + RAD_TILE - 1);
+		const int py0 = max(r.py0, (int)e.ty * RAD_TILE), py1 = min(r.py1, (int)e.ty * RAD_TILE + RAD_TILE - 1);
+		unsigned long long* __restrict__ keys = D.keys + (size_t)r.slot * D.RES;
+		// skip the tile when one edge has all four tile corners strictly outside (exact, conservative)
+		{
+			const int cx0 = px0 * 256 + 128, cx1 = px1 * 256 + 128, cy0 = py0 * 256 + 128, cy1 = py1 * 256 + 128;
+			bool out = false;
+			#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				const int ax = k == 0 ? w.X1 : (k == 1 ? w.X2 : w.X0), ay = k == 0 ? w.Y1 : (k == 1 ? w.Y2 : w.Y0);
+				const int bx = k == 0 ? w.X2 : (k == 1 ? w.X0 : w.X1), by = k == 0 ? w.Y2 : (k == 1 ? w.Y0 : w.Y1);
+				out |= edge_fn(ax, ay, bx, by, cx0, cy0) < 0 && edge_fn(ax, ay, bx, by, cx1, cy0) < 0 &&
+				       edge_fn(ax, ay, bx, by, cx0, cy1) < 0 && edge_fn(ax, ay, bx, by, cx1, cy1) < 0;
+			}
+			if (out) continue;
+		}
+		for (int by = py0; by <= py1; by += 4)
+			for (int bx = px0; bx <= px1; bx += 8) {
+				const int px = bx + (lane & 7), py = by + (lane >> 3);
+				if (px <= px1 && py <= py1) shade_pixel(w, b0, b1, b2, px, py, r.id1, keys, D.W);
+			}
+	}
+}
+
+// keys -> item buffer (id+1, 0 = empty).  With `reset` the keys are cleared for the next batch, so no
+// separate clear pass is needed in the steady state.  Also recycles the tile queue.
+__global__ void __launch_bounds__(256) resolve_kernel(RadDev D, int reset) {
+	const uint32_t slot = D.h0 + blockIdx.y;
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { D.ctl->pad = D.ctl->q_tris; D.ctl->q_tris = 0; D.ctl->q_entries = 0; }
+	unsigned long long* __restrict__ keys = D.keys + (size_t)slot * D.RES;
+	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.RES; i += gridDim.x * blockDim.x) {
+		const unsigned long long k = keys[i];
+		items[i] = k == RAD_CLEAR_KEY ? 0u : (uint32_t)(k & 0xFFFFFFFFull);
+		if (reset) keys[i] = RAD_CLEAR_KEY;
+	}
+}
+
+__global__ void __launch_bounds__(256) clear_keys_kernel(unsigned long long* __restrict__ keys, size_t n) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) keys[i] = RAD_CLEAR_KEY;
+}
+
+__global__ void read_depth_kernel(const unsigned long long* __restrict__ keys, uint32_t* __restrict__ out, uint32_t n) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { unsigned long long k = keys[i]; out[i] = k == RAD_CLEAR_KEY ? 0xFFFFFFu : (uint32_t)(k >> 32); }
+}
+
+} // namespace
+
+void rad_launch_camera(rad_ctx* c) {
+	camera_kernel<<<c->d.k, 32, 0, c->stream>>>(c->d);
+	c->launches++;
+}
+
+void rad_launch_raster_setup_only(rad_ctx* c) {
+	if (c->keys_dirty) rad_launch_clear_keys(c);
+	const RadDev& D = c->d;
+	const uint32_t nslots = D.h1 - D.h0;
+	if (nslots == 0) return;
+	const uint32_t bx = (D.P + 127) / 128;
+	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
+	if ((uint64_t)D.P * nslots < (1u << 18))
+		raster_setup_kernel<true><<<dim3(bx, RAD_NFACES, nslots), 128, 0, c->stream>>>(D);
+	else
+		raster_setup_kernel<false><<<dim3(bx, 1, nslots), 128, 0, c->stream>>>(D);
+	c->launches++;
+}
+
+void rad_launch_raster_tiles_only(rad_ctx* c) {
+	if (c->d.h1 == c->d.h0) return;
+	raster_tiles_kernel<<<148 * 4, 128, 0, c->stream>>>(c->d);
+	c->launches++;
+}
+
+void rad_launch_raster(rad_ctx* c) {
+	rad_launch_raster_setup_only(c);
+	rad_launch_raster_tiles_only(c);
+}
+
+void rad_launch_resolve(rad_ctx* c, bool reset) {
+	const RadDev& D = c->d;
+	const uint32_t nslots = D.h1 - D.h0;
+	if (nslots == 0) return;
+	uint32_t bx = (D.RES + 255) / 256;
+	if (bx > 148 * 8) bx = 148 * 8;
+	resolve_kernel<<<dim3(bx, nslots), 256, 0, c->stream>>>(D, reset ? 1 : 0);
+	c->launches++;
+	c->keys_dirty = !reset;
+}
+
+void rad_launch_clear_keys(rad_ctx* c) {
+	const RadDev& D = c->d;
+	clear_keys_kernel<<<148 * 8, 256, 0, c->stream>>>(D.keys, (size_t)D.k * D.RES);
+	c->launches++;
+	c->keys_dirty = false;
+}
+
+void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out) {
+	const RadDev& D = c->d;
+	read_depth_kernel<<<(D.RES + 255) / 256, 256, 0, c->stream>>>(D.keys + (size_t)hi * D.RES, d_out, D.RES);
+	c->launches++;
+}

@@ -1,0 +1,284 @@
+// K3 — shooter selection, K4 — fused energy transfer + emitter update (+ argmax of the new state).
+//
+// Replaces, from the reference:
+//   ModelContainer::getHighestRadiosityPatchesId  ModelContainer.cpp:259-299   (CPU list + sort)
+//   energy transfer                               Main.cpp:1272-1279           (CPU, O(k*P))
+//   emitter update + stop test                    Main.cpp:1286-1303
+//
+// K4 is ONE pass over the patches: B_i += sum_h ((S_h * F_h[i]) * rho) (.) c_h in hemicube order (the
+// reference's float association), F is zeroed for the next batch, emitters get I += S, B -= S, and —
+// for k == 1 — the squared length of the updated B goes through a warp-shuffle block reduction and a
+// single 64-bit atomicMax, which IS the next selection: key = (bits(|B|^2) << 32 | id) reproduces the
+// reference's k == 1 result exactly (largest energy, LAST index among equals, patch 0 if all zero).
+//
+// For k > 1: RAD_SELECT_REFERENCE runs a one-block emulation of the reference's list (seeded patch 0,
+// reject-below-minimum while not full, tie groups reversed by every insertion); RAD_SELECT_TOPK runs k
+// argmax rounds with exclusion, key = (bits << 32 | ~id): energy desc, id asc.
+#include "rad_internal.cuh"
+
+namespace {
+
+#define FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ float len2(float x, float y, float z) { return x * x + y * y + z * z; }   // Vector.h:356-359
+
+__device__ __forceinline__ unsigned long long warp_max(unsigned long long v) {
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		const unsigned long long o = __shfl_xor_sync(FULL, v, d);
+		v = o > v ? o : v;
+	}
+	return v;
+}
+// block-wide max, result valid in thread 0
+__device__ __forceinline__ unsigned long long block_max(unsigned long long v) {
+	__shared__ unsigned long long s_w[32];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	v = warp_max(v);
+	if (lane == 0) s_w[w] = v;
+	__syncthreads();
+	if (w == 0) {
+		v = lane < nw ? s_w[lane] : 0ull;
+		v = warp_max(v);
+	}
+	return v;
+}
+
+__device__ __forceinline__ unsigned long long energy_key_last(float e, uint32_t i) {   // ties -> larger id
+	return e > 0.0f ? ((unsigned long long)__float_as_uint(e) << 32) | i : 0ull;
+}
+
+// ---- k == 1: argmax of the current B into selkey[parity] ------------------------------------
+__global__ void __launch_bounds__(256) argmax_kernel(RadDev D, int parity) {
+	unsigned long long best = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.P; i += gridDim.x * blockDim.x)
+		best = max(best, energy_key_last(len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i]), i));
+	best = block_max(best);
+	if (threadIdx.x == 0 && best) atomicMax(&D.ctl->selkey[parity], best);
+}
+
+// k == 1: turn selkey[parity] into emitter slot 0 and recycle the other key for this batch's apply
+__global__ void emitter_from_selkey_kernel(RadDev D, int parity) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		const unsigned long long key = D.ctl->selkey[parity];
+		D.em[0].id = (uint32_t)(key & 0xFFFFFFFFull);      // all-zero energies -> key 0 -> patch 0 (the seeded entry)
+		D.em[0].valid = 1;
+		D.ctl->selkey[parity ^ 1] = 0ull;
+	}
+}
+
+// ---- reference list semantics for k > 1 (single block) --------------------------------------
+__global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
+	__shared__ float s_e[1024];
+	__shared__ unsigned s_flags[32];
+	__shared__ uint32_t l_id[65]; __shared__ float l_e[65];
+	__shared__ int s_n; __shared__ float s_min;
+	const uint32_t count = D.k;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	if (threadIdx.x == 0) { s_n = 0; s_min = 0.0f; }
+	__syncthreads();
+	for (uint32_t base = 0; base < D.P; base += 1024) {
+		const uint32_t i = base + threadIdx.x;
+		const float e = i < D.P ? len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i]) : 0.0f;
+		s_e[threadIdx.x] = e;
+		// superset of the accepted candidates: the list minimum never decreases
+		const bool cand = i < D.P && ((s_n == 0 && i == 0) || (e > 0.0f && e >= s_min));
+		const unsigned b = __ballot_sync(FULL, cand);
+		if (lane == 0) s_flags[w] = b;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			int n = s_n;
+			for (int ww = 0; ww < 32; ww++) {
+				unsigned m = s_flags[ww];
+				while (m) {
+					const int j = ww * 32 + __ffs(m) - 1;
+					m &= m - 1;
+					const float x = s_e[j];
+					if (!(n == 0 || (x > 0.0f && l_e[n - 1] <= x))) continue;
+					// every tie group is reversed by the stable-sort + reverse of the reference (ModelContainer.cpp:273-275)
+					for (int a = 0; a < n;) {
+						int z = a;
+						while (z + 1 < n && l_e[z + 1] == l_e[a]) z++;
+						for (int lo = a, hi = z; lo < hi; lo++, hi--) { const uint32_t t = l_id[lo]; l_id[lo] = l_id[hi]; l_id[hi] = t; }
+						a = z + 1;
+					}
+					int pos = 0;
+					while (pos < n && l_e[pos] > x) pos++;      // the newcomer leads its tie group
+					for (int q = n; q > pos; q--) { l_id[q] = l_id[q - 1]; l_e[q] = l_e[q - 1]; }
+					l_id[pos] = base + j; l_e[pos] = x;
+					n++;
+					if (n > (int)count) n = (int)count;
+				}
+			}
+			s_n = n;
+			s_min = n > 0 ? l_e[n - 1] : 0.0f;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x < count) {
+		const bool ok = (int)threadIdx.x < s_n;
+		D.em[threadIdx.x].id = ok ? l_id[threadIdx.x] : 0u;
+		D.em[threadIdx.x].valid = ok ? 1u : 0u;
+	}
+}
+
+// ---- clean top-k for k > 1: k argmax rounds with exclusion ----------------------------------
+__global__ void __launch_bounds__(256) topk_round_kernel(RadDev D, int r) {
+	if (blockIdx.x == 0 && threadIdx.x == 0 && r + 1 < (int)D.k) D.topkey[r + 1] = 0ull;
+	uint32_t excl = 0xFFFFFFFFu;
+	if (r > 0) {
+		const unsigned long long pk = D.topkey[r - 1];
+		if (pk == 0ull) return;                       // fewer than r patches carry energy
+		excl = 0xFFFFFFFFu - (uint32_t)(pk & 0xFFFFFFFFull);
+	}
+	unsigned long long best = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.P; i += gridDim.x * blockDim.x) {
+		uint32_t eb;
+		if (r == 0) { eb = __float_as_uint(len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i])); D.ework[i] = eb; }
+		else {
+			eb = D.ework[i];
+			if (i == excl) { eb = 0; D.ework[i] = 0; }
+		}
+		if (eb != 0 && eb < 0x7F800000u) best = max(best, ((unsigned long long)eb << 32) | (0xFFFFFFFFu - i));
+	}
+	best = block_max(best);
+	if (threadIdx.x == 0 && best) atomicMax(&D.topkey[r], best);
+}
+__global__ void topk_finalize_kernel(RadDev D) {
+	const uint32_t h = threadIdx.x;
+	if (h < D.k) {
+		const unsigned long long key = D.topkey[h];
+		bool ok = key != 0ull;
+		for (uint32_t j = 0; j < h && ok; j++) ok = D.topkey[j] != 0ull;   // an exhausted round ends the list
+		D.em[h].id = ok ? 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull) : 0u;
+		D.em[h].valid = ok ? 1u : 0u;
+	}
+	__syncthreads();
+	if (h == 0) D.topkey[0] = 0ull;
+}
+
+__global__ void set_emitters_kernel(RadDev D, const uint32_t* __restrict__ ids, uint32_t n) {
+	const uint32_t h = threadIdx.x;
+	if (h < D.k) { D.em[h].id = h < n ? ids[h] : 0u; D.em[h].valid = (h < n && ids[h] < D.P) ? 1u : 0u; }
+}
+
+// ---- K4: energy transfer + emitter update (+ fused argmax) -----------------------------------
+// MODE 0: single GPU — reference association B += d_0, += d_1, ...   (reads F of all k slots)
+// MODE 1: multi GPU, local part — dB = sum of this rank's slots      (B untouched)
+// MODE 2: multi GPU, final part — B += dB (after the all-reduce), emitter update
+template <int MODE>
+__global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, int parity) {
+	extern __shared__ RadEmitter s_em[];
+	for (uint32_t h = threadIdx.x; h < D.k; h += blockDim.x) s_em[h] = D.em[h];
+	__syncthreads();
+	const uint32_t P = D.P, k = D.k;
+	const float rho = D.reflectivity;
+	int last_h = -1; uint32_t nvalid = 0;
+	for (uint32_t h = 0; h < k; h++) if (s_em[h].valid) { last_h = (int)h; nvalid++; }
+	unsigned long long best = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+		if (MODE == 1) {
+			float dx = 0.0f, dy = 0.0f, dz = 0.0f;
+			for (uint32_t h = D.h0; h < D.h1; h++) {
+				if (!s_em[h].valid) continue;
+				float* fp = D.F + (size_t)h * P + i;
+				const float f = *fp;
+				if (f != 0.0f) *fp = 0.0f;
+				dx += ((s_em[h].S[0] * f) * rho) * s_em[h].color[0];
+				dy += ((s_em[h].S[1] * f) * rho) * s_em[h].color[1];
+				dz += ((s_em[h].S[2] * f) * rho) * s_em[h].color[2];
+			}
+			D.dB[i] = dx; D.dB[P + i] = dy; D.dB[2 * (size_t)P + i] = dz;
+			continue;
+		}
+		float bx = D.rad[i], by = D.rad[P + i], bz = D.rad[2 * (size_t)P + i];
+		if (MODE == 0) {
+			for (uint32_t h = 0; h < k; h++) {
+				if (!s_em[h].valid) continue;
+				float* fp = D.F + (size_t)h * P + i;
+				const float f = *fp;
+				if (f != 0.0f) *fp = 0.0f;                                  // fill_n(p_tmp_formfactors, 0) (Main.cpp:1278)
+				// p->radiosity += S_h * F[i] * reflectivity * colour(emitter_h)   (Main.cpp:1274)
+				bx += ((s_em[h].S[0] * f) * rho) * s_em[h].color[0];
+				by += ((s_em[h].S[1] * f) * rho) * s_em[h].color[1];
+				bz += ((s_em[h].S[2] * f) * rho) * s_em[h].color[2];
+			}
+		} else {
+			bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i];
+		}
+		// emitters: lastEnergy, I += S, B -= S   (Main.cpp:1286-1295)
+		for (uint32_t h = 0; h < k; h++) {
+			if (!s_em[h].valid || s_em[h].id != i) continue;
+			if ((int)h == last_h) {
+				const float l = sqrtf(len2(bx, by, bz));
+				D.ctl->last_energy_len = l;
+				if ((double)l < 0.1) D.ctl->stopped = 1;                    // Main.cpp:1298
+			}
+			D.illum[i] += s_em[h].S[0]; D.illum[P + i] += s_em[h].S[1]; D.illum[2 * (size_t)P + i] += s_em[h].S[2];
+			bx -= s_em[h].S[0]; by -= s_em[h].S[1]; bz -= s_em[h].S[2];
+		}
+		D.rad[i] = bx; D.rad[P + i] = by; D.rad[2 * (size_t)P + i] = bz;
+		if (fuse_select) best = max(best, energy_key_last(len2(bx, by, bz), i));
+	}
+	if (MODE != 1) {
+		if (blockIdx.x == 0 && threadIdx.x == 0) { D.ctl->batches_done += 1; D.ctl->shots_done += nvalid; }
+		if (fuse_select) {
+			best = block_max(best);
+			if (threadIdx.x == 0 && best) atomicMax(&D.ctl->selkey[parity ^ 1], best);
+		}
+	}
+}
+
+} // namespace
+
+static uint32_t patch_grid(uint32_t P, uint32_t threads) {
+	uint32_t b = (P + threads - 1) / threads;
+	const uint32_t cap = 148 * 8;
+	return b > cap ? cap : (b ? b : 1);
+}
+
+void rad_launch_argmax(rad_ctx* c) {
+	cudaMemsetAsync(&c->d.ctl->selkey[c->parity], 0, sizeof(unsigned long long), c->stream);
+	argmax_kernel<<<patch_grid(c->d.P, 256), 256, 0, c->stream>>>(c->d, (int)c->parity);
+	c->launches++;
+	c->selkey_valid = true;
+}
+
+void rad_launch_select(rad_ctx* c) {
+	const RadDev& D = c->d;
+	if (D.k == 1) {
+		if (!c->selkey_valid) rad_launch_argmax(c);
+		emitter_from_selkey_kernel<<<1, 32, 0, c->stream>>>(D, (int)c->parity);
+		c->launches++;
+	} else if (c->cfg.select_mode == RAD_SELECT_REFERENCE) {
+		select_reference_kernel<<<1, 1024, 0, c->stream>>>(D);
+		c->launches++;
+	} else {
+		for (uint32_t r = 0; r < D.k; r++) topk_round_kernel<<<patch_grid(D.P, 256), 256, 0, c->stream>>>(D, (int)r);
+		topk_finalize_kernel<<<1, 64, 0, c->stream>>>(D);
+		c->launches += D.k + 1;
+	}
+	rad_launch_camera(c);
+}
+
+void rad_launch_set_emitters(rad_ctx* c, const uint32_t* d_ids, uint32_t n) {
+	set_emitters_kernel<<<1, 64, 0, c->stream>>>(c->d, d_ids, n);
+	c->launches++;
+	rad_launch_camera(c);
+}
+
+void rad_launch_apply(rad_ctx* c, bool fuse_select) {
+	const RadDev& D = c->d;
+	apply_kernel<0><<<patch_grid(D.P, 256), 256, D.k * sizeof(RadEmitter), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
+	c->launches++;
+}
+void rad_launch_delta(rad_ctx* c) {
+	const RadDev& D = c->d;
+	apply_kernel<1><<<patch_grid(D.P, 256), 256, D.k * sizeof(RadEmitter), c->stream>>>(D, 0, 0);
+	c->launches++;
+}
+void rad_launch_finish(rad_ctx* c, bool fuse_select) {
+	const RadDev& D = c->d;
+	apply_kernel<2><<<patch_grid(D.P, 256), 256, D.k * sizeof(RadEmitter), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
+	c->launches++;
+}
