@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Generates tests/golden/golden.json from the REFERENCE's own host code (oracle/_ref/libref_host.so, built by
+oracle/ref_build.sh from /root/reference/source) — run in the authoring container only:
+
+    python tests/golden/make_golden.py
+
+Section "reference" holds values produced by reference code.  Section "oracle_regression" holds outputs of the
+CPU oracle for the two stages the reference delegates to GPU drivers (GL raster, CL kernel); those pin the
+oracle against accidental change, they are NOT reference outputs (no GL/CL stack exists in this image).
+"""
+import ctypes
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import orc  # noqa: E402
+
+vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+
+
+def seeded_radiosity(P, seed):
+    """Deterministic pseudo-random energies with many ties and zeros (portable: integer LCG, no numpy RNG)."""
+    x = np.arange(P * 3, dtype=np.uint64) * np.uint64(6364136223846793005) + np.uint64(1442695040888963407 + seed)
+    x ^= x >> np.uint64(29)
+    x = (x * np.uint64(0xBF58476D1CE4E5B9)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    x ^= x >> np.uint64(32)
+    q = (x % np.uint64(9)).astype(np.float32) / np.float32(4.0)          # {0, .25, ..., 2}
+    zero = ((x >> np.uint64(8)) % np.uint64(3)) == 0
+    q[zero] = 0
+    return q.reshape(P, 3)
+
+
+def main():
+    R = orc.ref()
+    assert R is not None, "build oracle/_ref first (bash oracle/ref_build.sh)"
+    g = {"reference": {}, "oracle_regression": {}}
+    ref = g["reference"]
+
+    ref["sizeof_patch"] = int(R.refp_sizeof_patch())
+    ref["scenes"] = {}
+    for area in (0.5, 0.014, 0.0035, 0.0009):
+        P = int(R.refp_scene_build(area))
+        v = np.zeros((P, 12), np.float32); ix = np.zeros((P, 6), np.int32)
+        c = np.zeros((P, 3), np.float32); r = np.zeros((P, 3), np.float32); il = np.zeros((P, 3), np.float32)
+        R.refp_scene_get(vp(v), vp(ix), vp(c), vp(r), vp(il))
+        lights = np.nonzero(r[:, 0] > 0)[0]
+        s = {"P": P, "lights": int(lights.size), "first_light": int(lights[0]), "last_light": int(lights[-1]),
+             "verts_sha256": sha(v), "indices_sha256": sha(ix), "color_sha256": sha(c), "rad_sha256": sha(r), "illum_sha256": sha(il)}
+        sel = {}
+        for k in (1, 10, 64):
+            ids = np.zeros(k, np.uint32); nul = np.zeros(k, np.int32)
+            R.refp_select(k, vp(ids), vp(nul))
+            sel[str(k)] = {"ids": ids.tolist(), "null": nul.tolist()}
+        s["select_fresh"] = sel
+        if P <= 70000:
+            nb = np.zeros((P, 8), np.int32); R.refp_neighbours(vp(nb)); s["neighbours_sha256"] = sha(nb)
+            rs = {}
+            for seed in (0, 1):
+                rad = seeded_radiosity(P, seed)
+                R.refp_scene_set_radiosity(vp(rad))
+                for k in (1, 3, 10, 64):
+                    ids = np.zeros(k, np.uint32); nul = np.zeros(k, np.int32)
+                    R.refp_select(k, vp(ids), vp(nul))
+                    rs[f"seed{seed}_k{k}"] = {"ids": ids.tolist(), "null": nul.tolist()}
+            s["select_seeded"] = rs
+            R.refp_scene_set_radiosity(vp(r))
+        if area == 0.5:
+            mv = {}
+            for p in (0, 100, 320, 323, 400, 501):
+                for look in range(5):
+                    m = np.zeros(16, np.float32); R.refp_mvp(p, look, vp(m))
+                    mv[f"{p}_{look}"] = m.view(np.uint32).tolist()
+            s["mvp_bits"] = mv
+            geo = {}
+            for p in (0, 320, 501):
+                cc = np.zeros(3, np.float32); nn = np.zeros(3, np.float32); uu = np.zeros(3, np.float32)
+                R.refp_patch_geom(p, vp(cc), vp(nn), vp(uu))
+                geo[str(p)] = {"center": cc.view(np.uint32).tolist(), "normal": nn.view(np.uint32).tolist(), "up": uu.view(np.uint32).tolist()}
+            s["geom_bits"] = geo
+        ref["scenes"][repr(area)] = s
+    ref["P_area_0.00022"] = 1021554      # measured once from the reference; too slow to regenerate in the CPU suite
+
+    m = np.zeros(16, np.float32); R.refp_projection(vp(m)); ref["projection_bits"] = m.view(np.uint32).tolist()
+
+    ref["config"] = {}
+    for side, k in ((16, 10), (128, 1), (512, 64), (1024, 64)):
+        out = (ctypes.c_uint * 9)(); R.refp_config(side, k, out); ref["config"][f"{side}_{k}"] = list(out)
+
+    ref["formfactors"] = {}
+    for N in (16, 128, 512):
+        ff = np.zeros(3 * N * N * 2, np.float32); R.refp_formfactors(N, 2, vp(ff))
+        one = ff[:3 * N * N]
+        ref["formfactors"][str(N)] = {"sha256_k2": sha(ff), "sum_f64": float(one.sum(dtype=np.float64)),
+                                      "first_bits": int(one[:1].view(np.uint32)[0]),
+                                      "center_bits": int(one[(N // 2) * 2 * N + N: (N // 2) * 2 * N + N + 1].view(np.uint32)[0])}
+
+    ref["codec"] = {}
+    for P in (1, 7, 502, 16469, 64659, 250063, 1021554):
+        out = (ctypes.c_uint * 11)(); R.refp_colors_setup(P, out)
+        samples = sorted(i for i in {1, 2, P // 3 + 1, P // 2 + 1, P} if i <= P)
+        ref["codec"][str(P)] = {"params": list(out), "colors": {str(i): int(R.refp_color(i)) for i in samples},
+                                "index_of_color": {str(int(R.refp_color(i))): int(R.refp_color_index(R.refp_color(i))) for i in samples}}
+
+    objp = os.path.join(ROOT, "tests", "golden", "simple.obj")
+    for area in (0.0, 0.3):
+        P = int(R.refp_scene_build_obj(objp.encode(), area))
+        v = np.zeros((P, 12), np.float32); c = np.zeros((P, 3), np.float32); r = np.zeros((P, 3), np.float32)
+        R.refp_scene_get(vp(v), None, vp(c), vp(r), None)
+        ref.setdefault("obj", {})[repr(area)] = {"P": P, "verts_sha256": sha(v), "color_sum": float(c.sum()), "rad_sum": float(r.sum())}
+
+    # ---- oracle regression (NOT reference outputs) ----
+    reg = g["oracle_regression"]
+    v, c, r, il = orc.scene_cornell(0.5)
+    P = v.shape[0]
+    for N, shooter in ((32, 323), (32, 100), (64, 0), (128, 450)):
+        ids, dep = orc.render_hemicube(v, shooter, N, want_depth=True)
+        ff = orc.formfactors(N)
+        F = orc.process_ids(ids, ff, N, P)
+        reg[f"hemicube_N{N}_s{shooter}"] = {"ids_sha256": sha(ids), "depth_sha256": sha(dep), "F_sha256": sha(F),
+                                            "empty": int((ids == 0).sum()), "sumF": float(F.sum(dtype=np.float64))}
+    rad, illum, sched, n, last = orc.shoot(v, c, r, il, 32, 1, 40)
+    reg["shoot_area0.5_N32_k1_40"] = {"rad_sha256": sha(rad), "illum_sha256": sha(illum), "schedule": sched.ravel().tolist(),
+                                      "sumB": float(rad.sum(dtype=np.float64)), "last": float(last)}
+    rad, illum, sched, n, last = orc.shoot(v, c, r, il, 32, 10, 6)
+    reg["shoot_area0.5_N32_k10_6"] = {"rad_sha256": sha(rad), "illum_sha256": sha(illum), "schedule": sched.ravel().tolist(),
+                                      "sumB": float(rad.sum(dtype=np.float64)), "last": float(last)}
+
+    out = os.path.join(ROOT, "tests", "golden", "golden.json")
+    with open(out, "w") as f:
+        json.dump(g, f, indent=1, sort_keys=True)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
+if __name__ == "__main__":
+    main()
