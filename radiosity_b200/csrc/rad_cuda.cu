@@ -90,7 +90,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(D.F, (size_t)D.k * Pm)); A(dalloc(D.dB, 3 * Pm));
 	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.ctl, 1));
 	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap));
-	A(dalloc(D.ework, Pm < 64 ? (size_t)64 : Pm)); A(dalloc(D.topkey, (size_t)D.k)); A(dalloc(proj, 16));
+	A(dalloc(D.ework, Pm < 64 ? (size_t)64 : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * 64)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * 64)); A(dalloc(proj, 16));
 	#undef A
 	if (!ok) {
 		g_create_err = std::string("rad_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -104,7 +104,6 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	cudaMemsetAsync(D.dB, 0, 3 * Pm * 4, c->stream);
 	cudaMemsetAsync(D.em, 0, (size_t)D.k * sizeof(RadEmitter), c->stream);
 	cudaMemsetAsync(D.ctl, 0, sizeof(RadControl), c->stream);
-	cudaMemsetAsync(D.topkey, 0, (size_t)D.k * 8, c->stream);
 	if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete c; return RAD_E_CUDA; }
 	*out = c;
 	return RAD_OK;
@@ -124,7 +123,7 @@ int rad_destroy(rad_ctx* c) {
 	cudaFree((void*)D.v0); cudaFree((void*)D.v1); cudaFree((void*)D.v2); cudaFree((void*)D.color);
 	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
 	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.ctl);
-	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.ework); cudaFree(D.topkey); cudaFree((void*)D.proj);
+	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->saved) cudaFree(c->saved);
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);

@@ -60,8 +60,8 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	RadControl* ctl;
 	RadBigTri* q_tri; RadQueueEntry* q_ent;
 	uint32_t q_tri_cap, q_ent_cap;
-	uint32_t* ework;              // [P] scratch energies for top-k rounds
-	unsigned long long* topkey;   // [k] winners of the top-k rounds
+	uint32_t* ework;              // [max(P,64)] scratch (emitter id staging)
+	unsigned long long* cand0; unsigned long long* cand1;   // top-k tournament candidates, ceil(P/2048)*64 keys each
 	const float* proj;            // [16]
 };
 

@@ -12,8 +12,8 @@
 // reference's k == 1 result exactly (largest energy, LAST index among equals, patch 0 if all zero).
 //
 // For k > 1: RAD_SELECT_REFERENCE runs a one-block emulation of the reference's list (seeded patch 0,
-// reject-below-minimum while not full, tie groups reversed by every insertion); RAD_SELECT_TOPK runs k
-// argmax rounds with exclusion, key = (bits << 32 | ~id): energy desc, id asc.
+// reject-below-minimum while not full, tie groups reversed by every insertion); RAD_SELECT_TOPK runs a
+// tournament of block-wide bitonic sorts over keys (bits << 32 | ~id): energy desc, id asc.
 #include "rad_internal.cuh"
 
 namespace {
@@ -122,39 +122,46 @@ __global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
 	}
 }
 
-// ---- clean top-k for k > 1: k argmax rounds with exclusion ----------------------------------
-__global__ void __launch_bounds__(256) topk_round_kernel(RadDev D, int r) {
-	if (blockIdx.x == 0 && threadIdx.x == 0 && r + 1 < (int)D.k) D.topkey[r + 1] = 0ull;
-	uint32_t excl = 0xFFFFFFFFu;
-	if (r > 0) {
-		const unsigned long long pk = D.topkey[r - 1];
-		if (pk == 0ull) return;                       // fewer than r patches carry energy
-		excl = 0xFFFFFFFFu - (uint32_t)(pk & 0xFFFFFFFFull);
-	}
-	unsigned long long best = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.P; i += gridDim.x * blockDim.x) {
-		uint32_t eb;
-		if (r == 0) { eb = __float_as_uint(len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i])); D.ework[i] = eb; }
-		else {
-			eb = D.ework[i];
-			if (i == excl) { eb = 0; D.ework[i] = 0; }
+// ---- clean top-k for k > 1: tournament of block-wide bitonic sorts -----------------------------
+// key = (bits(|B|^2) << 32 | ~id): unique, and descending key order == (energy desc, id asc).  Every block sorts a
+// chunk of 2048 keys in shared memory and keeps its best 64; levels repeat (P -> P/32 -> ...) until one block is
+// left, which writes the emitter list.  Exact and deterministic; 2 launches for 16 k patches, 3 for 1 M.
+constexpr int kTopChunk = 2048, kTopKeep = 64, kTopThreads = 256;
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const unsigned long long* __restrict__ in, uint32_t n_in,
+                                                                  unsigned long long* __restrict__ out, int final_level) {
+	__shared__ unsigned long long s[kTopChunk];
+	const uint32_t base = blockIdx.x * kTopChunk;
+	for (int t = threadIdx.x; t < kTopChunk; t += kTopThreads) {
+		const uint32_t i = base + t;
+		unsigned long long key = 0ull;
+		if (i < n_in) {
+			if (FIRST) {
+				const uint32_t eb = __float_as_uint(len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i]));
+				if (eb != 0 && eb < 0x7F800000u) key = ((unsigned long long)eb << 32) | (0xFFFFFFFFu - i);
+			} else key = in[i];
 		}
-		if (eb != 0 && eb < 0x7F800000u) best = max(best, ((unsigned long long)eb << 32) | (0xFFFFFFFFu - i));
-	}
-	best = block_max(best);
-	if (threadIdx.x == 0 && best) atomicMax(&D.topkey[r], best);
-}
-__global__ void topk_finalize_kernel(RadDev D) {
-	const uint32_t h = threadIdx.x;
-	if (h < D.k) {
-		const unsigned long long key = D.topkey[h];
-		bool ok = key != 0ull;
-		for (uint32_t j = 0; j < h && ok; j++) ok = D.topkey[j] != 0ull;   // an exhausted round ends the list
-		D.em[h].id = ok ? 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull) : 0u;
-		D.em[h].valid = ok ? 1u : 0u;
+		s[t] = key;
 	}
 	__syncthreads();
-	if (h == 0) D.topkey[0] = 0ull;
+	for (int k = 2; k <= kTopChunk; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int t = threadIdx.x; t < kTopChunk / 2; t += kTopThreads) {
+				const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
+				const unsigned long long a = s[i], b = s[l];
+				const bool desc = (i & k) == 0;
+				if ((a < b) == desc) { s[i] = b; s[l] = a; }
+			}
+			__syncthreads();
+		}
+	if (final_level) {
+		if (threadIdx.x < D.k) {
+			const unsigned long long key = s[threadIdx.x];
+			D.em[threadIdx.x].id = key ? 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull) : 0u;
+			D.em[threadIdx.x].valid = key ? 1u : 0u;
+		}
+	} else if (threadIdx.x < kTopKeep) out[(size_t)blockIdx.x * kTopKeep + threadIdx.x] = s[threadIdx.x];
 }
 
 __global__ void set_emitters_kernel(RadDev D, const uint32_t* __restrict__ ids, uint32_t n) {
@@ -254,9 +261,19 @@ void rad_launch_select(rad_ctx* c) {
 		select_reference_kernel<<<1, 1024, 0, c->stream>>>(D);
 		c->launches++;
 	} else {
-		for (uint32_t r = 0; r < D.k; r++) topk_round_kernel<<<patch_grid(D.P, 256), 256, 0, c->stream>>>(D, (int)r);
-		topk_finalize_kernel<<<1, 64, 0, c->stream>>>(D);
-		c->launches += D.k + 1;
+		uint32_t n = D.P;
+		const unsigned long long* in = nullptr;
+		unsigned long long* out = D.cand0;
+		bool first = true;
+		for (;;) {
+			const uint32_t nb = (n + kTopChunk - 1) / kTopChunk;
+			const int fin = nb == 1;
+			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, fin);
+			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, fin);
+			c->launches++;
+			if (fin) break;
+			n = nb * kTopKeep; in = out; out = out == D.cand0 ? D.cand1 : D.cand0; first = false;
+		}
 	}
 	rad_launch_camera(c);
 }

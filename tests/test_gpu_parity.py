@@ -230,7 +230,8 @@ def test_shoot_run_to_run_and_restore(api, orc, box):
     ctx.restore_state()
     ctx.shoot(64)
     r2, i2 = ctx.download_state()
-    assert rel_l2(r1, r2) < 1e-6 and (i1 == i2).all()      # float atomics reorder sums; emitters' I is exact
+    # float atomics reorder the F sums, so B and I (I += snapshot of B) agree to rounding, not bit for bit
+    assert rel_l2(r1, r2) < 1e-6 and rel_l2(i1, i2) < 1e-6
     ctx.close()
 
 
