@@ -753,7 +753,8 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 	formfactors(N, k, ff.data());
 	std::vector<uint64_t> keys(RES);
 	std::vector<uint32_t> atlas((size_t)RES * k);
-	std::vector<float> F(P, 0.0f);
+	std::vector<float> F(P, 0.0f), Fall;
+	if (threads > 1 && k > 1 && !via_codec) Fall.assign((size_t)P * k, 0.0f);
 	std::vector<unsigned> em(k); std::vector<int> isnull(k);
 	std::vector<V3> snap_rad(k);
 	Codec codec; codec_setup(codec, P);
@@ -765,13 +766,23 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 	for (unsigned shoot = 0; shoot < n_batches; shoot++) {
 		orc_select(P, rad3, k, select_mode, em.data(), isnull.data());                                    // S1
 		std::fill(atlas.begin(), atlas.end(), 0u);                                                        // glClear
-		for (unsigned hi = 0; hi < k; hi++) {                                                             // S2
+		for (unsigned hi = 0; hi < k; hi++) {                                                             // S2 (snapshots)
 			if (schedule) schedule[(size_t)shoot * k + hi] = isnull[hi] ? 0xFFFFFFFFu : em[hi];
+			if (!isnull[hi]) snap_rad[hi] = v3(rad3[3 * em[hi]], rad3[3 * em[hi] + 1], rad3[3 * em[hi] + 2]);
+		}
+		// the k hemicubes of a batch are independent given the snapshots (Main.cpp:1155-1198): with several host
+		// threads each thread renders whole hemicubes; with k == 1 the threads split the patches of the one hemicube
+		const bool par_hemi = threads > 1 && k > 1;
+		#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (par_hemi)
+		for (int hi = 0; hi < (int)k; hi++) {
 			if (isnull[hi]) continue;
-			snap_rad[hi] = v3(rad3[3 * em[hi]], rad3[3 * em[hi] + 1], rad3[3 * em[hi] + 2]);
-			render_hemicube_keys(P, verts, em[hi], (int)N, keys.data(), threads);
+			std::vector<uint64_t> local;
+			uint64_t* kk = keys.data();
+			if (par_hemi) { local.resize(RES); kk = local.data(); }
+			render_hemicube_keys(P, verts, em[hi], (int)N, kk, par_hemi ? 1 : threads);
 			uint32_t* a = atlas.data() + (size_t)RES * hi;
-			for (unsigned i = 0; i < RES; i++) a[i] = keys[i] == kClearKey ? 0u : (uint32_t)(keys[i] & 0xFFFFFFFFu);
+			for (unsigned i = 0; i < RES; i++) a[i] = kk[i] == kClearKey ? 0u : (uint32_t)(kk[i] & 0xFFFFFFFFu);
+			if (!via_codec && par_hemi) process_hemicube_ids(a, ff.data(), W, H, wx, P, Fall.data() + (size_t)P * hi);
 		}
 		unsigned nrec = 0;
 		if (via_codec) {
@@ -780,15 +791,17 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 		}
 		for (unsigned hi = 0; hi < k; hi++) {                                                             // S3 + S4
 			if (isnull[hi]) continue;
+			float* Fh = F.data();
 			if (via_codec) orc_gather_records(P, nrec, rec_h.data(), rec_i.data(), rec_e.data(), hi, F.data());
+			else if (par_hemi) Fh = Fall.data() + (size_t)P * hi;
 			else process_hemicube_ids(atlas.data() + (size_t)RES * hi, ff.data(), W, H, wx, P, F.data());
 			V3 ec = v3(color3[3 * em[hi]], color3[3 * em[hi] + 1], color3[3 * em[hi] + 2]);
 			for (unsigned i = 0; i < P; i++) {
 				// p->radiosity += p_tmp_radiosities[hi] * p_tmp_formfactors[i] * p->getReflectivity() * p_emitters[hi]->getColor();
-				V3 d = mulv(mulf(mulf(snap_rad[hi], F[i]), reflectivity), ec);
+				V3 d = mulv(mulf(mulf(snap_rad[hi], Fh[i]), reflectivity), ec);
 				rad3[3 * i] += d.x; rad3[3 * i + 1] += d.y; rad3[3 * i + 2] += d.z;
 			}
-			std::fill(F.begin(), F.end(), 0.0f);
+			std::fill(Fh, Fh + P, 0.0f);
 		}
 		V3 last = v3(0, 0, 0);                                                                            // S5
 		for (unsigned hi = 0; hi < k; hi++) {

@@ -10,8 +10,8 @@
 
 #define RAD_NFACES 5
 #define RAD_CLEAR_KEY 0xFFFFFFFFFFFFFFFFull
-#define RAD_TILE 64               // big-triangle tile edge in pixels
-#define RAD_BIG_AREA 4096         // bbox area (px) above which a triangle goes through the tile queue
+#define RAD_TILE 32               // big-triangle tile edge in pixels
+#define RAD_BIG_AREA 256          // bbox area (px) above which a triangle goes through the tile queue (load balance)
 #define RAD_INLINE_AREA 32        // bbox area (px) up to which the owning lane rasterises alone
 
 struct RadBigTri {                // one screen-space triangle parked for tile processing (64 B)

@@ -9,7 +9,7 @@
 //                        8-bit sub-pixel snap, back-face cull, scissored bbox; then three tiers:
 //                          tiny  bbox  -> the owning lane walks it alone
 //                          medium bbox -> the warp walks it cooperatively in 8x4 pixel blocks
-//                          big   bbox  -> parked in the tile queue (64x64 pixel tiles)
+//                          big   bbox  -> parked in the tile queue (32x32 pixel tiles)
 //   raster_tiles_kernel  persistent warps drain the tile queue
 //   resolve_kernel       64-bit keys -> uint32 item buffer (id+1), keys reset for the next batch
 // Visibility is a deterministic 64-bit atomicMin of (depth24 << 32 | id+1) per pixel: equal to GL_LESS
@@ -385,7 +385,7 @@ void rad_launch_raster_setup_only(rad_ctx* c) {
 
 void rad_launch_raster_tiles_only(rad_ctx* c) {
 	if (c->d.h1 == c->d.h0) return;
-	raster_tiles_kernel<<<148 * 4, 128, 0, c->stream>>>(c->d);
+	raster_tiles_kernel<<<148 * 8, 128, 0, c->stream>>>(c->d);
 	c->launches++;
 }
 

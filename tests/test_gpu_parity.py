@@ -191,14 +191,32 @@ def test_shoot_config1_vs_oracle(api, orc, box, k, batches, mode):
     """BASELINE config 1: built-in box, area 0.5 (P = 502), hemicube 128, 100 shots."""
     v, c, r, il = box
     N = 128
+    orad, oillum, sched, done, last = orc.shoot(v, c, r, il, N, k, batches, select_mode=mode)
     ctx = make_ctx(api, orc, box, N, k=k, select_mode=mode)
+    # (a) the SAME schedule (the oracle's emitter lists) through the staged S2..S6 calls: 1e-3 is north_star's bar,
+    #     1e-5 is what the implementation achieves (only the float summation order inside F differs)
+    for b in range(batches):
+        ctx.set_emitters([int(x) for x in sched[b] if x != 0xFFFFFFFF])
+        ctx.render(); ctx.process()
+        dev_last = ctx.apply()
+    rad, illum = ctx.download_state()
+    assert rel_l2(rad, orad) < 1e-3 and rel_l2(illum, oillum) < 1e-3
+    assert rel_l2(rad, orad) < 1e-5 and rel_l2(illum, oillum) < 1e-5
+    assert abs(dev_last - last) <= 1e-4 * max(1.0, last)
+    # (b) the free-running device loop (own selection every batch).  With k == 1 a near-tie can only swap two
+    #     consecutive shots; with k > 1 the reference's list semantics amplify last-bit differences of |B|^2 into a
+    #     different batch membership (the reference itself is not run-to-run reproducible there, SURVEY.md App. B),
+    #     so only the energy bookkeeping is compared.
+    ctx.upload_state(r, il)
     st = ctx.shoot(batches)
     assert st.batches_done == batches and st.queue_overflow == 0 and st.kernel_launches > 0
-    rad, illum = ctx.download_state()
-    orad, oillum, sched, done, last = orc.shoot(v, c, r, il, N, k, batches, select_mode=mode)
-    assert rel_l2(rad, orad) < 1e-3 and rel_l2(illum, oillum) < 1e-3          # tolerance stated by north_star
-    assert rel_l2(rad, orad) < 1e-5                                           # what the implementation actually achieves
-    assert abs(st.last_energy_len - last) <= 1e-4 * max(1.0, last)
+    rad2, illum2 = ctx.download_state()
+    if k == 1:
+        assert rel_l2(rad2, orad) < 1e-3 and rel_l2(illum2, oillum) < 1e-3
+        assert abs(st.last_energy_len - last) <= 1e-4 * max(1.0, last)
+    else:
+        tot, otot = float(rad2.sum(dtype=np.float64) + illum2.sum(dtype=np.float64)), float(orad.sum(dtype=np.float64) + oillum.sum(dtype=np.float64))
+        assert abs(tot - otot) < 0.02 * otot
     ctx.close()
 
 
