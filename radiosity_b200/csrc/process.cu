@@ -5,8 +5,9 @@
 //   F_h[i] = sum over atlas pixels px of hemicube h with item[px] == i+1 of dFF[px]
 //
 // The reference expresses this as run-length records appended through an atomic counter and
-// finished on the CPU.  Here every warp streams 32 consecutive pixels per step (coalesced 128 B of
-// ids + 128 B of dFF), collapses runs of equal ids with a 5-step segmented shuffle reduction
+// finished on the CPU.  Here every warp streams 128 consecutive pixels per step (one 16 B load of ids +
+// one 16 B load of dFF per lane), merges runs inside the lane, collapses runs of equal ids across lanes
+// with a 5-step segmented shuffle reduction
 // (ids are spatially coherent, so a run is almost always a contiguous lane range) and issues ONE
 // red.global.add.f32 per run straight into F_h — no record stream, no host round trip.
 // Algorithmic traffic: 4 B id + 4 B dFF per pixel (the dFF table of one hemicube is shared by all k
@@ -21,7 +22,7 @@
 namespace {
 
 #define FULL 0xFFFFFFFFu
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 2;
 
 __device__ __forceinline__ void segmented_add(uint32_t id, float v, int lane, float* __restrict__ F, uint32_t P) {
 	const uint32_t prev = __shfl_up_sync(FULL, id, 1);
@@ -36,6 +37,22 @@ __device__ __forceinline__ void segmented_add(uint32_t id, float v, int lane, fl
 	if (head && id != 0 && id - 1 < P) atomicAdd(F + (id - 1), v);   // RED.E.ADD.F32 (result unused)
 }
 
+__device__ __forceinline__ void flush_run(uint32_t id, float v, float* __restrict__ F, uint32_t P) {
+	if (id != 0 && id - 1 < P) atomicAdd(F + (id - 1), v);
+}
+
+// four consecutive pixels per lane: runs that end inside the lane are flushed by the lane itself, the lane's last run
+// joins the warp-wide segmented reduction (equal ids in neighbouring lanes collapse into one atomic)
+__device__ __forceinline__ void process4(const uint4 id, const float4 f, int lane, float* __restrict__ F, uint32_t P) {
+	uint32_t cur = id.x; float acc = f.x;
+	if (id.y == cur) acc += f.y; else { flush_run(cur, acc, F, P); cur = id.y; acc = f.y; }
+	if (id.z == cur) acc += f.z; else { flush_run(cur, acc, F, P); cur = id.z; acc = f.z; }
+	if (id.w == cur) acc += f.w; else { flush_run(cur, acc, F, P); cur = id.w; acc = f.w; }
+	segmented_add(cur, acc, lane, F, P);
+}
+
+__device__ __forceinline__ uint32_t key_id(unsigned long long k) { return k == RAD_CLEAR_KEY ? 0u : (uint32_t)(k & 0xFFFFFFFFull); }
+
 template <bool FROM_KEYS>
 __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) {
 	const uint32_t slot = D.h0 + blockIdx.y;
@@ -43,39 +60,40 @@ __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) 
 	if (!D.em[slot].valid) return;
 	const int lane = threadIdx.x & 31;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-	const uint32_t ngroups = D.RES >> 5;              // RES is a multiple of 32 (N % 16 == 0)
+	const uint32_t nsteps = D.RES >> 7;               // 128 pixels per warp step; RES = 3 N^2 is a multiple of 768
 	float* __restrict__ F = D.F + (size_t)slot * D.P;
-	const float* __restrict__ ff = D.ff;
-	unsigned long long* __restrict__ keys = D.keys + (size_t)slot * D.RES;
-	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
+	const float4* __restrict__ ff4 = reinterpret_cast<const float4*>(D.ff);
+	ulonglong2* __restrict__ keys2 = reinterpret_cast<ulonglong2*>(D.keys + (size_t)slot * D.RES);
+	uint4* __restrict__ items4 = reinterpret_cast<uint4*>(D.items + (size_t)slot * D.RES);
 
-	for (uint32_t g0 = gw * kUnroll; g0 < ngroups; g0 += nw * kUnroll) {
-		uint32_t id[kUnroll]; float v[kUnroll];
+	for (uint32_t g0 = gw * kUnroll; g0 < nsteps; g0 += nw * kUnroll) {
+		uint4 id[kUnroll]; float4 v[kUnroll];
 		#pragma unroll
 		for (int u = 0; u < kUnroll; u++) {
 			const uint32_t g = g0 + u;
-			id[u] = 0; v[u] = 0.0f;
-			if (g < ngroups) {
-				const uint32_t i = (g << 5) + lane;
+			id[u] = make_uint4(0u, 0u, 0u, 0u); v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (g < nsteps) {
+				const uint32_t q = (g << 5) + lane;   // index of this lane's 4-pixel group
 				if (FROM_KEYS) {
-					const unsigned long long k = keys[i];
-					id[u] = k == RAD_CLEAR_KEY ? 0u : (uint32_t)(k & 0xFFFFFFFFull);
+					const ulonglong2 k0 = keys2[2 * (size_t)q], k1 = keys2[2 * (size_t)q + 1];
+					id[u] = make_uint4(key_id(k0.x), key_id(k0.y), key_id(k1.x), key_id(k1.y));
 				} else {
-					id[u] = __ldcs(items + i);
+					id[u] = __ldcs(items4 + q);
 				}
-				v[u] = __ldg(ff + i);
+				v[u] = __ldg(ff4 + q);
 			}
 		}
 		#pragma unroll
 		for (int u = 0; u < kUnroll; u++) {
 			const uint32_t g = g0 + u;
-			if (g < ngroups) {
-				const uint32_t i = (g << 5) + lane;
+			if (g < nsteps) {
+				const uint32_t q = (g << 5) + lane;
 				if (FROM_KEYS) {
-					keys[i] = RAD_CLEAR_KEY;
-					if (keep_items) items[i] = id[u];
+					const ulonglong2 clr = make_ulonglong2(RAD_CLEAR_KEY, RAD_CLEAR_KEY);
+					keys2[2 * (size_t)q] = clr; keys2[2 * (size_t)q + 1] = clr;
+					if (keep_items) items4[q] = id[u];
 				}
-				segmented_add(id[u], v[u], lane, F, D.P);
+				process4(id[u], v[u], lane, F, D.P);
 			}
 		}
 	}
@@ -85,7 +103,7 @@ __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) 
 
 static dim3 process_grid(const RadDev& D) {
 	const uint32_t nslots = D.h1 - D.h0;
-	const uint32_t groups = D.RES >> 5;
+	const uint32_t groups = D.RES >> 7;
 	uint32_t warps = (groups + kUnroll - 1) / kUnroll;
 	uint32_t bx = (warps + 7) / 8;
 	const uint32_t cap = 148 * 16;                    // a few waves of 256-thread CTAs per hemicube
