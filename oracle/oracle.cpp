@@ -330,7 +330,7 @@ static void atlas_rects(int N, Rect vp[5], Rect sc[5]) {
 //                  scenes and x/y are handled by the scissor (guard-band style).  New vertices are
 //                  always interpolated from the inside vertex towards the outside one, so two
 //                  triangles sharing a clipped edge get the identical vertex.
-//   viewport     : xw = x/w * (N/2) + (vx + N/2), zw = z/w * 0.5 + 0.5
+//   viewport     : iw = 1/w, xw = (x*iw) * (N/2) + (vx + N/2), zw = (z*iw) * 0.5 + 0.5
 //   snapping     : 8 sub-pixel bits, round to nearest even
 //   culling      : GL_CULL_FACE, back, front = CCW (Main.cpp:12) -> keep signed area > 0
 //   coverage     : pixel centres, exact integer edge functions, top-left rule on ties
@@ -380,7 +380,8 @@ static void raster_tri(const CV t[3], const Rect& vp, const Rect& sc, int W, uin
 	float hw = (float)vp.w * 0.5f, hh = (float)vp.h * 0.5f;
 	float ox = (float)vp.x + hw, oy = (float)vp.y + hh;
 	for (int i = 0; i < 3; i++) {
-		float xn = t[i].x / t[i].w, yn = t[i].y / t[i].w, zn = t[i].z / t[i].w;
+		float iw = 1.0f / t[i].w;                               // perspective divide: reciprocal, then multiply
+		float xn = t[i].x * iw, yn = t[i].y * iw, zn = t[i].z * iw;
 		X[i] = snap(xn * hw + ox);
 		Y[i] = snap(yn * hh + oy);
 		Z[i] = zn * 0.5f + 0.5f;

@@ -10,9 +10,8 @@
 
 #define RAD_NFACES 5
 #define RAD_CLEAR_KEY 0xFFFFFFFFFFFFFFFFull
-#define RAD_TILE 32               // big-triangle tile edge in pixels
-#define RAD_BIG_AREA 256          // bbox area (px) above which a triangle goes through the tile queue (load balance)
-#define RAD_INLINE_AREA 32        // bbox area (px) up to which the owning lane rasterises alone
+#define RAD_TILE 32               // chunk edge in pixels (chunks are bbox-relative)
+#define RAD_INLINE_AREA 32        // bbox area (px) up to which the owning lane rasterises alone; larger -> chunk queue
 
 struct RadBigTri {                // one screen-space triangle parked for tile processing (64 B)
 	int X0, Y0, X1, Y1, X2, Y2;   // snapped window coordinates, 8 sub-pixel bits

@@ -6,20 +6,20 @@
 // Pipeline per batch (all on the context's stream):
 //   camera_kernel        k x 5 lanes: radiosity snapshot, emitter colour, the five MVPs
 //   raster_setup_kernel  one lane per (patch[,face]): vertex transform, near-plane clip, viewport,
-//                        8-bit sub-pixel snap, back-face cull, scissored bbox; then three tiers:
-//                          tiny  bbox  -> the owning lane walks it alone
-//                          medium bbox -> the warp walks it cooperatively in 8x4 pixel blocks
-//                          big   bbox  -> parked in the tile queue (32x32 pixel tiles)
-//   raster_tiles_kernel  persistent warps drain the tile queue
+//                        8-bit sub-pixel snap, back-face cull, scissored bbox; then two tiers:
+//                          small bbox (<= 32 px) -> the owning lane walks it alone
+//                          anything larger       -> parked in the chunk queue (bbox-relative 32x32 pixel chunks,
+//                                                   queue slots claimed with one atomic per warp)
+//   raster_chunks_kernel persistent warps drain the chunk queue, one warp per chunk, 8x4 pixels per step
 //   resolve_kernel       64-bit keys -> uint32 item buffer (id+1), keys reset for the next batch
 // Visibility is a deterministic 64-bit atomicMin of (depth24 << 32 | id+1) per pixel: equal to GL_LESS
 // with patches drawn in id order (Main.cpp:715-720), independent of thread scheduling.
 //
 // Raster rules (identical, operation for operation, to oracle/oracle.cpp): clip = MVP*(p,1) with
 // row r = ((m0r*x + m1r*y) + m2r*z) + m3r; near clip z+w>=0 with new vertices interpolated from the
-// inside vertex; xw = x/w*(N/2) + (vx+N/2); RNE snap to 1/256 px; keep signed area > 0 (CCW front,
+// inside vertex; iw = 1/w, xw = (x*iw)*(N/2) + (vx+N/2); RNE snap to 1/256 px; keep signed area > 0 (CCW front,
 // GL_CULL_FACE back); pixel centres, exact int64 edge functions, top-left tie rule; depth =
-// barycentric interpolation of z/w*0.5+0.5, RNE-quantised to 24 bit, d >= 0xFFFFFF fails (LESS vs 1.0).
+// barycentric interpolation of (z*iw)*0.5+0.5, RNE-quantised to 24 bit, d >= 0xFFFFFF fails (LESS vs 1.0).
 #include "rad_internal.cuh"
 
 namespace {
@@ -139,8 +139,10 @@ struct Tri {                 // screen-space triangle ready for coverage
 	int bx;                  // px0 | px1 << 16
 	int by;                  // py0 | py1 << 16
 };
+struct PV { int X, Y; float Z; };   // projected, snapped vertex
 
-// coverage + depth + visibility for one pixel
+// coverage + depth + visibility for one pixel.  The atomicMin is fire-and-forget (RED.MIN.64): nothing in the
+// pixel loop waits on memory.
 __device__ __forceinline__ void shade_pixel(const Tri& t, int b0, int b1, int b2, int px, int py, uint32_t id1,
                                             unsigned long long* __restrict__ keys, uint32_t W) {
 	int cx = px * 256 + 128, cy = py * 256 + 128;
@@ -153,57 +155,82 @@ __device__ __forceinline__ void shade_pixel(const Tri& t, int b0, int b1, int b2
 	z = fminf(fmaxf(z, 0.0f), 1.0f);
 	uint32_t dq = __float2uint_rn(z * 16777215.0f);
 	if (dq >= 0xFFFFFFu) return;
-	unsigned long long key = ((unsigned long long)dq << 32) | id1;
-	unsigned long long* a = keys + (size_t)py * W + px;
-	if (key < __ldcg(a)) atomicMin(a, key);   // the stale read only skips atomics that cannot win
+	atomicMin(keys + (size_t)py * W + px, ((unsigned long long)dq << 32) | id1);
 }
 
-// project + snap + cull + bbox.  Returns bbox area in pixels (0 = nothing to draw).
-__device__ __forceinline__ int setup_tri(const CV& a, const CV& b, const CV& c, int vpx, int vpy, int N,
-                                         int scx, int scy, int scw, int sch, Tri& t) {
-	// exact trivial reject (w > 0 after the near clip): wholly beyond one viewport edge
-	if ((a.x > a.w && b.x > b.w && c.x > c.w) || (a.x < -a.w && b.x < -b.w && c.x < -c.w) ||
-	    (a.y > a.w && b.y > b.w && c.y > c.w) || (a.y < -a.w && b.y < -b.w && c.y < -c.w)) return 0;
-	float hw = (float)N * 0.5f;
-	float ox = (float)vpx + hw, oy = (float)vpy + hw;
-	t.X0 = snap256((a.x / a.w) * hw + ox); t.Y0 = snap256((a.y / a.w) * hw + oy);
-	t.X1 = snap256((b.x / b.w) * hw + ox); t.Y1 = snap256((b.y / b.w) * hw + oy);
-	t.X2 = snap256((c.x / c.w) * hw + ox); t.Y2 = snap256((c.y / c.w) * hw + oy);
-	long long area2 = edge_fn(t.X0, t.Y0, t.X1, t.Y1, t.X2, t.Y2);
-	if (area2 <= 0) return 0;
-	int minx = min(t.X0, min(t.X1, t.X2)), maxx = max(t.X0, max(t.X1, t.X2));
-	int miny = min(t.Y0, min(t.Y1, t.Y2)), maxy = max(t.Y0, max(t.Y1, t.Y2));
-	int px0 = max((minx - 128 + 255) >> 8, scx), px1 = min((maxx - 128) >> 8, scx + scw - 1);
-	int py0 = max((miny - 128 + 255) >> 8, scy), py1 = min((maxy - 128) >> 8, scy + sch - 1);
+// perspective divide (reciprocal, then multiply), viewport, 8-bit sub-pixel snap
+__device__ __forceinline__ PV project(const CV& c, float hw, float ox, float oy) {
+	const float iw = 1.0f / c.w;
+	PV p;
+	p.X = snap256((c.x * iw) * hw + ox);
+	p.Y = snap256((c.y * iw) * hw + oy);
+	p.Z = (c.z * iw) * 0.5f + 0.5f;
+	return p;
+}
+
+// cull + scissored bbox + depth plane.  Returns the bbox area in pixels (0 = nothing to draw).
+__device__ __forceinline__ int setup_tri(const PV& a, const PV& b, const PV& c, int scx, int scy, int scw, int sch, Tri& t) {
+	const long long area2 = edge_fn(a.X, a.Y, b.X, b.Y, c.X, c.Y);
+	if (area2 <= 0) return 0;                    // back-facing (CW in window space) or degenerate
+	const int minx = min(a.X, min(b.X, c.X)), maxx = max(a.X, max(b.X, c.X));
+	const int miny = min(a.Y, min(b.Y, c.Y)), maxy = max(a.Y, max(b.Y, c.Y));
+	const int px0 = max((minx - 128 + 255) >> 8, scx), px1 = min((maxx - 128) >> 8, scx + scw - 1);
+	const int py0 = max((miny - 128 + 255) >> 8, scy), py1 = min((maxy - 128) >> 8, scy + sch - 1);
 	if (px0 > px1 || py0 > py1) return 0;
-	float za = (a.z / a.w) * 0.5f + 0.5f, zb = (b.z / b.w) * 0.5f + 0.5f, zc = (c.z / c.w) * 0.5f + 0.5f;
-	t.z0 = za; t.dz1 = zb - za; t.dz2 = zc - za;
+	t.X0 = a.X; t.Y0 = a.Y; t.X1 = b.X; t.Y1 = b.Y; t.X2 = c.X; t.Y2 = c.Y;
+	t.z0 = a.Z; t.dz1 = b.Z - a.Z; t.dz2 = c.Z - a.Z;
 	t.inv_area = 1.0f / (float)area2;
 	t.bx = px0 | (px1 << 16); t.by = py0 | (py1 << 16);
 	return (px1 - px0 + 1) * (py1 - py0 + 1);
 }
 
-__device__ __forceinline__ void park_big(const RadDev& D, const Tri& t, uint32_t id1, uint32_t slot) {
-	uint32_t ti = atomicAdd(&D.ctl->q_tris, 1u);
-	if (ti >= D.q_tri_cap) { D.ctl->q_overflow = 1; return; }
+#define FULL 0xFFFFFFFFu
+
+// One triangle per lane (area == 0: none).  Small bboxes are walked by the owning lane; everything else is parked
+// in the chunk queue — bbox-relative chunks of RAD_TILE x RAD_TILE pixels, one warp each in raster_chunks_kernel —
+// so that no warp of the set-up kernel ever carries a long pixel loop (load balance).  Queue slots are claimed
+// with one atomic per warp.
+__device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
+                                         unsigned long long* __restrict__ keys) {
+	if (area > 0 && area <= RAD_INLINE_AREA) {
+		const int b0 = edge_bias(tr.X1, tr.Y1, tr.X2, tr.Y2), b1 = edge_bias(tr.X2, tr.Y2, tr.X0, tr.Y0), b2 = edge_bias(tr.X0, tr.Y0, tr.X1, tr.Y1);
+		const int px0 = tr.bx & 0xFFFF, px1 = tr.bx >> 16, py0 = tr.by & 0xFFFF, py1 = tr.by >> 16;
+		for (int py = py0; py <= py1; py++)
+			for (int px = px0; px <= px1; px++)
+				shade_pixel(tr, b0, b1, b2, px, py, id1, keys, D.W);
+	}
+	const bool big = area > RAD_INLINE_AREA;
+	const unsigned mb = __ballot_sync(FULL, big);
+	if (mb == 0) return;
+	int ncx = 0, ncy = 0, nent = 0;
+	if (big) {
+		ncx = ((tr.bx >> 16) - (tr.bx & 0xFFFF)) / RAD_TILE + 1;
+		ncy = ((tr.by >> 16) - (tr.by & 0xFFFF)) / RAD_TILE + 1;
+		nent = ncx * ncy;
+	}
+	int pre = nent;                               // inclusive warp scan of the entry counts
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += o; }
+	const int total = __shfl_sync(FULL, pre, 31);
+	uint32_t tbase = 0, ebase = 0;
+	if (lane == 0) { tbase = atomicAdd(&D.ctl->q_tris, (uint32_t)__popc(mb)); ebase = atomicAdd(&D.ctl->q_entries, (uint32_t)total); }
+	tbase = __shfl_sync(FULL, tbase, 0); ebase = __shfl_sync(FULL, ebase, 0);
+	if (!big) return;
+	const uint32_t ti = tbase + __popc(mb & ((1u << lane) - 1u));
+	uint32_t e = ebase + (uint32_t)(pre - nent);
+	if (ti >= D.q_tri_cap || e + nent > D.q_ent_cap) { D.ctl->q_overflow = 1; return; }
 	RadBigTri r;
-	r.X0 = t.X0; r.Y0 = t.Y0; r.X1 = t.X1; r.Y1 = t.Y1; r.X2 = t.X2; r.Y2 = t.Y2;
-	r.z0 = t.z0; r.dz1 = t.dz1; r.dz2 = t.dz2; r.inv_area = t.inv_area;
+	r.X0 = tr.X0; r.Y0 = tr.Y0; r.X1 = tr.X1; r.Y1 = tr.Y1; r.X2 = tr.X2; r.Y2 = tr.Y2;
+	r.z0 = tr.z0; r.dz1 = tr.dz1; r.dz2 = tr.dz2; r.inv_area = tr.inv_area;
 	r.id1 = id1; r.slot = slot;
-	r.px0 = t.bx & 0xFFFF; r.px1 = t.bx >> 16; r.py0 = t.by & 0xFFFF; r.py1 = t.by >> 16;
+	r.px0 = tr.bx & 0xFFFF; r.px1 = tr.bx >> 16; r.py0 = tr.by & 0xFFFF; r.py1 = tr.by >> 16;
 	D.q_tri[ti] = r;
-	int tx0 = r.px0 / RAD_TILE, tx1 = r.px1 / RAD_TILE, ty0 = r.py0 / RAD_TILE, ty1 = r.py1 / RAD_TILE;
-	uint32_t n = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
-	uint32_t e = atomicAdd(&D.ctl->q_entries, n);
-	if (e + n > D.q_ent_cap) { D.ctl->q_overflow = 1; return; }
-	for (int ty = ty0; ty <= ty1; ty++)
-		for (int tx = tx0; tx <= tx1; tx++) {
-			RadQueueEntry q; q.tri = ti; q.tx = (uint16_t)tx; q.ty = (uint16_t)ty;
+	for (int cy = 0; cy < ncy; cy++)
+		for (int cx = 0; cx < ncx; cx++) {
+			RadQueueEntry q; q.tri = ti; q.tx = (uint16_t)cx; q.ty = (uint16_t)cy;
 			D.q_ent[e++] = q;
 		}
 }
-
-#define FULL 0xFFFFFFFFu
 
 // grid: x = patch chunk, y = face (SPLIT) or 1, z = local hemicube slot
 template <bool SPLIT_FACES>
@@ -220,6 +247,7 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
 	const bool live = p < D.P;
 	const int lane = threadIdx.x & 31;
 	const int N = (int)D.N;
+	const float hw = (float)N * 0.5f;
 	unsigned long long* __restrict__ keys = D.keys + (size_t)slot * D.RES;
 	Quad q;
 	if (live) q = load_quad(D, p);
@@ -235,21 +263,40 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
 		case 3: vpx = N + N / 2; vpy = 0; scx = N + N / 2; scy = 0; scw = N / 2; sch = N; break;
 		default: vpx = N / 2; vpy = 0; scx = N / 2; scy = 0; scw = N; sch = N; break;
 		}
+		const float ox = (float)vpx + hw, oy = (float)vpy + hw;
 		CV c[4]; float dn[4]; int nin = 0;
 		if (live) {
 			c[0] = xform(s_mvp[f], q.a); c[1] = xform(s_mvp[f], q.b); c[2] = xform(s_mvp[f], q.c); c[3] = xform(s_mvp[f], q.d);
 			#pragma unroll
 			for (int i = 0; i < 4; i++) { dn[i] = c[i].z + c[i].w; nin += dn[i] >= 0.0f; }
+			// exact trivial reject of the whole quad (all four inside the near plane, so w > 0): wholly beyond one
+			// viewport edge means no snapped vertex can bring a pixel centre inside the scissor
+			if (nin == 4 && ((c[0].x > c[0].w && c[1].x > c[1].w && c[2].x > c[2].w && c[3].x > c[3].w) ||
+			                 (c[0].x < -c[0].w && c[1].x < -c[1].w && c[2].x < -c[2].w && c[3].x < -c[3].w) ||
+			                 (c[0].y > c[0].w && c[1].y > c[1].w && c[2].y > c[2].w && c[3].y > c[3].w) ||
+			                 (c[0].y < -c[0].w && c[1].y < -c[1].w && c[2].y < -c[2].w && c[3].y < -c[3].w))) nin = 0;
 		}
 		if (!__any_sync(FULL, nin > 0)) continue;
 
+		// common case: nothing crosses the near plane -> project the four vertices once
+		PV pv[4];
+		if (nin == 4) {
+			#pragma unroll
+			for (int i = 0; i < 4; i++) pv[i] = project(c[i], hw, ox, oy);
+		}
+		const bool any_clip = __any_sync(FULL, nin > 0 && nin < 4);
 		#pragma unroll
 		for (int t = 0; t < 2; t++) {          // triangles (0,1,2) and (0,2,3), ModelContainer.cpp:112-117
+			Tri tr; int area = 0;
+			if (nin == 4) area = setup_tri(pv[0], pv[t + 1], pv[t + 2], scx, scy, scw, sch, tr);
+			emit_tri(D, tr, area, id1, slot, lane, keys);
+			if (!any_clip) continue;
+			// rare: the triangle crosses the near plane (z + w >= 0).  New vertices are interpolated from the inside
+			// vertex; vertex order as produced by walking the edges 0-1, 1-2, 2-0.
 			CV p0, p1, p2, p3; int n = 0;
-			if (live && nin > 0) {
+			if (nin > 0 && nin < 4) {
 				const CV in0 = c[0], in1 = c[t + 1], in2 = c[t + 2];
 				const float d0 = dn[0], d1 = dn[t + 1], d2 = dn[t + 2];
-				// near-plane clip; vertex order as produced by walking the edges 0-1, 1-2, 2-0
 				switch ((d0 >= 0.0f ? 1 : 0) | (d1 >= 0.0f ? 2 : 0) | (d2 >= 0.0f ? 4 : 0)) {
 				case 7: p0 = in0; p1 = in1; p2 = in2; n = 3; break;
 				case 1: p0 = in0; p1 = clip_lerp(in0, in1, d0, d1); p2 = clip_lerp(in0, in2, d0, d2); n = 3; break;
@@ -263,47 +310,20 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
 			}
 			for (int sub = 0; sub < 2; sub++) {
 				if (!__any_sync(FULL, n >= 3 + sub)) break;
-				Tri tr; int area = 0;
-				if (n >= 3 + sub) area = setup_tri(p0, sub ? p2 : p1, sub ? p3 : p2, vpx, vpy, N, scx, scy, scw, sch, tr);
-				int b0 = 0, b1 = 0, b2 = 0;
-				if (area > 0) { b0 = edge_bias(tr.X1, tr.Y1, tr.X2, tr.Y2); b1 = edge_bias(tr.X2, tr.Y2, tr.X0, tr.Y0); b2 = edge_bias(tr.X0, tr.Y0, tr.X1, tr.Y1); }
-				// tier 1: tiny bbox, the owning lane walks it alone
-				if (area > 0 && area <= RAD_INLINE_AREA) {
-					const int px0 = tr.bx & 0xFFFF, px1 = tr.bx >> 16, py0 = tr.by & 0xFFFF, py1 = tr.by >> 16;
-					for (int py = py0; py <= py1; py++)
-						for (int px = px0; px <= px1; px++)
-							shade_pixel(tr, b0, b1, b2, px, py, id1, keys, D.W);
+				area = 0;
+				if (n >= 3 + sub) {
+					const PV a = project(p0, hw, ox, oy), b = project(sub ? p2 : p1, hw, ox, oy), cc = project(sub ? p3 : p2, hw, ox, oy);
+					area = setup_tri(a, b, cc, scx, scy, scw, sch, tr);
 				}
-				// tier 3: big bbox, parked for the tile pass
-				if (area > RAD_BIG_AREA) park_big(D, tr, id1, slot);
-				// tier 2: medium bbox, the warp walks it together in 8x4 blocks
-				unsigned m = __ballot_sync(FULL, area > RAD_INLINE_AREA && area <= RAD_BIG_AREA);
-				while (m) {
-					const int src = __ffs(m) - 1;
-					m &= m - 1;
-					Tri w;
-					w.X0 = __shfl_sync(FULL, tr.X0, src); w.Y0 = __shfl_sync(FULL, tr.Y0, src);
-					w.X1 = __shfl_sync(FULL, tr.X1, src); w.Y1 = __shfl_sync(FULL, tr.Y1, src);
-					w.X2 = __shfl_sync(FULL, tr.X2, src); w.Y2 = __shfl_sync(FULL, tr.Y2, src);
-					w.z0 = __shfl_sync(FULL, tr.z0, src); w.dz1 = __shfl_sync(FULL, tr.dz1, src);
-					w.dz2 = __shfl_sync(FULL, tr.dz2, src); w.inv_area = __shfl_sync(FULL, tr.inv_area, src);
-					w.bx = __shfl_sync(FULL, tr.bx, src); w.by = __shfl_sync(FULL, tr.by, src);
-					const uint32_t wid = __shfl_sync(FULL, id1, src);
-					const int wb0 = edge_bias(w.X1, w.Y1, w.X2, w.Y2), wb1 = edge_bias(w.X2, w.Y2, w.X0, w.Y0), wb2 = edge_bias(w.X0, w.Y0, w.X1, w.Y1);
-					const int px0 = w.bx & 0xFFFF, px1 = w.bx >> 16, py0 = w.by & 0xFFFF, py1 = w.by >> 16;
-					for (int by = py0; by <= py1; by += 4)
-						for (int bx = px0; bx <= px1; bx += 8) {
-							const int px = bx + (lane & 7), py = by + (lane >> 3);
-							if (px <= px1 && py <= py1) shade_pixel(w, wb0, wb1, wb2, px, py, wid, keys, D.W);
-						}
-				}
+				emit_tri(D, tr, area, id1, slot, lane, keys);
 			}
 		}
 	}
 }
 
-// persistent warps drain the (triangle, tile) queue
-__global__ void __launch_bounds__(128) raster_tiles_kernel(RadDev D) {
+// persistent warps drain the (triangle, chunk) queue: one warp per chunk of at most RAD_TILE x RAD_TILE pixels,
+// walked in 8x4 pixel blocks
+__global__ void __launch_bounds__(128) raster_chunks_kernel(RadDev D) {
 	const uint32_t nent = min(D.ctl->q_entries, D.q_ent_cap);
 	const int lane = threadIdx.x & 31;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -315,10 +335,10 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(RadDev D) {
 		w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
 		w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
 		const int b0 = edge_bias(w.X1, w.Y1, w.X2, w.Y2), b1 = edge_bias(w.X2, w.Y2, w.X0, w.Y0), b2 = edge_bias(w.X0, w.Y0, w.X1, w.Y1);
-		const int px0 = max(r.px0, (int)e.tx * RAD_TILE), px1 = min(r.px1, (int)e.tx * RAD_TILE + RAD_TILE - 1);
-		const int py0 = max(r.py0, (int)e.ty * RAD_TILE), py1 = min(r.py1, (int)e.ty * RAD_TILE + RAD_TILE - 1);
+		const int px0 = r.px0 + (int)e.tx * RAD_TILE, px1 = min(r.px1, px0 + RAD_TILE - 1);
+		const int py0 = r.py0 + (int)e.ty * RAD_TILE, py1 = min(r.py1, py0 + RAD_TILE - 1);
 		unsigned long long* __restrict__ keys = D.keys + (size_t)r.slot * D.RES;
-		// skip the tile when one edge has all four tile corners strictly outside (exact, conservative)
+		// skip the chunk when one edge has all four corner pixels strictly outside (exact, conservative)
 		{
 			const int cx0 = px0 * 256 + 128, cx1 = px1 * 256 + 128, cy0 = py0 * 256 + 128, cy1 = py1 * 256 + 128;
 			bool out = false;
@@ -385,7 +405,7 @@ void rad_launch_raster_setup_only(rad_ctx* c) {
 
 void rad_launch_raster_tiles_only(rad_ctx* c) {
 	if (c->d.h1 == c->d.h0) return;
-	raster_tiles_kernel<<<148 * 8, 128, 0, c->stream>>>(c->d);
+	raster_chunks_kernel<<<148 * 8, 128, 0, c->stream>>>(c->d);
 	c->launches++;
 }
 
