@@ -76,7 +76,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
 	D.P = 0; D.h0 = 0; D.h1 = D.k;
 	D.reflectivity = cfg->reflectivity;
-	D.q_tri_cap = 1u << 20; D.q_ent_cap = 1u << 22;
+	D.q_tri_cap = 1u << 22; D.q_ent_cap = 1u << 23;
 	const size_t Pm = cfg->max_patches;
 	float4 *v0, *v1, *v2; float *color, *ff, *proj;
 	bool ok = true;

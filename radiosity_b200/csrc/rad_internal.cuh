@@ -85,7 +85,7 @@ struct rad_ctx {
 
 // ---- launchers (each enqueues on ctx->stream and bumps ctx->launches) -------------------------
 void rad_launch_select(rad_ctx* c);                 // S1 + camera/snapshots (all modes)
-void rad_launch_camera(rad_ctx* c);                 // camera/snapshots only (emitters already set)
+void rad_launch_camera(rad_ctx* c, int sel_parity = -1);   // camera/snapshots (+ k==1: emitter from selkey[sel_parity])
 void rad_launch_raster(rad_ctx* c);                 // setup + inline/warp raster, then tile queue
 void rad_launch_raster_setup_only(rad_ctx* c);
 void rad_launch_raster_tiles_only(rad_ctx* c);

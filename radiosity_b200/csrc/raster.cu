@@ -85,20 +85,32 @@ __device__ void build_mvp(const Quad& q, int face, const float* __restrict__ pro
 	mat_product(out, proj, mv);     // t_projection * t_modelview (Main.cpp:1183)
 }
 
-// one block per hemicube slot: lanes 0..4 build the face matrices, lane 0 takes the snapshot
-__global__ void camera_kernel(RadDev D) {
-	uint32_t h = blockIdx.x;
-	RadEmitter e = D.em[h];
-	if (!e.valid || e.id >= D.P) return;
-	if (threadIdx.x < RAD_NFACES) {
-		Quad q = load_quad(D, e.id);
-		build_mvp(q, threadIdx.x, D.proj, D.mvp + ((size_t)h * RAD_NFACES + threadIdx.x) * 16);
-	}
+// one block per hemicube slot: lanes 0..4 build the face matrices, lane 0 takes the snapshot.
+// sel_parity >= 0 (k == 1 only): the emitter is first decoded from the fused argmax key selkey[sel_parity]
+// (all-zero energies leave key 0 == patch 0, the reference's seeded entry) and the other key is recycled.
+__global__ void camera_kernel(RadDev D, int sel_parity) {
+	__shared__ RadEmitter s_e;
+	const uint32_t h = blockIdx.x;
 	if (threadIdx.x == 0) {
-		for (int c = 0; c < 3; c++) {
-			D.em[h].S[c] = D.rad[(size_t)c * D.P + e.id];          // p_tmp_radiosities[hi] (Main.cpp:1161)
-			D.em[h].color[c] = D.color[(size_t)c * D.P + e.id];
+		RadEmitter e = D.em[h];
+		if (sel_parity >= 0) {
+			const unsigned long long key = D.ctl->selkey[sel_parity];
+			e.id = (uint32_t)(key & 0xFFFFFFFFull); e.valid = 1;
+			D.ctl->selkey[sel_parity ^ 1] = 0ull;
 		}
+		if (e.valid && e.id < D.P) {
+			for (int c = 0; c < 3; c++) {
+				e.S[c] = D.rad[(size_t)c * D.P + e.id];            // p_tmp_radiosities[hi] (Main.cpp:1161)
+				e.color[c] = D.color[(size_t)c * D.P + e.id];
+			}
+		} else e.valid = 0;
+		D.em[h] = e;
+		s_e = e;
+	}
+	__syncthreads();
+	if (s_e.valid && threadIdx.x < RAD_NFACES) {
+		Quad q = load_quad(D, s_e.id);
+		build_mvp(q, threadIdx.x, D.proj, D.mvp + ((size_t)h * RAD_NFACES + threadIdx.x) * 16);
 	}
 }
 
@@ -141,21 +153,32 @@ struct Tri {                 // screen-space triangle ready for coverage
 };
 struct PV { int X, Y; float Z; };   // projected, snapped vertex
 
-// coverage + depth + visibility for one pixel.  The atomicMin is fire-and-forget (RED.MIN.64): nothing in the
-// pixel loop waits on memory.
-__device__ __forceinline__ void shade_pixel(const Tri& t, int b0, int b1, int b2, int px, int py, uint32_t id1,
-                                            unsigned long long* __restrict__ keys, uint32_t W) {
-	int cx = px * 256 + 128, cy = py * 256 + 128;
-	long long e0 = edge_fn(t.X1, t.Y1, t.X2, t.Y2, cx, cy);
-	long long e1 = edge_fn(t.X2, t.Y2, t.X0, t.Y0, cx, cy);
-	long long e2 = edge_fn(t.X0, t.Y0, t.X1, t.Y1, cx, cy);
-	if (((e0 + b0) | (e1 + b1) | (e2 + b2)) < 0) return;
-	float l1 = (float)e1 * t.inv_area, l2 = (float)e2 * t.inv_area;
+// Edge functions are exact int64 and stepped incrementally; E[i] carries the top-left bias (0 / -1) so that
+// "inside" is (E0 | E1 | E2) >= 0.  Depth uses the unbiased values.  The atomicMin is fire-and-forget (RED.MIN.64):
+// nothing in a pixel loop waits on memory.
+struct EdgeSet {
+	long long e0, e1, e2;        // biased edge values at the current pixel centre
+	long long sx0, sx1, sx2;     // step for +1 pixel in x
+	long long sy0, sy1, sy2;     // step for +1 pixel in y
+	int b1, b2;
+};
+__device__ __forceinline__ void edges_at(const Tri& t, int px, int py, EdgeSet& E) {
+	const int cx = px * 256 + 128, cy = py * 256 + 128;
+	const int b0 = edge_bias(t.X1, t.Y1, t.X2, t.Y2);
+	E.b1 = edge_bias(t.X2, t.Y2, t.X0, t.Y0); E.b2 = edge_bias(t.X0, t.Y0, t.X1, t.Y1);
+	E.e0 = edge_fn(t.X1, t.Y1, t.X2, t.Y2, cx, cy) + b0;
+	E.e1 = edge_fn(t.X2, t.Y2, t.X0, t.Y0, cx, cy) + E.b1;
+	E.e2 = edge_fn(t.X0, t.Y0, t.X1, t.Y1, cx, cy) + E.b2;
+	E.sx0 = -(long long)(t.Y2 - t.Y1) * 256; E.sy0 = (long long)(t.X2 - t.X1) * 256;
+	E.sx1 = -(long long)(t.Y0 - t.Y2) * 256; E.sy1 = (long long)(t.X0 - t.X2) * 256;
+	E.sx2 = -(long long)(t.Y1 - t.Y0) * 256; E.sy2 = (long long)(t.X1 - t.X0) * 256;
+}
+__device__ __forceinline__ void shade_covered(const Tri& t, long long e1, long long e2, uint32_t id1, unsigned long long* __restrict__ a) {
+	const float l1 = (float)e1 * t.inv_area, l2 = (float)e2 * t.inv_area;
 	float z = (t.z0 + l1 * t.dz1) + l2 * t.dz2;
 	z = fminf(fmaxf(z, 0.0f), 1.0f);
-	uint32_t dq = __float2uint_rn(z * 16777215.0f);
-	if (dq >= 0xFFFFFFu) return;
-	atomicMin(keys + (size_t)py * W + px, ((unsigned long long)dq << 32) | id1);
+	const uint32_t dq = __float2uint_rn(z * 16777215.0f);
+	if (dq < 0xFFFFFFu) atomicMin(a, ((unsigned long long)dq << 32) | id1);
 }
 
 // perspective divide (reciprocal, then multiply), viewport, 8-bit sub-pixel snap
@@ -193,11 +216,14 @@ __device__ __forceinline__ int setup_tri(const PV& a, const PV& b, const PV& c, 
 __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
                                          unsigned long long* __restrict__ keys) {
 	if (area > 0 && area <= RAD_INLINE_AREA) {
-		const int b0 = edge_bias(tr.X1, tr.Y1, tr.X2, tr.Y2), b1 = edge_bias(tr.X2, tr.Y2, tr.X0, tr.Y0), b2 = edge_bias(tr.X0, tr.Y0, tr.X1, tr.Y1);
 		const int px0 = tr.bx & 0xFFFF, px1 = tr.bx >> 16, py0 = tr.by & 0xFFFF, py1 = tr.by >> 16;
-		for (int py = py0; py <= py1; py++)
-			for (int px = px0; px <= px1; px++)
-				shade_pixel(tr, b0, b1, b2, px, py, id1, keys, D.W);
+		EdgeSet E; edges_at(tr, px0, py0, E);
+		for (int py = py0; py <= py1; py++, E.e0 += E.sy0, E.e1 += E.sy1, E.e2 += E.sy2) {
+			long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
+			unsigned long long* row = keys + (size_t)py * D.W;
+			for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
+				if ((e0 | e1 | e2) >= 0) shade_covered(tr, e1 - E.b1, e2 - E.b2, id1, row + px);
+		}
 	}
 	const bool big = area > RAD_INLINE_AREA;
 	const unsigned mb = __ballot_sync(FULL, big);
@@ -334,28 +360,36 @@ __global__ void __launch_bounds__(128) raster_chunks_kernel(RadDev D) {
 		Tri w;
 		w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
 		w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
-		const int b0 = edge_bias(w.X1, w.Y1, w.X2, w.Y2), b1 = edge_bias(w.X2, w.Y2, w.X0, w.Y0), b2 = edge_bias(w.X0, w.Y0, w.X1, w.Y1);
 		const int px0 = r.px0 + (int)e.tx * RAD_TILE, px1 = min(r.px1, px0 + RAD_TILE - 1);
 		const int py0 = r.py0 + (int)e.ty * RAD_TILE, py1 = min(r.py1, py0 + RAD_TILE - 1);
 		unsigned long long* __restrict__ keys = D.keys + (size_t)r.slot * D.RES;
-		// skip the chunk when one edge has all four corner pixels strictly outside (exact, conservative)
-		{
-			const int cx0 = px0 * 256 + 128, cx1 = px1 * 256 + 128, cy0 = py0 * 256 + 128, cy1 = py1 * 256 + 128;
-			bool out = false;
-			#pragma unroll
-			for (int k = 0; k < 3; k++) {
-				const int ax = k == 0 ? w.X1 : (k == 1 ? w.X2 : w.X0), ay = k == 0 ? w.Y1 : (k == 1 ? w.Y2 : w.Y0);
-				const int bx = k == 0 ? w.X2 : (k == 1 ? w.X0 : w.X1), by = k == 0 ? w.Y2 : (k == 1 ? w.Y0 : w.Y1);
-				out |= edge_fn(ax, ay, bx, by, cx0, cy0) < 0 && edge_fn(ax, ay, bx, by, cx1, cy0) < 0 &&
-				       edge_fn(ax, ay, bx, by, cx0, cy1) < 0 && edge_fn(ax, ay, bx, by, cx1, cy1) < 0;
-			}
+		// this lane's first pixel; steps of 8 pixels in x and 4 in y
+		const int lx = px0 + (lane & 7), ly = py0 + (lane >> 3);
+		EdgeSet E; edges_at(w, lx, ly, E);
+		// a triangle spread over several chunks: skip the chunk when one edge has all four corner pixels outside
+		if (r.px1 - r.px0 >= RAD_TILE || r.py1 - r.py0 >= RAD_TILE) {
+			// corner values from lane 0's origin value: e(px0,py0) + dx*sx + dy*sy
+			const long long dx = px1 - px0, dy = py1 - py0;
+			const long long c0 = __shfl_sync(FULL, E.e0, 0), c1 = __shfl_sync(FULL, E.e1, 0), c2 = __shfl_sync(FULL, E.e2, 0);
+			const bool out = (c0 < 0 && c0 + dx * E.sx0 < 0 && c0 + dy * E.sy0 < 0 && c0 + dx * E.sx0 + dy * E.sy0 < 0) ||
+			                 (c1 < 0 && c1 + dx * E.sx1 < 0 && c1 + dy * E.sy1 < 0 && c1 + dx * E.sx1 + dy * E.sy1 < 0) ||
+			                 (c2 < 0 && c2 + dx * E.sx2 < 0 && c2 + dy * E.sy2 < 0 && c2 + dx * E.sx2 + dy * E.sy2 < 0);
 			if (out) continue;
 		}
-		for (int by = py0; by <= py1; by += 4)
-			for (int bx = px0; bx <= px1; bx += 8) {
-				const int px = bx + (lane & 7), py = by + (lane >> 3);
-				if (px <= px1 && py <= py1) shade_pixel(w, b0, b1, b2, px, py, r.id1, keys, D.W);
-			}
+		for (int py = ly; py <= py1; py += 4, E.e0 += 4 * E.sy0, E.e1 += 4 * E.sy1, E.e2 += 4 * E.sy2) {
+			long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
+			unsigned long long* row = keys + (size_t)py * D.W;
+			for (int px = lx; px <= px1; px += 8, e0 += 8 * E.sx0, e1 += 8 * E.sx1, e2 += 8 * E.sx2)
+				if ((e0 | e1 | e2) >= 0) shade_covered(w, e1 - E.b1, e2 - E.b2, r.id1, row + px);
+		}
+	}
+}
+
+// recycles the chunk queue between hemicube groups of one batch (see rad_launch_raster)
+__global__ void queue_reset_kernel(RadDev D, int first_group) {
+	if (threadIdx.x == 0) {
+		D.ctl->pad = (first_group ? 0u : D.ctl->pad) + D.ctl->q_tris;
+		D.ctl->q_tris = 0; D.ctl->q_entries = 0;
 	}
 }
 
@@ -363,7 +397,7 @@ __global__ void __launch_bounds__(128) raster_chunks_kernel(RadDev D) {
 // separate clear pass is needed in the steady state.  Also recycles the tile queue.
 __global__ void __launch_bounds__(256) resolve_kernel(RadDev D, int reset) {
 	const uint32_t slot = D.h0 + blockIdx.y;
-	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { D.ctl->pad = D.ctl->q_tris; D.ctl->q_tris = 0; D.ctl->q_entries = 0; }
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && D.ctl->q_tris) { D.ctl->pad = D.ctl->q_tris; D.ctl->q_tris = 0; D.ctl->q_entries = 0; }
 	unsigned long long* __restrict__ keys = D.keys + (size_t)slot * D.RES;
 	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.RES; i += gridDim.x * blockDim.x) {
@@ -384,29 +418,53 @@ __global__ void read_depth_kernel(const unsigned long long* __restrict__ keys, u
 
 } // namespace
 
-void rad_launch_camera(rad_ctx* c) {
-	camera_kernel<<<c->d.k, 32, 0, c->stream>>>(c->d);
+void rad_launch_camera(rad_ctx* c, int sel_parity) {
+	camera_kernel<<<c->d.k, 32, 0, c->stream>>>(c->d, sel_parity);
+	c->launches++;
+}
+
+// hemicube slots rendered per set-up launch: bounded so that the chunk queue cannot overflow even if every patch
+// parked both of its triangles (in practice well under half of them do)
+static uint32_t raster_group(const RadDev& D) {
+	const uint32_t nslots = D.h1 - D.h0;
+	uint64_t g = (uint64_t)D.q_tri_cap / (2ull * (D.P ? D.P : 1));
+	if (g < 1) g = 1;
+	return g > nslots ? nslots : (uint32_t)g;
+}
+
+static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n) {
+	RadDev D = c->d;
+	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n;
+	const uint32_t bx = (D.P + 127) / 128;
+	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
+	if ((uint64_t)D.P * n < (1u << 18))
+		raster_setup_kernel<true><<<dim3(bx, RAD_NFACES, n), 128, 0, c->stream>>>(D);
+	else
+		raster_setup_kernel<false><<<dim3(bx, 1, n), 128, 0, c->stream>>>(D);
+	c->launches++;
+}
+static void launch_chunks(rad_ctx* c) {
+	raster_chunks_kernel<<<148 * 8, 128, 0, c->stream>>>(c->d);
 	c->launches++;
 }
 
 void rad_launch_raster_setup_only(rad_ctx* c) {
 	if (c->keys_dirty) rad_launch_clear_keys(c);
-	const RadDev& D = c->d;
-	const uint32_t nslots = D.h1 - D.h0;
-	if (nslots == 0) return;
-	const uint32_t bx = (D.P + 127) / 128;
-	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
-	if ((uint64_t)D.P * nslots < (1u << 18))
-		raster_setup_kernel<true><<<dim3(bx, RAD_NFACES, nslots), 128, 0, c->stream>>>(D);
-	else
-		raster_setup_kernel<false><<<dim3(bx, 1, nslots), 128, 0, c->stream>>>(D);
-	c->launches++;
+	if (c->d.h1 == c->d.h0) return;
+	launch_setup(c, 0, raster_group(c->d));
 }
 
 void rad_launch_raster_tiles_only(rad_ctx* c) {
 	if (c->d.h1 == c->d.h0) return;
-	raster_chunks_kernel<<<148 * 8, 128, 0, c->stream>>>(c->d);
-	c->launches++;
+	launch_chunks(c);
+	// remaining hemicube groups of the batch (only when the batch does not fit the chunk queue at once)
+	const uint32_t nslots = c->d.h1 - c->d.h0, g = raster_group(c->d);
+	for (uint32_t s0 = g; s0 < nslots; s0 += g) {
+		queue_reset_kernel<<<1, 32, 0, c->stream>>>(c->d, s0 == g ? 1 : 0);
+		c->launches++;
+		launch_setup(c, s0, nslots - s0 < g ? nslots - s0 : g);
+		launch_chunks(c);
+	}
 }
 
 void rad_launch_raster(rad_ctx* c) {

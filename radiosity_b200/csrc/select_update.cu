@@ -57,16 +57,6 @@ __global__ void __launch_bounds__(256) argmax_kernel(RadDev D, int parity) {
 	if (threadIdx.x == 0 && best) atomicMax(&D.ctl->selkey[parity], best);
 }
 
-// k == 1: turn selkey[parity] into emitter slot 0 and recycle the other key for this batch's apply
-__global__ void emitter_from_selkey_kernel(RadDev D, int parity) {
-	if (threadIdx.x == 0 && blockIdx.x == 0) {
-		const unsigned long long key = D.ctl->selkey[parity];
-		D.em[0].id = (uint32_t)(key & 0xFFFFFFFFull);      // all-zero energies -> key 0 -> patch 0 (the seeded entry)
-		D.em[0].valid = 1;
-		D.ctl->selkey[parity ^ 1] = 0ull;
-	}
-}
-
 // ---- reference list semantics for k > 1 (single block) --------------------------------------
 __global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
 	__shared__ float s_e[1024];
@@ -255,8 +245,8 @@ void rad_launch_select(rad_ctx* c) {
 	const RadDev& D = c->d;
 	if (D.k == 1) {
 		if (!c->selkey_valid) rad_launch_argmax(c);
-		emitter_from_selkey_kernel<<<1, 32, 0, c->stream>>>(D, (int)c->parity);
-		c->launches++;
+		rad_launch_camera(c, (int)c->parity);      // decodes the fused argmax key, then snapshot + MVPs
+		return;
 	} else if (c->cfg.select_mode == RAD_SELECT_REFERENCE) {
 		select_reference_kernel<<<1, 1024, 0, c->stream>>>(D);
 		c->launches++;
