@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) 
 	const uint32_t nsteps = D.RES >> 7;               // 128 pixels per warp step; RES = 3 N^2 is a multiple of 768
 	float* __restrict__ F = D.F + (size_t)slot * D.P;
 	const float4* __restrict__ ff4 = reinterpret_cast<const float4*>(D.ff);
-	ulonglong2* __restrict__ keys2 = reinterpret_cast<ulonglong2*>(D.keys + (size_t)slot * D.RES);
+	ulonglong2* __restrict__ keys2 = reinterpret_cast<ulonglong2*>(D.keys + (size_t)(slot - D.kbase) * D.RES);
 	uint4* __restrict__ items4 = reinterpret_cast<uint4*>(D.items + (size_t)slot * D.RES);
 
 	for (uint32_t g0 = gw * kUnroll; g0 < nsteps; g0 += nw * kUnroll) {
@@ -119,10 +119,15 @@ void rad_launch_process(rad_ctx* c) {
 	c->launches++;
 }
 
-void rad_launch_resolve_process(rad_ctx* c, bool keep_items) {
-	const RadDev& D = c->d;
-	if (D.h1 == D.h0) return;
+void rad_launch_process_group(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase, bool keep_items) {
+	RadDev D = c->d;
+	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
 	process_kernel<true><<<process_grid(D), 256, 0, c->stream>>>(D, keep_items ? 1 : 0);
 	c->launches++;
 	c->keys_dirty = false;
+}
+
+void rad_launch_resolve_process(rad_ctx* c, bool keep_items) {
+	if (c->d.h1 == c->d.h0) return;
+	rad_launch_process_group(c, 0, c->d.h1 - c->d.h0, 0, keep_items);
 }

@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 #include <dlfcn.h>
 
 static std::string g_create_err;
@@ -77,6 +78,8 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.P = 0; D.h0 = 0; D.h1 = D.k;
 	D.reflectivity = cfg->reflectivity;
 	D.q_tri_cap = 1u << 22; D.q_ent_cap = 1u << 23;
+	D.kbase = 0; D.inline_area = 64;
+	if (const char* e = getenv("RAD_INLINE_AREA")) { const int v = atoi(e); if (v >= 1 && v <= 4096) D.inline_area = (uint32_t)v; }   // tuning knob
 	const size_t Pm = cfg->max_patches;
 	float4 *v0, *v1, *v2; float *color, *ff, *proj;
 	bool ok = true;
@@ -296,8 +299,7 @@ int rad_apply(rad_ctx* c, float* last_energy_len) {
 // one steady-state batch on the stream (single GPU): select -> camera -> raster -> fused resolve+process -> apply
 static void enqueue_batch(rad_ctx* c, bool keep_items) {
 	rad_launch_select(c);
-	rad_launch_raster(c);
-	rad_launch_resolve_process(c, keep_items);
+	rad_launch_raster_process(c, keep_items);
 	const bool fuse = c->d.k == 1;
 	rad_launch_apply(c, fuse);
 	if (fuse) { c->parity ^= 1; c->selkey_valid = true; }
@@ -305,8 +307,7 @@ static void enqueue_batch(rad_ctx* c, bool keep_items) {
 
 static int enqueue_batch_multi(rad_ctx* c, bool keep_items) {
 	rad_launch_select(c);
-	rad_launch_raster(c);
-	rad_launch_resolve_process(c, keep_items);
+	rad_launch_raster_process(c, keep_items);
 	rad_launch_delta(c);
 	if (c->nccl_comm) {
 		int rc = g_nccl.AllReduce(c->d.dB, c->d.dB, (size_t)3 * c->d.P, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream);
@@ -440,29 +441,22 @@ int rad_bench_process(rad_ctx* c, uint32_t repeat, float* ms_per_launch) {
 int rad_profile_batch(rad_ctx* c, float* ms6) {
 	int r = need_ready(c, "rad_profile_batch"); if (r) return r;
 	if (!ms6) return RAD_E_ARG;
-	cudaEvent_t ev[7];
-	for (int i = 0; i < 7; i++) cudaEventCreate(&ev[i]);
 	const bool keep = (c->cfg.flags & RAD_FLAG_KEEP_ITEMBUFFER) != 0;
 	if (c->d.k == 1 && !c->selkey_valid) rad_launch_argmax(c);
-	cudaEventRecord(ev[0], c->stream);
-	rad_launch_select(c);
-	cudaEventRecord(ev[1], c->stream);
-	{   // raster split in two for the report
-		rad_launch_raster_setup_only(c);
-		cudaEventRecord(ev[2], c->stream);
-		rad_launch_raster_tiles_only(c);
-	}
-	cudaEventRecord(ev[3], c->stream);
-	cudaEventRecord(ev[4], c->stream);            // resolve is fused into process in the steady state
-	rad_launch_resolve_process(c, keep);
-	cudaEventRecord(ev[5], c->stream);
+	if (c->keys_dirty) rad_launch_clear_keys(c);
+	// the same launch sequence as one steady-state batch of rad_shoot, with an event after every launch
+	std::vector<cudaEvent_t> ev; std::vector<int> stage;
+	auto mark = [&](int st) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); ev.push_back(e); stage.push_back(st); };
+	mark(-1);
+	rad_launch_select(c); mark(0);
+	rad_launch_raster_process_marked(c, keep, [&](int st) { mark(st); });
 	const bool fuse = c->d.k == 1;
-	rad_launch_apply(c, fuse);
+	rad_launch_apply(c, fuse); mark(5);
 	if (fuse) { c->parity ^= 1; c->selkey_valid = true; }
-	cudaEventRecord(ev[6], c->stream);
 	r = sync_check(c);
-	for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ms6[i], ev[i], ev[i + 1]);
-	for (int i = 0; i < 7; i++) cudaEventDestroy(ev[i]);
+	for (int i = 0; i < 6; i++) ms6[i] = 0.0f;
+	for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); ms6[stage[i]] += ms; }
+	for (cudaEvent_t e : ev) cudaEventDestroy(e);
 	c->emitters_ready = c->rendered = c->processed = false;
 	return r;
 }
@@ -523,8 +517,7 @@ int rad_batch_partial(rad_ctx* c) {
 	int r = need_ready(c, "rad_batch_partial"); if (r) return r;
 	const bool keep = (c->cfg.flags & RAD_FLAG_KEEP_ITEMBUFFER) != 0;
 	rad_launch_select(c);
-	rad_launch_raster(c);
-	rad_launch_resolve_process(c, keep);
+	rad_launch_raster_process(c, keep);
 	rad_launch_delta(c);
 	return sync_check(c);
 }

@@ -6,12 +6,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <functional>
 #include "../../include/rad_cuda.h"
 
 #define RAD_NFACES 5
 #define RAD_CLEAR_KEY 0xFFFFFFFFFFFFFFFFull
 #define RAD_TILE 32               // chunk edge in pixels (chunks are bbox-relative)
-#define RAD_INLINE_AREA 32        // bbox area (px) up to which the owning lane rasterises alone; larger -> chunk queue
 
 struct RadBigTri {                // one screen-space triangle parked for tile processing (64 B)
 	int X0, Y0, X1, Y1, X2, Y2;   // snapped window coordinates, 8 sub-pixel bits
@@ -39,11 +39,15 @@ struct RadEmitter {               // per hemicube slot
 	uint32_t valid;               // 0 == the reference's NULL emitter
 	float S[3];                   // radiosity snapshot (Main.cpp:1161)
 	float color[3];               // emitter colour (Main.cpp:1274)
+	float eye[3];                 // patch centre (hemicube eye) and un-normalised patch normal: conservative culling only
+	float nrm[3];
 };
 
 struct RadDev {                   // device pointers + sizes, passed by value to kernels
 	uint32_t P, N, W, H, RES, k;
-	uint32_t h0, h1;              // hemicube slots this rank renders/processes
+	uint32_t h0, h1;              // hemicube slots this rank renders/processes (kernels: slots of this launch)
+	uint32_t kbase;               // slot whose keys live in key buffer 0 (fused path recycles L2-resident key buffers per group)
+	uint32_t inline_area;         // bbox area (px) up to which the owning lane rasterises alone; larger -> chunk queue
 	float reflectivity;
 	const float4* v0; const float4* v1; const float4* v2;   // verts: (v1.xyz,v2.x) (v2.yz,v3.xy) (v3.z,v4.xyz)
 	const float* color;           // [3][P] planes
@@ -93,7 +97,9 @@ void rad_launch_set_emitters(rad_ctx* c, const uint32_t* d_ids, uint32_t n);
 void rad_launch_resolve(rad_ctx* c, bool reset);    // keys -> items (+ keys reset)
 void rad_launch_clear_keys(rad_ctx* c);
 void rad_launch_process(rad_ctx* c);                // items -> F
-void rad_launch_resolve_process(rad_ctx* c, bool keep_items);   // fused
+void rad_launch_resolve_process(rad_ctx* c, bool keep_items);   // fused (all slots, keys indexed from kbase = h0)
+void rad_launch_raster_process(rad_ctx* c, bool keep_items);    // steady state: per L2-sized hemicube group raster -> fused process
+void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::function<void(int)>& mark);   // same, mark(stage) after each launch (1 set-up, 2 chunks, 4 process)
 void rad_launch_apply(rad_ctx* c, bool fuse_select); // S4..S6 (+ argmax of the new B for k==1)
 void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB
 void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update

@@ -103,6 +103,10 @@ __global__ void camera_kernel(RadDev D, int sel_parity) {
 				e.S[c] = D.rad[(size_t)c * D.P + e.id];            // p_tmp_radiosities[hi] (Main.cpp:1161)
 				e.color[c] = D.color[(size_t)c * D.P + e.id];
 			}
+			const Quad q = load_quad(D, e.id);
+			e.eye[0] = (q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f; e.eye[1] = (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f; e.eye[2] = (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f;
+			const V3 n = rcross(vsub(q.b, q.a), vsub(q.d, q.a));
+			e.nrm[0] = n.x; e.nrm[1] = n.y; e.nrm[2] = n.z;
 		} else e.valid = 0;
 		D.em[h] = e;
 		s_e = e;
@@ -215,7 +219,7 @@ __device__ __forceinline__ int setup_tri(const PV& a, const PV& b, const PV& c, 
 // with one atomic per warp.
 __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
                                          unsigned long long* __restrict__ keys) {
-	if (area > 0 && area <= RAD_INLINE_AREA) {
+	if (area > 0 && area <= (int)D.inline_area) {
 		const int px0 = tr.bx & 0xFFFF, px1 = tr.bx >> 16, py0 = tr.by & 0xFFFF, py1 = tr.by >> 16;
 		EdgeSet E; edges_at(tr, px0, py0, E);
 		for (int py = py0; py <= py1; py++, E.e0 += E.sy0, E.e1 += E.sy1, E.e2 += E.sy2) {
@@ -225,7 +229,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 				if ((e0 | e1 | e2) >= 0) shade_covered(tr, e1 - E.b1, e2 - E.b2, id1, row + px);
 		}
 	}
-	const bool big = area > RAD_INLINE_AREA;
+	const bool big = area > (int)D.inline_area;
 	const unsigned mb = __ballot_sync(FULL, big);
 	if (mb == 0) return;
 	int ncx = 0, ncy = 0, nent = 0;
@@ -274,10 +278,37 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
 	const int N = (int)D.N;
 	const float hw = (float)N * 0.5f;
-	unsigned long long* __restrict__ keys = D.keys + (size_t)slot * D.RES;
+	unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
 	Quad q;
 	if (live) q = load_quad(D, p);
 	const uint32_t id1 = p + 1;
+
+	// Conservative patch-level culling (wide margins; the exact tests below decide everything that survives):
+	//  - both triangles clearly face away from the eye (more than ~6 degrees past edge-on): the exact path would
+	//    compute a negative window-space area for them on every face;
+	//  - all four vertices clearly below the shooter's horizon plane: clipped by the near plane on FRONT and
+	//    projected below the scissor on the four side faces.
+	bool culled = !live;
+	if (live) {
+		const V3 eye = mk(em.eye[0], em.eye[1], em.eye[2]), ns = mk(em.nrm[0], em.nrm[1], em.nrm[2]);
+		const V3 da = vsub(eye, q.a);
+		const V3 n1 = rcross(vsub(q.b, q.a), vsub(q.c, q.a)), n2 = rcross(vsub(q.c, q.a), vsub(q.d, q.a));
+		const float d2 = da.x * da.x + da.y * da.y + da.z * da.z;
+		const float s1 = n1.x * da.x + n1.y * da.y + n1.z * da.z, s2 = n2.x * da.x + n2.y * da.y + n2.z * da.z;
+		const float m1 = 0.01f * (n1.x * n1.x + n1.y * n1.y + n1.z * n1.z) * d2, m2 = 0.01f * (n2.x * n2.x + n2.y * n2.y + n2.z * n2.z) * d2;
+		const bool back = (s1 < 0.0f && s1 * s1 > m1 || m1 == 0.0f) && (s2 < 0.0f && s2 * s2 > m2 || m2 == 0.0f) && (m1 > 0.0f || m2 > 0.0f);
+		const float ns2 = ns.x * ns.x + ns.y * ns.y + ns.z * ns.z;
+		bool below = true;
+		const V3* vv[4] = { &q.a, &q.b, &q.c, &q.d };
+		#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const V3 r = vsub(*vv[i], eye);
+			const float h = r.x * ns.x + r.y * ns.y + r.z * ns.z;
+			below = below && h < 0.0f && h * h > 1e-6f * ns2 * (r.x * r.x + r.y * r.y + r.z * r.z);
+		}
+		culled = back || below;
+	}
+	if (!__any_sync(FULL, !culled)) return;
 
 	for (int f = f_begin; f < f_end; f++) {
 		// viewport origin and scissor of this face (Main.cpp:314-389)
@@ -291,7 +322,7 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
 		}
 		const float ox = (float)vpx + hw, oy = (float)vpy + hw;
 		CV c[4]; float dn[4]; int nin = 0;
-		if (live) {
+		if (!culled) {
 			c[0] = xform(s_mvp[f], q.a); c[1] = xform(s_mvp[f], q.b); c[2] = xform(s_mvp[f], q.c); c[3] = xform(s_mvp[f], q.d);
 			#pragma unroll
 			for (int i = 0; i < 4; i++) { dn[i] = c[i].z + c[i].w; nin += dn[i] >= 0.0f; }
@@ -362,7 +393,7 @@ __global__ void __launch_bounds__(128) raster_chunks_kernel(RadDev D) {
 		w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
 		const int px0 = r.px0 + (int)e.tx * RAD_TILE, px1 = min(r.px1, px0 + RAD_TILE - 1);
 		const int py0 = r.py0 + (int)e.ty * RAD_TILE, py1 = min(r.py1, py0 + RAD_TILE - 1);
-		unsigned long long* __restrict__ keys = D.keys + (size_t)r.slot * D.RES;
+		unsigned long long* __restrict__ keys = D.keys + (size_t)(r.slot - D.kbase) * D.RES;
 		// this lane's first pixel; steps of 8 pixels in x and 4 in y
 		const int lx = px0 + (lane & 7), ly = py0 + (lane >> 3);
 		EdgeSet E; edges_at(w, lx, ly, E);
@@ -398,7 +429,7 @@ __global__ void queue_reset_kernel(RadDev D, int first_group) {
 __global__ void __launch_bounds__(256) resolve_kernel(RadDev D, int reset) {
 	const uint32_t slot = D.h0 + blockIdx.y;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && D.ctl->q_tris) { D.ctl->pad = D.ctl->q_tris; D.ctl->q_tris = 0; D.ctl->q_entries = 0; }
-	unsigned long long* __restrict__ keys = D.keys + (size_t)slot * D.RES;
+	unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
 	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.RES; i += gridDim.x * blockDim.x) {
 		const unsigned long long k = keys[i];
@@ -425,16 +456,24 @@ void rad_launch_camera(rad_ctx* c, int sel_parity) {
 
 // hemicube slots rendered per set-up launch: bounded so that the chunk queue cannot overflow even if every patch
 // parked both of its triangles (in practice well under half of them do)
-static uint32_t raster_group(const RadDev& D) {
+static uint32_t queue_group(const RadDev& D) {
 	const uint32_t nslots = D.h1 - D.h0;
 	uint64_t g = (uint64_t)D.q_tri_cap / (2ull * (D.P ? D.P : 1));
 	if (g < 1) g = 1;
 	return g > nslots ? nslots : (uint32_t)g;
 }
+// fused steady state: additionally keep the group's 64-bit key buffers (8 B/pixel) inside the 126 MB L2, so that the
+// rasteriser's atomics and the fused ProcessHemicube pass never touch HBM for them
+static uint32_t l2_group(const RadDev& D) {
+	uint64_t g = (64ull << 20) / ((uint64_t)D.RES * 8ull);
+	if (g < 1) g = 1;
+	const uint32_t q = queue_group(D);
+	return g > q ? q : (uint32_t)g;
+}
 
-static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n) {
+static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 	RadDev D = c->d;
-	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n;
+	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
 	const uint32_t bx = (D.P + 127) / 128;
 	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
 	if ((uint64_t)D.P * n < (1u << 18))
@@ -443,34 +482,56 @@ static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n) {
 		raster_setup_kernel<false><<<dim3(bx, 1, n), 128, 0, c->stream>>>(D);
 	c->launches++;
 }
-static void launch_chunks(rad_ctx* c) {
-	raster_chunks_kernel<<<148 * 8, 128, 0, c->stream>>>(c->d);
+static void launch_chunks(rad_ctx* c, uint32_t kbase) {
+	RadDev D = c->d;
+	D.kbase = kbase;
+	raster_chunks_kernel<<<148 * 8, 128, 0, c->stream>>>(D);
 	c->launches++;
 }
 
 void rad_launch_raster_setup_only(rad_ctx* c) {
 	if (c->keys_dirty) rad_launch_clear_keys(c);
 	if (c->d.h1 == c->d.h0) return;
-	launch_setup(c, 0, raster_group(c->d));
+	launch_setup(c, 0, queue_group(c->d), 0);
 }
 
 void rad_launch_raster_tiles_only(rad_ctx* c) {
 	if (c->d.h1 == c->d.h0) return;
-	launch_chunks(c);
+	launch_chunks(c, 0);
 	// remaining hemicube groups of the batch (only when the batch does not fit the chunk queue at once)
-	const uint32_t nslots = c->d.h1 - c->d.h0, g = raster_group(c->d);
+	const uint32_t nslots = c->d.h1 - c->d.h0, g = queue_group(c->d);
 	for (uint32_t s0 = g; s0 < nslots; s0 += g) {
 		queue_reset_kernel<<<1, 32, 0, c->stream>>>(c->d, s0 == g ? 1 : 0);
 		c->launches++;
-		launch_setup(c, s0, nslots - s0 < g ? nslots - s0 : g);
-		launch_chunks(c);
+		launch_setup(c, s0, nslots - s0 < g ? nslots - s0 : g, 0);
+		launch_chunks(c, 0);
 	}
 }
 
+// staged API: all slots rendered into their own key buffers (kbase = 0: slot s uses key buffer s)
 void rad_launch_raster(rad_ctx* c) {
 	rad_launch_raster_setup_only(c);
 	rad_launch_raster_tiles_only(c);
 }
+
+void rad_launch_process_group(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase, bool keep_items);   // process.cu
+
+// steady state (rad_shoot): per L2-sized group of hemicubes  set-up -> chunks -> fused resolve+ProcessHemicube, the
+// group's key buffers being reused by the next group
+void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::function<void(int)>& mark) {
+	if (c->keys_dirty) rad_launch_clear_keys(c);
+	const uint32_t nslots = c->d.h1 - c->d.h0;
+	if (nslots == 0) return;
+	const uint32_t g = l2_group(c->d);
+	for (uint32_t s0 = 0; s0 < nslots; s0 += g) {
+		const uint32_t n = nslots - s0 < g ? nslots - s0 : g;
+		const uint32_t kbase = c->d.h0 + s0;
+		launch_setup(c, s0, n, kbase); if (mark) mark(1);
+		launch_chunks(c, kbase); if (mark) mark(2);
+		rad_launch_process_group(c, s0, n, kbase, keep_items); if (mark) mark(4);
+	}
+}
+void rad_launch_raster_process(rad_ctx* c, bool keep_items) { rad_launch_raster_process_marked(c, keep_items, nullptr); }
 
 void rad_launch_resolve(rad_ctx* c, bool reset) {
 	const RadDev& D = c->d;
