@@ -750,9 +750,13 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
                    unsigned n_batches, int select_mode, int via_codec, int stop_test, int threads, uint32_t* schedule, float* last_energy_len) {
 	const unsigned W = 2 * N, H = (unsigned)(N * 1.5), RES = W * H;
 	const float reflectivity = 0.3f;   // Patch.h:13
-	std::vector<float> ff((size_t)RES * k);
-	formfactors(N, k, ff.data());
+	// the reference replicates the one-hemicube table k times (FormFactors.cpp:317-323); only the literal kernel
+	// restatement needs the copies, every other consumer indexes the first one
+	std::vector<float> ff((size_t)RES * (via_codec ? k : 1));
+	formfactors(N, via_codec ? k : 1, ff.data());
 	std::vector<uint64_t> keys(RES);
+	std::vector<std::vector<uint64_t> > tkeys(threads > 1 && k > 1 ? threads : 0);
+	for (size_t t = 0; t < tkeys.size(); t++) tkeys[t].resize(RES);
 	std::vector<uint32_t> atlas((size_t)RES * k);
 	std::vector<float> F(P, 0.0f), Fall;
 	if (threads > 1 && k > 1 && !via_codec) Fall.assign((size_t)P * k, 0.0f);
@@ -766,7 +770,8 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 	float last_len = 0;
 	for (unsigned shoot = 0; shoot < n_batches; shoot++) {
 		orc_select(P, rad3, k, select_mode, em.data(), isnull.data());                                    // S1
-		std::fill(atlas.begin(), atlas.end(), 0u);                                                        // glClear
+		for (unsigned hi = 0; hi < k; hi++)                                                               // glClear (rendered slots are fully rewritten below)
+			if (isnull[hi]) std::fill(atlas.begin() + (size_t)RES * hi, atlas.begin() + (size_t)RES * (hi + 1), 0u);
 		for (unsigned hi = 0; hi < k; hi++) {                                                             // S2 (snapshots)
 			if (schedule) schedule[(size_t)shoot * k + hi] = isnull[hi] ? 0xFFFFFFFFu : em[hi];
 			if (!isnull[hi]) snap_rad[hi] = v3(rad3[3 * em[hi]], rad3[3 * em[hi] + 1], rad3[3 * em[hi] + 2]);
@@ -777,9 +782,10 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 		#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) if (par_hemi)
 		for (int hi = 0; hi < (int)k; hi++) {
 			if (isnull[hi]) continue;
-			std::vector<uint64_t> local;
 			uint64_t* kk = keys.data();
-			if (par_hemi) { local.resize(RES); kk = local.data(); }
+#ifdef _OPENMP
+			if (par_hemi) kk = tkeys[omp_get_thread_num()].data();
+#endif
 			render_hemicube_keys(P, verts, em[hi], (int)N, kk, par_hemi ? 1 : threads);
 			uint32_t* a = atlas.data() + (size_t)RES * hi;
 			for (unsigned i = 0; i < RES; i++) a[i] = kk[i] == kClearKey ? 0u : (uint32_t)(kk[i] & 0xFFFFFFFFu);

@@ -72,6 +72,8 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->h_stage = nullptr; c->h_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
 	c->launches = 0;
+	c->split_limit = 1u << 16;
+	if (const char* e = getenv("RAD_SPLIT_LIMIT")) c->split_limit = strtoull(e, nullptr, 10);   // tuning knob
 	RadDev& D = c->d;
 	memset(&D, 0, sizeof(D));
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;

@@ -85,6 +85,7 @@ struct rad_ctx {
 	// multi-GPU
 	int rank, world; void* nccl_comm; bool partition_only;
 	uint32_t launches;            // kernels launched since last reset
+	uint64_t split_limit;         // P * hemicubes below which the set-up kernel runs one lane per (patch, face)
 };
 
 // ---- launchers (each enqueues on ctx->stream and bumps ctx->launches) -------------------------

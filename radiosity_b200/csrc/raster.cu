@@ -476,7 +476,7 @@ static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
 	const uint32_t bx = (D.P + 127) / 128;
 	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
-	if ((uint64_t)D.P * n < (1u << 18))
+	if ((uint64_t)D.P * n < c->split_limit)
 		raster_setup_kernel<true><<<dim3(bx, RAD_NFACES, n), 128, 0, c->stream>>>(D);
 	else
 		raster_setup_kernel<false><<<dim3(bx, 1, n), 128, 0, c->stream>>>(D);
