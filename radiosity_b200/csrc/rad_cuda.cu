@@ -72,7 +72,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->h_stage = nullptr; c->h_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
 	c->launches = 0;
-	c->split_limit = 1u << 16;
+	c->split_limit = 1u << 22; c->inline_area_forced = false;
 	if (const char* e = getenv("RAD_SPLIT_LIMIT")) c->split_limit = strtoull(e, nullptr, 10);   // tuning knob
 	RadDev& D = c->d;
 	memset(&D, 0, sizeof(D));
@@ -81,7 +81,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.reflectivity = cfg->reflectivity;
 	D.q_tri_cap = 1u << 22; D.q_ent_cap = 1u << 23;
 	D.kbase = 0; D.inline_area = 64;
-	if (const char* e = getenv("RAD_INLINE_AREA")) { const int v = atoi(e); if (v >= 1 && v <= 4096) D.inline_area = (uint32_t)v; }   // tuning knob
+	if (const char* e = getenv("RAD_INLINE_AREA")) { const int v = atoi(e); if (v >= 1 && v <= 4096) { D.inline_area = (uint32_t)v; c->inline_area_forced = true; } }   // tuning knob
 	const size_t Pm = cfg->max_patches;
 	float4 *v0, *v1, *v2; float *color, *ff, *proj;
 	bool ok = true;

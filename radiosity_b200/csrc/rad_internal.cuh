@@ -85,6 +85,7 @@ struct rad_ctx {
 	// multi-GPU
 	int rank, world; void* nccl_comm; bool partition_only;
 	uint32_t launches;            // kernels launched since last reset
+	bool inline_area_forced;      // RAD_INLINE_AREA set: do not auto-tune the inline tier
 	uint64_t split_limit;         // P * hemicubes below which the set-up kernel runs one lane per (patch, face)
 };
 

@@ -185,6 +185,36 @@ __device__ __forceinline__ void shade_covered(const Tri& t, long long e1, long l
 	if (dq < 0xFFFFFFu) atomicMin(a, ((unsigned long long)dq << 32) | id1);
 }
 
+// 32-bit form of the same edge functions for triangles that are small around the walk origin: with R = largest
+// |vertex - origin| and S = largest pixel-centre offset (sub-pixel units), |E| <= 4 R (R + S), so R (R + S) < 2^29 keeps
+// every product and sum inside int32.  Same integers, hence the same coverage and (float)E as the 64-bit walk.
+struct EdgeSet32 { int e0, e1, e2, sx0, sx1, sx2, sy0, sy1, sy2, b1, b2; };
+__device__ __forceinline__ bool fits32(const Tri& t, int px, int py, int span_px) {
+	const int cx = px * 256 + 128, cy = py * 256 + 128;
+	const int r = max(max(max(abs(t.X0 - cx), abs(t.Y0 - cy)), max(abs(t.X1 - cx), abs(t.Y1 - cy))), max(abs(t.X2 - cx), abs(t.Y2 - cy)));
+	return (long long)r * (long long)(r + span_px * 256) < (1ll << 29);
+}
+__device__ __forceinline__ void edges_at32(const Tri& t, int px, int py, EdgeSet32& E) {
+	const int cx = px * 256 + 128, cy = py * 256 + 128;
+	const int x0 = t.X0 - cx, y0 = t.Y0 - cy, x1 = t.X1 - cx, y1 = t.Y1 - cy, x2 = t.X2 - cx, y2 = t.Y2 - cy;
+	const int b0 = edge_bias(t.X1, t.Y1, t.X2, t.Y2);
+	E.b1 = edge_bias(t.X2, t.Y2, t.X0, t.Y0); E.b2 = edge_bias(t.X0, t.Y0, t.X1, t.Y1);
+	// edge_fn(a, b, c) with c at the origin: (bx-ax)(0-ay) - (by-ay)(0-ax)
+	E.e0 = (x2 - x1) * (-y1) - (y2 - y1) * (-x1) + b0;
+	E.e1 = (x0 - x2) * (-y2) - (y0 - y2) * (-x2) + E.b1;
+	E.e2 = (x1 - x0) * (-y0) - (y1 - y0) * (-x0) + E.b2;
+	E.sx0 = -(y2 - y1) * 256; E.sy0 = (x2 - x1) * 256;
+	E.sx1 = -(y0 - y2) * 256; E.sy1 = (x0 - x2) * 256;
+	E.sx2 = -(y1 - y0) * 256; E.sy2 = (x1 - x0) * 256;
+}
+__device__ __forceinline__ void shade_covered32(const Tri& t, int e1, int e2, uint32_t id1, unsigned long long* __restrict__ a) {
+	const float l1 = (float)e1 * t.inv_area, l2 = (float)e2 * t.inv_area;
+	float z = (t.z0 + l1 * t.dz1) + l2 * t.dz2;
+	z = fminf(fmaxf(z, 0.0f), 1.0f);
+	const uint32_t dq = __float2uint_rn(z * 16777215.0f);
+	if (dq < 0xFFFFFFu) atomicMin(a, ((unsigned long long)dq << 32) | id1);
+}
+
 // perspective divide (reciprocal, then multiply), viewport, 8-bit sub-pixel snap
 __device__ __forceinline__ PV project(const CV& c, float hw, float ox, float oy) {
 	const float iw = 1.0f / c.w;
@@ -221,12 +251,22 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
                                          unsigned long long* __restrict__ keys) {
 	if (area > 0 && area <= (int)D.inline_area) {
 		const int px0 = tr.bx & 0xFFFF, px1 = tr.bx >> 16, py0 = tr.by & 0xFFFF, py1 = tr.by >> 16;
-		EdgeSet E; edges_at(tr, px0, py0, E);
-		for (int py = py0; py <= py1; py++, E.e0 += E.sy0, E.e1 += E.sy1, E.e2 += E.sy2) {
-			long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
-			unsigned long long* row = keys + (size_t)py * D.W;
-			for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
-				if ((e0 | e1 | e2) >= 0) shade_covered(tr, e1 - E.b1, e2 - E.b2, id1, row + px);
+		if (fits32(tr, px0, py0, max(px1 - px0, py1 - py0))) {
+			EdgeSet32 E; edges_at32(tr, px0, py0, E);
+			for (int py = py0; py <= py1; py++, E.e0 += E.sy0, E.e1 += E.sy1, E.e2 += E.sy2) {
+				int e0 = E.e0, e1 = E.e1, e2 = E.e2;
+				unsigned long long* row = keys + (size_t)py * D.W;
+				for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
+					if ((e0 | e1 | e2) >= 0) shade_covered32(tr, e1 - E.b1, e2 - E.b2, id1, row + px);
+			}
+		} else {
+			EdgeSet E; edges_at(tr, px0, py0, E);
+			for (int py = py0; py <= py1; py++, E.e0 += E.sy0, E.e1 += E.sy1, E.e2 += E.sy2) {
+				long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
+				unsigned long long* row = keys + (size_t)py * D.W;
+				for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
+					if ((e0 | e1 | e2) >= 0) shade_covered(tr, e1 - E.b1, e2 - E.b2, id1, row + px);
+			}
 		}
 	}
 	const bool big = area > (int)D.inline_area;
@@ -396,6 +436,16 @@ __global__ void __launch_bounds__(128) raster_chunks_kernel(RadDev D) {
 		unsigned long long* __restrict__ keys = D.keys + (size_t)(r.slot - D.kbase) * D.RES;
 		// this lane's first pixel; steps of 8 pixels in x and 4 in y
 		const int lx = px0 + (lane & 7), ly = py0 + (lane >> 3);
+		if (fits32(w, px0, py0, RAD_TILE)) {          // warp-uniform: small triangle around this chunk -> int32 walk
+			EdgeSet32 E; edges_at32(w, lx, ly, E);
+			for (int py = ly; py <= py1; py += 4, E.e0 += 4 * E.sy0, E.e1 += 4 * E.sy1, E.e2 += 4 * E.sy2) {
+				int e0 = E.e0, e1 = E.e1, e2 = E.e2;
+				unsigned long long* row = keys + (size_t)py * D.W;
+				for (int px = lx; px <= px1; px += 8, e0 += 8 * E.sx0, e1 += 8 * E.sx1, e2 += 8 * E.sx2)
+					if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, r.id1, row + px);
+			}
+			continue;
+		}
 		EdgeSet E; edges_at(w, lx, ly, E);
 		// a triangle spread over several chunks: skip the chunk when one edge has all four corner pixels outside
 		if (r.px1 - r.px0 >= RAD_TILE || r.py1 - r.py0 >= RAD_TILE) {
@@ -474,6 +524,8 @@ static uint32_t l2_group(const RadDev& D) {
 static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 	RadDev D = c->d;
 	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
+	// one hemicube in flight (k == 1): latency matters, keep the per-lane pixel loops short and let the chunk warps share the rest
+	if (!c->inline_area_forced) D.inline_area = (uint64_t)D.P * n < (1u << 16) ? 16u : 64u;
 	const uint32_t bx = (D.P + 127) / 128;
 	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
 	if ((uint64_t)D.P * n < c->split_limit)
