@@ -36,7 +36,10 @@ def shoot_batches_hosted(engine, dist, n_batches):
         engine.batch_partial()
         dB = torch.from_numpy(np.ascontiguousarray(engine.read_delta(), dtype=np.float32))
         if dist is not None and dist.get_world_size() > 1:
+            if dist.get_backend() == "nccl":          # NCCL reduces device tensors only
+                dB = dB.cuda()
             dist.all_reduce(dB, op=dist.ReduceOp.SUM)
+            dB = dB.cpu()
         engine.write_delta(dB.numpy())
         last = engine.batch_finish()
     return last
