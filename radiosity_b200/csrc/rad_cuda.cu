@@ -72,7 +72,8 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->h_stage = nullptr; c->h_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
 	c->launches = 0;
-	c->split_limit = 1u << 22; c->inline_area_forced = false;
+	c->split_limit = 1u << 22; c->inline_area_forced = false; c->setup_minb = 4;
+	if (const char* e = getenv("RAD_SETUP_MINB")) c->setup_minb = atoi(e);   // tuning knob
 	if (const char* e = getenv("RAD_SPLIT_LIMIT")) c->split_limit = strtoull(e, nullptr, 10);   // tuning knob
 	RadDev& D = c->d;
 	memset(&D, 0, sizeof(D));

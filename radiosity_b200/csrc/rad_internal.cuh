@@ -86,6 +86,7 @@ struct rad_ctx {
 	int rank, world; void* nccl_comm; bool partition_only;
 	uint32_t launches;            // kernels launched since last reset
 	bool inline_area_forced;      // RAD_INLINE_AREA set: do not auto-tune the inline tier
+	int setup_minb;               // min resident CTAs/SM the set-up kernel variant was compiled for (register cap)
 	uint64_t split_limit;         // P * hemicubes below which the set-up kernel runs one lane per (patch, face)
 };
 

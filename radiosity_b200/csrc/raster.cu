@@ -303,8 +303,8 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 }
 
 // grid: x = patch chunk, y = face (SPLIT) or 1, z = local hemicube slot
-template <bool SPLIT_FACES>
-__global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
+template <bool SPLIT_FACES, int MINB>
+__global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 	__shared__ float s_mvp[RAD_NFACES][16];
 	const uint32_t slot = D.h0 + blockIdx.z;
 	const RadEmitter em = D.em[slot];
@@ -528,10 +528,15 @@ static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 	if (!c->inline_area_forced) D.inline_area = (uint64_t)D.P * n < (1u << 16) ? 16u : 64u;
 	const uint32_t bx = (D.P + 127) / 128;
 	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
-	if ((uint64_t)D.P * n < c->split_limit)
-		raster_setup_kernel<true><<<dim3(bx, RAD_NFACES, n), 128, 0, c->stream>>>(D);
-	else
-		raster_setup_kernel<false><<<dim3(bx, 1, n), 128, 0, c->stream>>>(D);
+	const dim3 gs(bx, RAD_NFACES, n), gp(bx, 1, n);
+	if ((uint64_t)D.P * n < c->split_limit) {
+		if (c->setup_minb >= 8) raster_setup_kernel<true, 8><<<gs, 128, 0, c->stream>>>(D);
+		else if (c->setup_minb >= 6) raster_setup_kernel<true, 6><<<gs, 128, 0, c->stream>>>(D);
+		else raster_setup_kernel<true, 4><<<gs, 128, 0, c->stream>>>(D);
+	} else {
+		if (c->setup_minb >= 6) raster_setup_kernel<false, 6><<<gp, 128, 0, c->stream>>>(D);
+		else raster_setup_kernel<false, 3><<<gp, 128, 0, c->stream>>>(D);
+	}
 	c->launches++;
 }
 static void launch_chunks(rad_ctx* c, uint32_t kbase) {
