@@ -1,0 +1,96 @@
+"""GPU: full-size properties at the larger BASELINE configs (size-independent invariants + oracle spot checks)."""
+import os
+
+import numpy as np
+import pytest
+
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config3_size_invariants_and_oracle_spot_check(api, orc):
+    """P = 250 063, hemicube 1024 (BASELINE config 3 cross-check scene): closed box => no empty pixel, sum F == sum dFF,
+    F[self] == 0, ids in range; bit-exact run to run; one hemicube against the oracle."""
+    N, k = 1024, 4
+    v, c, r, il = orc.scene_cornell(0.0009)
+    P = v.shape[0]
+    assert P == 250063
+    ctx = api.Context(N, k, P, select_mode=api.SELECT_TOPK)
+    ff = api.formfactors(N)
+    ctx.set_formfactors(ff)
+    ctx.upload_scene(v, c, r, il)
+    shooters = [173030, 0, 100000, P - 1]
+    ctx.set_emitters(shooters)
+    ctx.render()
+    items = [ctx.read_itembuffer(h) for h in range(k)]
+    for it in items:
+        assert (it == 0).sum() == 0 and it.max() <= P
+    ctx.process()
+    sff = float(ff.sum(dtype=np.float64))
+    for h, s in enumerate(shooters):
+        F = ctx.read_formfactors(h)
+        assert F[s] == 0
+        assert abs(float(F.sum(dtype=np.float64)) - sff) < 2e-5
+    ctx.render()
+    for h in range(k):
+        assert (ctx.read_itembuffer(h) == items[h]).all()
+    exp = orc.render_hemicube(v, shooters[0], N, threads=8)
+    agree = float((items[0] == exp).mean())
+    assert agree >= 0.999
+    assert agree == 1.0
+    assert rel_l2(ctx.read_formfactors(0), orc.process_ids(exp, ff, N, P)) < 1e-5
+    ctx.close()
+
+
+def test_batched_topk_run_config3_energy_bookkeeping(api, orc):
+    """k = 64 batches on the 250 k-patch scene through rad_shoot: every shot moves S from B to I of its emitter."""
+    N, k = 512, 64
+    v, c, r, il = orc.scene_cornell(0.0009)
+    P = v.shape[0]
+    ctx = api.Context(N, k, P, select_mode=api.SELECT_TOPK)
+    ctx.set_formfactors(api.formfactors(N))
+    ctx.upload_scene(v, c, r, il)
+    st = ctx.shoot(3)
+    assert st.batches_done == 3 and st.shots_done == 192 and st.queue_overflow == 0
+    rad, illum = ctx.download_state()
+    lights = np.nonzero(r[:, 0] > 0)[0]
+    shot = np.nonzero(illum[:, 0] > 1.5)[0]
+    assert len(shot) == 192 and set(shot) <= set(lights)          # the 192 first lights (id order among equal energies)
+    assert (shot == lights[:192]).all()
+    assert np.allclose(illum[shot], 101.0, rtol=1e-3)               # I = 1 + B, B = 100 (+ what it received before shooting)
+    assert np.isfinite(rad).all() and rad.min() > -1e-3
+    ctx.close()
+
+
+def test_obj_scene_with_emitter_extension(api, orc, tmp_path):
+    """A Wavefront OBJ room (mm units, quads + triangles) with the #@color / #@emit extension, shot on the GPU; geometry
+    equals what the reference's loader produces (the oracle's loader, pinned to the reference in the CPU suite)."""
+    p = tmp_path / "room.obj"
+    L = 2000
+    vs = [(0, 0, 0), (L, 0, 0), (L, L, 0), (0, L, 0), (0, 0, L), (L, 0, L), (L, L, L), (0, L, L)]
+    lines = ["v %d %d %d" % t for t in vs]
+    lines += ["#@color 0.8 0.8 0.8", "f 1 2 3 4", "f 8 7 6 5", "f 1 5 6 2", "f 2 6 7 3", "f 3 7 8 4", "f 4 8 5 1"]
+    lines += ["v 800 1990 800", "v 1200 1990 800", "v 1200 1990 1200", "v 800 1990 1200", "#@color 1 1 1", "#@emit 50 50 40", "f 9 10 11 12", "#@emit 0 0 0"]
+    lines += ["v 500 0 500", "v 900 0 500", "v 700 600 700", "#@color 1 0.2 0.2", "f 13 15 14"]          # a triangle -> degenerate quad
+    p.write_text("\n".join(lines) + "\n")
+    scene = api.Scene(0.05, obj=str(p))
+    v, _, c, r, il = scene.arrays()
+    ov, oc, orr, oil = orc.scene_obj(str(p), 0.05)
+    assert (v.view(np.uint32) == ov.view(np.uint32)).all()          # same geometry as the reference-pinned loader
+    assert r.sum() > 0 and c.sum() > 0 and orr.sum() == 0
+    N = 128
+    ctx = api.context_for_scene(scene, N, 1)
+    em = int(np.nonzero(r[:, 0] > 0)[0][-1])
+    ids, valid = ctx.select()
+    assert ids[0] == em
+    ctx.render()
+    got = ctx.read_itembuffer(0)
+    exp = orc.render_hemicube(v, em, N)
+    assert (got == exp).all()
+    st = ctx.shoot(30)
+    rad, illum = ctx.download_state()
+    orad, oillum, *_ = orc.shoot(v, c, r, il, N, 1, 30)
+    assert rel_l2(rad, orad) < 1e-3 and rel_l2(illum, oillum) < 1e-3
+    ctx.close()
