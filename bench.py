@@ -51,13 +51,18 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region.  The sampler is started before the warm-up
+    (nvidia-smi's own start-up perturbs the GPUs for tens of ms, worst with 8 of them) and only samples whose timestamp
+    falls inside [mark_start, mark_end] are summarised."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, device):
-        self.device = device; self.proc = None; self.path = None
+    def __init__(self, device, enabled=True):
+        self.device = device; self.proc = None; self.path = None; self.enabled = enabled
+        self.t0 = self.t1 = None
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv"); os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -65,6 +70,14 @@ class ClockSampler:
         except Exception:
             self.proc = None
         return self
+
+    def mark_start(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -75,6 +88,7 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.path or not os.path.exists(self.path):
             return out
@@ -82,13 +96,16 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                if self.t0 and self.t1 and not (self.t0 - datetime.timedelta(milliseconds=100) <= ts <= self.t1 + datetime.timedelta(milliseconds=100)):
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(names, f[4:8]):
                 if v.lower() == "active":
                     reasons.add(n)
         os.unlink(self.path)
@@ -212,12 +229,14 @@ def main():
         ctx.restore_state()
         return ctx.shoot(batches)
 
-    for _ in range(args.warmup):
-        st = step_device()
     launches = 0
     gpu_ms = []
-    barrier()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
+        time.sleep(0.5)                                                   # let nvidia-smi finish starting before anything is timed
+        for _ in range(args.warmup):
+            st = step_device()
+        barrier()
+        clk.mark_start()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             st = step_device()
@@ -249,6 +268,7 @@ def main():
         ctx.restore_state()
         ctx.select(); ctx.render()
         k2_ms = ctx.bench_process(20)
+        clk.mark_end()
     clocks = clk.summary()
 
     total_ms = float(sum(gpu_ms)); e2e_s = float(sum(e2e_t))

@@ -69,7 +69,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->have_ff = c->have_scene = c->emitters_ready = c->rendered = c->processed = c->keys_dirty = false;
 	c->parity = 0; c->selkey_valid = false;
 	c->graph_exec = nullptr; c->graph_batches = 0; c->graph_keep_items = false;
-	c->h_stage = nullptr; c->h_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
+	c->h_stage = nullptr; c->h_stage_bytes = 0; c->d_stage = nullptr; c->d_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
 	c->launches = 0;
 	c->split_limit = 1u << 22; c->inline_area_forced = false; c->setup_minb = 4;
@@ -132,6 +132,7 @@ int rad_destroy(rad_ctx* c) {
 	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->saved) cudaFree(c->saved);
+	if (c->d_stage) cudaFree(c->d_stage);
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -157,12 +158,31 @@ int rad_set_formfactors(rad_ctx* c, const float* ff, uint32_t n) {
 	return RAD_OK;
 }
 
-// AoS float[P*3] -> three planes
-static void to_planes(const float* src, float* dst, size_t P) {
-	for (size_t i = 0; i < P; i++) { dst[i] = src[3 * i]; dst[P + i] = src[3 * i + 1]; dst[2 * P + i] = src[3 * i + 2]; }
+// Host arrays travel in the reference's layouts (AoS float[P*3], float[P*12]); the conversion to / from the device
+// layouts (three planes, three float4 streams) runs on the GPU (layout.cu), so the host only does one straight copy
+// through the pinned staging buffer per array.
+static int h2d_aos3(rad_ctx* c, const float* src, float* dst_planes, size_t P) {
+	memcpy(c->h_stage, src, 3 * P * 4);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, c->h_stage, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
+	rad_launch_aos3_to_planes(c, c->d_stage, dst_planes, (uint32_t)P);
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));       // the staging buffers are reused by the next array
+	return RAD_OK;
 }
-static void from_planes(const float* src, float* dst, size_t P) {
-	for (size_t i = 0; i < P; i++) { dst[3 * i] = src[i]; dst[3 * i + 1] = src[P + i]; dst[3 * i + 2] = src[2 * P + i]; }
+static int d2h_aos3(rad_ctx* c, const float* src_planes, float* dst, size_t P) {
+	rad_launch_planes_to_aos3(c, src_planes, c->d_stage, (uint32_t)P);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_stage, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	memcpy(dst, c->h_stage, 3 * P * 4);
+	return RAD_OK;
+}
+static int stage_dev(rad_ctx* c, size_t bytes) {
+	int r = stage(c, bytes); if (r) return r;
+	if (c->d_stage_bytes >= bytes) return RAD_OK;
+	if (c->d_stage) cudaFree(c->d_stage);
+	c->d_stage = nullptr; c->d_stage_bytes = 0;
+	RAD_CUDA_TRY(c, cudaMalloc((void**)&c->d_stage, bytes));
+	c->d_stage_bytes = bytes;
+	return RAD_OK;
 }
 
 int rad_upload_state(rad_ctx* c, const float* rad3, const float* illum3) {
@@ -170,10 +190,9 @@ int rad_upload_state(rad_ctx* c, const float* rad3, const float* illum3) {
 	if (!c->have_scene) { c->err = "rad_upload_state: no scene"; return RAD_E_STATE; }
 	cudaSetDevice(c->cfg.device);
 	const size_t P = c->d.P;
-	int r = stage(c, 6 * P * 4); if (r) return r;
-	to_planes(rad3, c->h_stage, P); to_planes(illum3, c->h_stage + 3 * P, P);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.rad, c->h_stage, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.illum, c->h_stage + 3 * P, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
+	int r = stage_dev(c, 12 * P * 4); if (r) return r;
+	if ((r = h2d_aos3(c, rad3, c->d.rad, P))) return r;
+	if ((r = h2d_aos3(c, illum3, c->d.illum, P))) return r;
 	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.ctl, 0, sizeof(RadControl), c->stream));
 	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
 	c->selkey_valid = false; c->emitters_ready = c->rendered = c->processed = false;
@@ -185,20 +204,13 @@ int rad_upload_scene(rad_ctx* c, const float* verts12, const float* color3, cons
 	if (P < 1 || P > c->cfg.max_patches) { c->err = "rad_upload_scene: P out of range (max_patches)"; return RAD_E_ARG; }
 	cudaSetDevice(c->cfg.device);
 	drop_graph(c);
-	int r = stage(c, (size_t)P * 12 * 4); if (r) return r;
-	float* s = c->h_stage;
+	int r = stage_dev(c, (size_t)P * 12 * 4); if (r) return r;
 	// 48-byte quad records -> three float4 streams (coalesced 16 B loads per lane in the rasteriser)
-	for (size_t i = 0; i < P; i++) {
-		memcpy(s + 4 * i, verts12 + 12 * i, 16);
-		memcpy(s + 4 * (size_t)P + 4 * i, verts12 + 12 * i + 4, 16);
-		memcpy(s + 8 * (size_t)P + 4 * i, verts12 + 12 * i + 8, 16);
-	}
-	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.v0, s, (size_t)P * 16, cudaMemcpyHostToDevice, c->stream));
-	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.v1, s + 4 * (size_t)P, (size_t)P * 16, cudaMemcpyHostToDevice, c->stream));
-	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.v2, s + 8 * (size_t)P, (size_t)P * 16, cudaMemcpyHostToDevice, c->stream));
+	memcpy(c->h_stage, verts12, (size_t)P * 48);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, c->h_stage, (size_t)P * 48, cudaMemcpyHostToDevice, c->stream));
+	rad_launch_split_quads(c, c->d_stage, P);
 	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-	to_planes(color3, s, P);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync((void*)c->d.color, s, (size_t)P * 12, cudaMemcpyHostToDevice, c->stream));
+	if ((r = h2d_aos3(c, color3, (float*)c->d.color, P))) return r;
 	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.F, 0, (size_t)c->d.k * P * 4, c->stream));
 	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
 	c->d.P = P;
@@ -211,12 +223,9 @@ int rad_download_state(rad_ctx* c, float* rad3, float* illum3) {
 	if (!c->have_scene) { c->err = "rad_download_state: no scene"; return RAD_E_STATE; }
 	cudaSetDevice(c->cfg.device);
 	const size_t P = c->d.P;
-	int r = stage(c, 6 * P * 4); if (r) return r;
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d.rad, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage + 3 * P, c->d.illum, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
-	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-	from_planes(c->h_stage, rad3, P); from_planes(c->h_stage + 3 * P, illum3, P);
-	return RAD_OK;
+	int r = stage_dev(c, 12 * P * 4); if (r) return r;
+	if ((r = d2h_aos3(c, c->d.rad, rad3, P))) return r;
+	return d2h_aos3(c, c->d.illum, illum3, P);
 }
 
 static int need_ready(rad_ctx* c, const char* who) {
@@ -527,21 +536,14 @@ int rad_batch_partial(rad_ctx* c) {
 int rad_read_delta(rad_ctx* c, float* dB3) {
 	if (!c || !dB3) return RAD_E_ARG;
 	cudaSetDevice(c->cfg.device);
-	const size_t P = c->d.P;
-	int r = stage(c, 3 * P * 4); if (r) return r;
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d.dB, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
-	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-	from_planes(c->h_stage, dB3, P);
-	return RAD_OK;
+	int r = stage_dev(c, 12 * (size_t)c->d.P * 4); if (r) return r;
+	return d2h_aos3(c, c->d.dB, dB3, c->d.P);
 }
 int rad_write_delta(rad_ctx* c, const float* dB3) {
 	if (!c || !dB3) return RAD_E_ARG;
 	cudaSetDevice(c->cfg.device);
-	const size_t P = c->d.P;
-	int r = stage(c, 3 * P * 4); if (r) return r;
-	to_planes(dB3, c->h_stage, P);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d.dB, c->h_stage, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
-	return sync_check(c);
+	int r = stage_dev(c, 12 * (size_t)c->d.P * 4); if (r) return r;
+	return h2d_aos3(c, dB3, c->d.dB, c->d.P);
 }
 int rad_batch_finish(rad_ctx* c, float* last_energy_len) {
 	int r = need_ready(c, "rad_batch_finish"); if (r) return r;

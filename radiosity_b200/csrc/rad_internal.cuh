@@ -81,7 +81,8 @@ struct rad_ctx {
 	cudaGraphExec_t graph_exec; uint32_t graph_batches; bool graph_keep_items; uint32_t graph_launches, graph_parity0;
 	float* saved;                 // device snapshot of (B, I) for rad_save_state / rad_restore_state
 	// host staging
-	float* h_stage; size_t h_stage_bytes;
+	float* h_stage; size_t h_stage_bytes;      // pinned
+	float* d_stage; size_t d_stage_bytes;      // device mirror of the staging buffer
 	// multi-GPU
 	int rank, world; void* nccl_comm; bool partition_only;
 	uint32_t launches;            // kernels launched since last reset
@@ -108,6 +109,9 @@ void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB
 void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update
 void rad_launch_argmax(rad_ctx* c);                 // k==1: prime selkey[parity] from the current B
 void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out);
+void rad_launch_aos3_to_planes(rad_ctx* c, const float* aos, float* planes, uint32_t P);   // layout.cu
+void rad_launch_planes_to_aos3(rad_ctx* c, const float* planes, float* aos, uint32_t P);
+void rad_launch_split_quads(rad_ctx* c, const float* verts12, uint32_t P);
 
 #define RAD_CUDA_TRY(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
 	(c)->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return RAD_E_CUDA; } } while (0)
