@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
 // key = (bits(|B|^2) << 32 | ~id): unique, and descending key order == (energy desc, id asc).  Every block sorts a
 // chunk of 2048 keys in shared memory and keeps its best 64; levels repeat (P -> P/32 -> ...) until one block is
 // left, which writes the emitter list.  Exact and deterministic; 2 launches for 16 k patches, 3 for 1 M.
-constexpr int kTopChunk = 2048, kTopKeep = 64, kTopThreads = 256;
+constexpr int kTopChunk = 2048, kTopKeep = 64, kTopThreads = 1024;   // one compare-exchange per thread per bitonic stage
 
 template <bool FIRST>
 __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const unsigned long long* __restrict__ in, uint32_t n_in,
