@@ -371,11 +371,18 @@ static inline int edge_bias(int ax, int ay, int bx, int by) {   // 0 for top/lef
 
 static const uint64_t kClearKey = 0xFFFFFFFFFFFFFFFFull;
 
+// optional work statistics (orc_raster_stats): [0] triangles reaching raster_tri, [1] after the frustum reject, [2] front-facing,
+// [3] with a non-empty scissored bbox, [4] bbox pixels, [5] covered fragments, [6] fragments that won the depth test when drawn,
+// [8..8+20) histogram of bbox area by floor(log2(area))
+static uint64_t* g_stats = NULL;
+
 static void raster_tri(const CV t[3], const Rect& vp, const Rect& sc, int W, uint32_t id1, uint64_t* keys) {
 	// exact trivial reject: a triangle wholly beyond one viewport edge cannot produce a pixel inside the
 	// scissor (x > w  =>  x/w >= 1  =>  every snapped X lies at or beyond the viewport edge); w > 0 here
+	if (g_stats) g_stats[0]++;
 	if ((t[0].x > t[0].w && t[1].x > t[1].w && t[2].x > t[2].w) || (t[0].x < -t[0].w && t[1].x < -t[1].w && t[2].x < -t[2].w) ||
 	    (t[0].y > t[0].w && t[1].y > t[1].w && t[2].y > t[2].w) || (t[0].y < -t[0].w && t[1].y < -t[1].w && t[2].y < -t[2].w)) return;
+	if (g_stats) g_stats[1]++;
 	int X[3], Y[3]; float Z[3];
 	float hw = (float)vp.w * 0.5f, hh = (float)vp.h * 0.5f;
 	float ox = (float)vp.x + hw, oy = (float)vp.y + hh;
@@ -388,11 +395,13 @@ static void raster_tri(const CV t[3], const Rect& vp, const Rect& sc, int W, uin
 	}
 	int64_t area2 = edge_fn(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
 	if (area2 <= 0) return;
+	if (g_stats) g_stats[2]++;
 	int minx = std::min(X[0], std::min(X[1], X[2])), maxx = std::max(X[0], std::max(X[1], X[2]));
 	int miny = std::min(Y[0], std::min(Y[1], Y[2])), maxy = std::max(Y[0], std::max(Y[1], Y[2]));
 	int px0 = std::max((minx - 128 + 255) >> 8, sc.x), px1 = std::min((maxx - 128) >> 8, sc.x + sc.w - 1);
 	int py0 = std::max((miny - 128 + 255) >> 8, sc.y), py1 = std::min((maxy - 128) >> 8, sc.y + sc.h - 1);
 	if (px0 > px1 || py0 > py1) return;
+	if (g_stats) { g_stats[3]++; uint64_t a = (uint64_t)(px1 - px0 + 1) * (py1 - py0 + 1); g_stats[4] += a; int l = 0; while ((a >> (l + 1)) != 0) l++; g_stats[8 + (l < 19 ? l : 19)]++; }
 	int b0 = edge_bias(X[1], Y[1], X[2], Y[2]), b1 = edge_bias(X[2], Y[2], X[0], Y[0]), b2 = edge_bias(X[0], Y[0], X[1], Y[1]);
 	float inv_area = 1.0f / (float)area2;
 	float dz1 = Z[1] - Z[0], dz2 = Z[2] - Z[0];
@@ -416,6 +425,7 @@ static void raster_tri(const CV t[3], const Rect& vp, const Rect& sc, int W, uin
 			uint32_t d = (uint32_t)lrintf(z * 16777215.0f);
 			if (d >= 0xFFFFFFu) continue;                 // GL_LESS against the cleared 1.0
 			uint64_t key = ((uint64_t)d << 32) | id1;       // LESS + draw order == min over (depth, id)
+			if (g_stats) { g_stats[5]++; if (key < krow[px]) g_stats[6]++; }
 			if (key < krow[px]) krow[px] = key;
 		}
 	}
@@ -824,6 +834,16 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 	}
 	if (last_energy_len) *last_energy_len = last_len;
 	return done;
+}
+
+// work statistics of one hemicube (single thread); out[28]
+void orc_raster_stats(unsigned P, const float* verts, unsigned shooter, unsigned N, uint64_t* out) {
+	size_t RES = (size_t)(2 * N) * (size_t)(unsigned)(N * 1.5);
+	std::vector<uint64_t> keys(RES);
+	memset(out, 0, 28 * sizeof(uint64_t));
+	g_stats = out;
+	render_hemicube_keys(P, verts, shooter, (int)N, keys.data(), 1);
+	g_stats = NULL;
 }
 
 int orc_max_threads() {

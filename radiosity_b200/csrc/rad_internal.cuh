@@ -12,6 +12,7 @@
 #define RAD_NFACES 5
 #define RAD_CLEAR_KEY 0xFFFFFFFFFFFFFFFFull
 #define RAD_TILE 32               // chunk edge in pixels (chunks are bbox-relative)
+#define RAD_SMALL_STEPS 64         // quarter-warp walk: rows x ceil(width / 8) steps at most
 
 struct RadBigTri {                // one screen-space triangle parked for tile processing (64 B)
 	int X0, Y0, X1, Y1, X2, Y2;   // snapped window coordinates, 8 sub-pixel bits
@@ -27,11 +28,13 @@ struct RadControl {               // small device-resident control block
 	uint32_t q_tris;              // tile queue: triangles parked
 	uint32_t q_entries;           // tile queue: (triangle, tile) entries
 	uint32_t q_overflow;
+	uint32_t q_small;             // small-triangle queue: records (one quarter warp each)
 	uint32_t stopped;             // |lastEnergy| < 0.1 seen
 	float last_energy_len;
 	uint32_t batches_done;
 	uint32_t shots_done;
-	uint32_t pad;
+	uint32_t pad;                 // triangles parked by the last batch (statistics)
+	uint32_t pad2[3];
 };
 
 struct RadEmitter {               // per hemicube slot
@@ -63,6 +66,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	RadControl* ctl;
 	RadBigTri* q_tri; RadQueueEntry* q_ent;
 	uint32_t q_tri_cap, q_ent_cap;
+	RadBigTri* q_sm; uint32_t q_sm_cap;   // small-triangle queue (bbox steps <= RAD_SMALL_STEPS, int32 walk)
 	uint32_t* ework;              // [max(P,64)] scratch (emitter id staging)
 	unsigned long long* cand0; unsigned long long* cand1;   // top-k tournament candidates, ceil(P/2048)*64 keys each
 	const float* proj;            // [16]

@@ -10,7 +10,8 @@
 //                          small bbox (<= 32 px) -> the owning lane walks it alone
 //                          anything larger       -> parked in the chunk queue (bbox-relative 32x32 pixel chunks,
 //                                                   queue slots claimed with one atomic per warp)
-//   raster_chunks_kernel persistent warps drain the chunk queue, one warp per chunk, 8x4 pixels per step
+//   raster_queue_kernel  persistent warps drain the two queues: small triangles four per warp (a quarter warp each,
+//                        8x1 pixel rows, int32 walk), chunks one warp each, 8x4 pixels per step
 //   resolve_kernel       64-bit keys -> uint32 item buffer (id+1), keys reset for the next batch
 // Visibility is a deterministic 64-bit atomicMin of (depth24 << 32 | id+1) per pixel: equal to GL_LESS
 // with patches drawn in id order (Main.cpp:715-720), independent of thread scheduling.
@@ -244,7 +245,7 @@ __device__ __forceinline__ int setup_tri(const PV& a, const PV& b, const PV& c, 
 #define FULL 0xFFFFFFFFu
 
 // One triangle per lane (area == 0: none).  Small bboxes are walked by the owning lane; everything else is parked
-// in the chunk queue — bbox-relative chunks of RAD_TILE x RAD_TILE pixels, one warp each in raster_chunks_kernel —
+// in the chunk queue — bbox-relative chunks of RAD_TILE x RAD_TILE pixels, one warp each in raster_queue_kernel —
 // so that no warp of the set-up kernel ever carries a long pixel loop (load balance).  Queue slots are claimed
 // with one atomic per warp.
 __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
@@ -269,15 +270,33 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 			}
 		}
 	}
-	const bool big = area > (int)D.inline_area;
-	const unsigned mb = __ballot_sync(FULL, big);
+	// everything else is parked: triangles whose bbox walk is short and fits int32 go to the small queue (a quarter
+	// warp each in raster_queue_kernel), the rest to the chunk queue
+	const int bw = (tr.bx >> 16) - (tr.bx & 0xFFFF) + 1, bh = (tr.by >> 16) - (tr.by & 0xFFFF) + 1;
+	const bool parked = area > (int)D.inline_area;
+	const bool small = parked && bh * ((bw + 7) >> 3) <= RAD_SMALL_STEPS && fits32(tr, tr.bx & 0xFFFF, tr.by & 0xFFFF, max(bw, bh) + 8);   // +8: lanes start up to 7 px right of the origin
+	const bool big = parked && !small;
+	const unsigned ms = __ballot_sync(FULL, small), mb = __ballot_sync(FULL, big);
+	if ((ms | mb) == 0) return;
+	RadBigTri r;
+	if (parked) {
+		r.X0 = tr.X0; r.Y0 = tr.Y0; r.X1 = tr.X1; r.Y1 = tr.Y1; r.X2 = tr.X2; r.Y2 = tr.Y2;
+		r.z0 = tr.z0; r.dz1 = tr.dz1; r.dz2 = tr.dz2; r.inv_area = tr.inv_area;
+		r.id1 = id1; r.slot = slot;
+		r.px0 = tr.bx & 0xFFFF; r.px1 = tr.bx >> 16; r.py0 = tr.by & 0xFFFF; r.py1 = tr.by >> 16;
+	}
+	if (ms) {
+		uint32_t sbase = 0;
+		if (lane == 0) sbase = atomicAdd(&D.ctl->q_small, (uint32_t)__popc(ms));
+		sbase = __shfl_sync(FULL, sbase, 0);
+		if (small) {
+			const uint32_t si = sbase + __popc(ms & ((1u << lane) - 1u));
+			if (si < D.q_sm_cap) D.q_sm[si] = r; else D.ctl->q_overflow = 1;
+		}
+	}
 	if (mb == 0) return;
 	int ncx = 0, ncy = 0, nent = 0;
-	if (big) {
-		ncx = ((tr.bx >> 16) - (tr.bx & 0xFFFF)) / RAD_TILE + 1;
-		ncy = ((tr.by >> 16) - (tr.by & 0xFFFF)) / RAD_TILE + 1;
-		nent = ncx * ncy;
-	}
+	if (big) { ncx = (bw - 1) / RAD_TILE + 1; ncy = (bh - 1) / RAD_TILE + 1; nent = ncx * ncy; }
 	int pre = nent;                               // inclusive warp scan of the entry counts
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += o; }
@@ -289,11 +308,6 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 	const uint32_t ti = tbase + __popc(mb & ((1u << lane) - 1u));
 	uint32_t e = ebase + (uint32_t)(pre - nent);
 	if (ti >= D.q_tri_cap || e + nent > D.q_ent_cap) { D.ctl->q_overflow = 1; return; }
-	RadBigTri r;
-	r.X0 = tr.X0; r.Y0 = tr.Y0; r.X1 = tr.X1; r.Y1 = tr.Y1; r.X2 = tr.X2; r.Y2 = tr.Y2;
-	r.z0 = tr.z0; r.dz1 = tr.dz1; r.dz2 = tr.dz2; r.inv_area = tr.inv_area;
-	r.id1 = id1; r.slot = slot;
-	r.px0 = tr.bx & 0xFFFF; r.px1 = tr.bx >> 16; r.py0 = tr.by & 0xFFFF; r.py1 = tr.by >> 16;
 	D.q_tri[ti] = r;
 	for (int cy = 0; cy < ncy; cy++)
 		for (int cx = 0; cx < ncx; cx++) {
@@ -418,12 +432,46 @@ __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 	}
 }
 
-// persistent warps drain the (triangle, chunk) queue: one warp per chunk of at most RAD_TILE x RAD_TILE pixels,
-// walked in 8x4 pixel blocks
-__global__ void __launch_bounds__(128) raster_chunks_kernel(RadDev D) {
-	const uint32_t nent = min(D.ctl->q_entries, D.q_ent_cap);
+// persistent warps drain both queues.
+//  1. small queue: FOUR triangles per warp step, one quarter warp (8 lanes) each, walking the bbox in 8x1 pixel rows
+//     with int32 incremental edge functions (guaranteed to fit by the set-up kernel);
+//  2. chunk queue: one warp per (triangle, chunk) of at most RAD_TILE x RAD_TILE pixels, 8x4 pixels per step.
+__global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	{
+		const uint32_t nsm = min(D.ctl->q_small, D.q_sm_cap);
+		const int sub = lane >> 3, l8 = lane & 7;
+		for (uint32_t base = gw * 4; base < nsm; base += nw * 4) {
+			const uint32_t i = base + sub;
+			int steps = 0, cw = 1, px0 = 0, px1 = -1, py0 = 0;
+			Tri w; EdgeSet32 E; uint32_t id1 = 0; unsigned long long* keys = nullptr;
+			if (i < nsm) {
+				const RadBigTri r = D.q_sm[i];
+				w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
+				w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
+				px0 = r.px0; px1 = r.px1; py0 = r.py0; id1 = r.id1;
+				cw = (r.px1 - r.px0 + 8) >> 3;
+				steps = (r.py1 - r.py0 + 1) * cw;
+				keys = D.keys + (size_t)(r.slot - D.kbase) * D.RES;
+				edges_at32(w, px0 + l8, py0, E);
+			}
+			int msteps = steps;
+			msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 8)); msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 16));
+			int e0 = E.e0, e1 = E.e1, e2 = E.e2;          // current pixel
+			int r0 = E.e0, r1 = E.e1, r2 = E.e2;          // start of the current row
+			int col = 0, py = py0;
+			for (int s = 0; s < msteps; s++) {
+				if (s < steps) {
+					const int px = px0 + col * 8 + l8;
+					if (px <= px1 && (e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, id1, keys + (size_t)py * D.W + px);
+					if (++col == cw) { col = 0; py++; r0 += E.sy0; r1 += E.sy1; r2 += E.sy2; e0 = r0; e1 = r1; e2 = r2; }
+					else { e0 += 8 * E.sx0; e1 += 8 * E.sx1; e2 += 8 * E.sx2; }
+				}
+			}
+		}
+	}
+	const uint32_t nent = min(D.ctl->q_entries, D.q_ent_cap);
 	for (uint32_t i = gw; i < nent; i += nw) {
 		const RadQueueEntry e = D.q_ent[i];
 		if (e.tri >= D.q_tri_cap) continue;
@@ -469,8 +517,8 @@ __global__ void __launch_bounds__(128) raster_chunks_kernel(RadDev D) {
 // recycles the chunk queue between hemicube groups of one batch (see rad_launch_raster)
 __global__ void queue_reset_kernel(RadDev D, int first_group) {
 	if (threadIdx.x == 0) {
-		D.ctl->pad = (first_group ? 0u : D.ctl->pad) + D.ctl->q_tris;
-		D.ctl->q_tris = 0; D.ctl->q_entries = 0;
+		D.ctl->pad = (first_group ? 0u : D.ctl->pad) + D.ctl->q_tris + D.ctl->q_small;
+		D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0;
 	}
 }
 
@@ -478,7 +526,7 @@ __global__ void queue_reset_kernel(RadDev D, int first_group) {
 // separate clear pass is needed in the steady state.  Also recycles the tile queue.
 __global__ void __launch_bounds__(256) resolve_kernel(RadDev D, int reset) {
 	const uint32_t slot = D.h0 + blockIdx.y;
-	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && D.ctl->q_tris) { D.ctl->pad = D.ctl->q_tris; D.ctl->q_tris = 0; D.ctl->q_entries = 0; }
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small)) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; }
 	unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
 	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.RES; i += gridDim.x * blockDim.x) {
@@ -508,7 +556,7 @@ void rad_launch_camera(rad_ctx* c, int sel_parity) {
 // parked both of its triangles (in practice well under half of them do)
 static uint32_t queue_group(const RadDev& D) {
 	const uint32_t nslots = D.h1 - D.h0;
-	uint64_t g = (uint64_t)D.q_tri_cap / (2ull * (D.P ? D.P : 1));
+	uint64_t g = (uint64_t)min(D.q_tri_cap, D.q_sm_cap) / (2ull * (D.P ? D.P : 1));
 	if (g < 1) g = 1;
 	return g > nslots ? nslots : (uint32_t)g;
 }
@@ -542,7 +590,7 @@ static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 static void launch_chunks(rad_ctx* c, uint32_t kbase) {
 	RadDev D = c->d;
 	D.kbase = kbase;
-	raster_chunks_kernel<<<148 * 8, 128, 0, c->stream>>>(D);
+	raster_queue_kernel<<<148 * 8, 128, 0, c->stream>>>(D);
 	c->launches++;
 }
 
