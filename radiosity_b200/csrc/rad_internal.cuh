@@ -12,7 +12,7 @@
 #define RAD_NFACES 5
 #define RAD_CLEAR_KEY 0xFFFFFFFFFFFFFFFFull
 #define RAD_TILE 32               // chunk edge in pixels (chunks are bbox-relative)
-#define RAD_SMALL_STEPS 64         // quarter-warp walk: rows x ceil(width / 8) steps at most
+#define RAD_SMALL_STEPS 64         // quarter-warp walk: ceil(bbox pixels / 8) steps at most
 
 struct RadBigTri {                // one screen-space triangle parked for tile processing (64 B)
 	int X0, Y0, X1, Y1, X2, Y2;   // snapped window coordinates, 8 sub-pixel bits

@@ -274,7 +274,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 	// warp each in raster_queue_kernel), the rest to the chunk queue
 	const int bw = (tr.bx >> 16) - (tr.bx & 0xFFFF) + 1, bh = (tr.by >> 16) - (tr.by & 0xFFFF) + 1;
 	const bool parked = area > (int)D.inline_area;
-	const bool small = parked && bh * ((bw + 7) >> 3) <= RAD_SMALL_STEPS && fits32(tr, tr.bx & 0xFFFF, tr.by & 0xFFFF, max(bw, bh) + 8);   // +8: lanes start up to 7 px right of the origin
+	const bool small = parked && bw * bh <= 8 * RAD_SMALL_STEPS && fits32(tr, tr.bx & 0xFFFF, tr.by & 0xFFFF, max(bw, bh) + 8);   // +8: lanes start up to 7 px right of the origin
 	const bool big = parked && !small;
 	const unsigned ms = __ballot_sync(FULL, small), mb = __ballot_sync(FULL, big);
 	if ((ms | mb) == 0) return;
@@ -444,30 +444,30 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 		const int sub = lane >> 3, l8 = lane & 7;
 		for (uint32_t base = gw * 4; base < nsm; base += nw * 4) {
 			const uint32_t i = base + sub;
-			int steps = 0, cw = 1, px0 = 0, px1 = -1, py0 = 0;
+			// the bbox is walked as ONE linear run of w*h pixels, 8 per step, so narrow boxes do not waste lanes
+			int npx = 0, w8 = 1, px0 = 0, py0 = 0, q8 = 0, r8 = 0;
 			Tri w; EdgeSet32 E; uint32_t id1 = 0; unsigned long long* keys = nullptr;
 			if (i < nsm) {
 				const RadBigTri r = D.q_sm[i];
 				w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
 				w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
-				px0 = r.px0; px1 = r.px1; py0 = r.py0; id1 = r.id1;
-				cw = (r.px1 - r.px0 + 8) >> 3;
-				steps = (r.py1 - r.py0 + 1) * cw;
+				px0 = r.px0; py0 = r.py0; id1 = r.id1;
+				w8 = r.px1 - r.px0 + 1;
+				npx = w8 * (r.py1 - r.py0 + 1);
+				q8 = 8 / w8; r8 = 8 - q8 * w8;
 				keys = D.keys + (size_t)(r.slot - D.kbase) * D.RES;
-				edges_at32(w, px0 + l8, py0, E);
+				edges_at32(w, px0, py0, E);               // biased edge values at the bbox origin; per-pixel steps in sx / sy
 			}
-			int msteps = steps;
+			int msteps = (npx + 7) >> 3;
 			msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 8)); msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 16));
-			int e0 = E.e0, e1 = E.e1, e2 = E.e2;          // current pixel
-			int r0 = E.e0, r1 = E.e1, r2 = E.e2;          // start of the current row
-			int col = 0, py = py0;
+			int idx = l8, y = l8 / w8, x = l8 - y * w8;
 			for (int s = 0; s < msteps; s++) {
-				if (s < steps) {
-					const int px = px0 + col * 8 + l8;
-					if (px <= px1 && (e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, id1, keys + (size_t)py * D.W + px);
-					if (++col == cw) { col = 0; py++; r0 += E.sy0; r1 += E.sy1; r2 += E.sy2; e0 = r0; e1 = r1; e2 = r2; }
-					else { e0 += 8 * E.sx0; e1 += 8 * E.sx1; e2 += 8 * E.sx2; }
+				if (idx < npx) {
+					const int e0 = E.e0 + x * E.sx0 + y * E.sy0, e1 = E.e1 + x * E.sx1 + y * E.sy1, e2 = E.e2 + x * E.sx2 + y * E.sy2;
+					if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, id1, keys + (size_t)(py0 + y) * D.W + (px0 + x));
 				}
+				idx += 8; x += r8; y += q8;
+				if (x >= w8) { x -= w8; y++; }
 			}
 		}
 	}
