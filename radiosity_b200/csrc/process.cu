@@ -15,8 +15,8 @@
 //
 // Two entry points: process_kernel<false> reads the uint32 item buffer (the API seam of
 // rad_process_hemicubes / rad_bench_process); process_kernel<true> is the fused steady-state form used
-// by rad_shoot: it reads the rasteriser's 64-bit keys directly, resets them for the next batch and
-// only materialises the item buffer when asked to.
+// by rad_shoot: it reads the rasteriser's 64-bit keys directly (a key counts iff its top byte is the group's
+// epoch tag, so nothing is cleared) and only materialises the item buffer when asked to.
 #include "rad_internal.cuh"
 
 namespace {
@@ -51,7 +51,7 @@ __device__ __forceinline__ void process4(const uint4 id, const float4 f, int lan
 	segmented_add(cur, acc, lane, F, P);
 }
 
-__device__ __forceinline__ uint32_t key_id(unsigned long long k) { return k == RAD_CLEAR_KEY ? 0u : (uint32_t)(k & 0xFFFFFFFFull); }
+__device__ __forceinline__ uint32_t key_id(unsigned long long k, uint32_t tag) { return (uint32_t)(k >> 56) == tag ? (uint32_t)(k & 0xFFFFFFFFull) : 0u; }
 
 template <bool FROM_KEYS>
 __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) 
 	const uint32_t nsteps = D.RES >> 7;               // 128 pixels per warp step; RES = 3 N^2 is a multiple of 768
 	float* __restrict__ F = D.F + (size_t)slot * D.P;
 	const float4* __restrict__ ff4 = reinterpret_cast<const float4*>(D.ff);
-	ulonglong2* __restrict__ keys2 = reinterpret_cast<ulonglong2*>(D.keys + (size_t)(slot - D.kbase) * D.RES);
+	const ulonglong2* __restrict__ keys2 = reinterpret_cast<const ulonglong2*>(D.keys + (size_t)(slot - D.kbase) * D.RES);
 	uint4* __restrict__ items4 = reinterpret_cast<uint4*>(D.items + (size_t)slot * D.RES);
 
 	for (uint32_t g0 = gw * kUnroll; g0 < nsteps; g0 += nw * kUnroll) {
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) 
 				const uint32_t q = (g << 5) + lane;   // index of this lane's 4-pixel group
 				if (FROM_KEYS) {
 					const ulonglong2 k0 = keys2[2 * (size_t)q], k1 = keys2[2 * (size_t)q + 1];
-					id[u] = make_uint4(key_id(k0.x), key_id(k0.y), key_id(k1.x), key_id(k1.y));
+					id[u] = make_uint4(key_id(k0.x, D.tag), key_id(k0.y, D.tag), key_id(k1.x, D.tag), key_id(k1.y, D.tag));
 				} else {
 					id[u] = __ldcs(items4 + q);
 				}
@@ -89,9 +89,7 @@ __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) 
 			if (g < nsteps) {
 				const uint32_t q = (g << 5) + lane;
 				if (FROM_KEYS) {
-					const ulonglong2 clr = make_ulonglong2(RAD_CLEAR_KEY, RAD_CLEAR_KEY);
-					keys2[2 * (size_t)q] = clr; keys2[2 * (size_t)q + 1] = clr;
-					if (keep_items) items4[q] = id[u];
+					if (keep_items) items4[q] = id[u];   // keys are not cleared: the next render uses a smaller epoch tag
 				}
 				process4(id[u], v[u], lane, F, D.P);
 			}

@@ -71,7 +71,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->graph_exec = nullptr; c->graph_batches = 0; c->graph_keep_items = false;
 	c->h_stage = nullptr; c->h_stage_bytes = 0; c->d_stage = nullptr; c->d_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
-	c->launches = 0;
+	c->launches = 0; c->epoch = 254;
 	c->split_limit = 1u << 22; c->inline_area_forced = false; c->setup_minb = 4;
 	if (const char* e = getenv("RAD_SETUP_MINB")) c->setup_minb = atoi(e);   // tuning knob
 	if (const char* e = getenv("RAD_SPLIT_LIMIT")) c->split_limit = strtoull(e, nullptr, 10);   // tuning knob
@@ -271,7 +271,6 @@ int rad_set_emitters(rad_ctx* c, const uint32_t* ids, uint32_t n) {
 int rad_render_hemicubes(rad_ctx* c) {
 	int r = need_ready(c, "rad_render_hemicubes"); if (r) return r;
 	if (!c->emitters_ready) { c->err = "rad_render_hemicubes: call rad_select / rad_set_emitters first"; return RAD_E_STATE; }
-	rad_launch_clear_keys(c);
 	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.items, 0, (size_t)c->d.k * c->d.RES * 4, c->stream));   // glClear: NULL emitters stay black
 	rad_launch_raster(c);
 	rad_launch_resolve(c, /*reset=*/false);       // keys stay readable for rad_read_depthbuffer
@@ -355,7 +354,9 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 				cudaGraph_t g = nullptr;
 				const uint32_t parity0 = c->parity; const bool sk0 = c->selkey_valid; const uint32_t l0 = c->launches;
 				RAD_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+				rad_launch_clear_keys(c);          // a replay re-uses the captured epoch tags: start every replay from cleared keys
 				for (uint32_t b = 0; b < GB; b++) enqueue_batch(c, keep);
+				c->graph_epoch_after = c->epoch;
 				RAD_CUDA_TRY(c, cudaStreamEndCapture(c->stream, &g));
 				RAD_CUDA_TRY(c, cudaGraphInstantiate(&c->graph_exec, g, 0));
 				cudaGraphDestroy(g);
@@ -368,6 +369,7 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 				RAD_CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
 				launches += c->graph_launches;
 				done += GB;
+				c->epoch = c->graph_epoch_after;
 				if (c->d.k == 1) c->selkey_valid = true;
 				if (stop_test) { RadControl t; if ((r = read_ctl(c, &t))) return r; stopped = t.stopped != 0; }
 			}

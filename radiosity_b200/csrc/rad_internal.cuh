@@ -50,6 +50,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	uint32_t P, N, W, H, RES, k;
 	uint32_t h0, h1;              // hemicube slots this rank renders/processes (kernels: slots of this launch)
 	uint32_t kbase;               // slot whose keys live in key buffer 0 (fused path recycles L2-resident key buffers per group)
+	uint32_t tag;                 // epoch tag (top byte of every key written / accepted by this launch)
 	uint32_t inline_area;         // bbox area (px) up to which the owning lane rasterises alone; larger -> chunk queue
 	float reflectivity;
 	const float4* v0; const float4* v1; const float4* v2;   // verts: (v1.xyz,v2.x) (v2.yz,v3.xy) (v3.z,v4.xyz)
@@ -57,7 +58,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	float* rad;                   // [3][P] planes  (B, unshot)
 	float* illum;                 // [3][P] planes  (I, shot)
 	const float* ff;              // [RES]
-	unsigned long long* keys;     // [k][RES] (depth24 << 32 | id+1), RAD_CLEAR_KEY when empty
+	unsigned long long* keys;     // [k][RES] (epoch tag << 56 | depth24 << 32 | id+1); empty = any other top byte
 	uint32_t* items;              // [k][RES] id+1
 	float* F;                     // [k][P]
 	float* dB;                    // [3][P] partial received energy (multi-GPU)
@@ -90,6 +91,8 @@ struct rad_ctx {
 	// multi-GPU
 	int rank, world; void* nccl_comm; bool partition_only;
 	uint32_t launches;            // kernels launched since last reset
+	uint32_t graph_epoch_after;   // epoch value after one replay of the captured graph
+	uint32_t epoch;               // next key epoch tag (254 .. 1, decreasing; 0 = clear the key buffers first)
 	bool inline_area_forced;      // RAD_INLINE_AREA set: do not auto-tune the inline tier
 	int setup_minb;               // min resident CTAs/SM the set-up kernel variant was compiled for (register cap)
 	uint64_t split_limit;         // P * hemicubes below which the set-up kernel runs one lane per (patch, face)
@@ -104,6 +107,7 @@ void rad_launch_raster_tiles_only(rad_ctx* c);
 void rad_launch_set_emitters(rad_ctx* c, const uint32_t* d_ids, uint32_t n);
 void rad_launch_resolve(rad_ctx* c, bool reset);    // keys -> items (+ keys reset)
 void rad_launch_clear_keys(rad_ctx* c);
+uint32_t rad_next_tag(rad_ctx* c);
 void rad_launch_process(rad_ctx* c);                // items -> F
 void rad_launch_resolve_process(rad_ctx* c, bool keep_items);   // fused (all slots, keys indexed from kbase = h0)
 void rad_launch_raster_process(rad_ctx* c, bool keep_items);    // steady state: per L2-sized hemicube group raster -> fused process

@@ -178,12 +178,12 @@ __device__ __forceinline__ void edges_at(const Tri& t, int px, int py, EdgeSet& 
 	E.sx1 = -(long long)(t.Y0 - t.Y2) * 256; E.sy1 = (long long)(t.X0 - t.X2) * 256;
 	E.sx2 = -(long long)(t.Y1 - t.Y0) * 256; E.sy2 = (long long)(t.X1 - t.X0) * 256;
 }
-__device__ __forceinline__ void shade_covered(const Tri& t, long long e1, long long e2, uint32_t id1, unsigned long long* __restrict__ a) {
+__device__ __forceinline__ void shade_covered(const Tri& t, long long e1, long long e2, uint32_t id1, unsigned long long* __restrict__ a, uint32_t tagsh) {
 	const float l1 = (float)e1 * t.inv_area, l2 = (float)e2 * t.inv_area;
 	float z = (t.z0 + l1 * t.dz1) + l2 * t.dz2;
 	z = fminf(fmaxf(z, 0.0f), 1.0f);
 	const uint32_t dq = __float2uint_rn(z * 16777215.0f);
-	if (dq < 0xFFFFFFu) atomicMin(a, ((unsigned long long)dq << 32) | id1);
+	if (dq < 0xFFFFFFu) atomicMin(a, ((unsigned long long)(tagsh | dq) << 32) | id1);
 }
 
 // 32-bit form of the same edge functions for triangles that are small around the walk origin: with R = largest
@@ -208,12 +208,12 @@ __device__ __forceinline__ void edges_at32(const Tri& t, int px, int py, EdgeSet
 	E.sx1 = -(y0 - y2) * 256; E.sy1 = (x0 - x2) * 256;
 	E.sx2 = -(y1 - y0) * 256; E.sy2 = (x1 - x0) * 256;
 }
-__device__ __forceinline__ void shade_covered32(const Tri& t, int e1, int e2, uint32_t id1, unsigned long long* __restrict__ a) {
+__device__ __forceinline__ void shade_covered32(const Tri& t, int e1, int e2, uint32_t id1, unsigned long long* __restrict__ a, uint32_t tagsh) {
 	const float l1 = (float)e1 * t.inv_area, l2 = (float)e2 * t.inv_area;
 	float z = (t.z0 + l1 * t.dz1) + l2 * t.dz2;
 	z = fminf(fmaxf(z, 0.0f), 1.0f);
 	const uint32_t dq = __float2uint_rn(z * 16777215.0f);
-	if (dq < 0xFFFFFFu) atomicMin(a, ((unsigned long long)dq << 32) | id1);
+	if (dq < 0xFFFFFFu) atomicMin(a, ((unsigned long long)(tagsh | dq) << 32) | id1);
 }
 
 // perspective divide (reciprocal, then multiply), viewport, 8-bit sub-pixel snap
@@ -250,6 +250,7 @@ __device__ __forceinline__ int setup_tri(const PV& a, const PV& b, const PV& c, 
 // with one atomic per warp.
 __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
                                          unsigned long long* __restrict__ keys) {
+	const uint32_t tagsh = D.tag << 24;
 	if (area > 0 && area <= (int)D.inline_area) {
 		const int px0 = tr.bx & 0xFFFF, px1 = tr.bx >> 16, py0 = tr.by & 0xFFFF, py1 = tr.by >> 16;
 		if (fits32(tr, px0, py0, max(px1 - px0, py1 - py0))) {
@@ -258,7 +259,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 				int e0 = E.e0, e1 = E.e1, e2 = E.e2;
 				unsigned long long* row = keys + (size_t)py * D.W;
 				for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
-					if ((e0 | e1 | e2) >= 0) shade_covered32(tr, e1 - E.b1, e2 - E.b2, id1, row + px);
+					if ((e0 | e1 | e2) >= 0) shade_covered32(tr, e1 - E.b1, e2 - E.b2, id1, row + px, tagsh);
 			}
 		} else {
 			EdgeSet E; edges_at(tr, px0, py0, E);
@@ -266,7 +267,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 				long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
 				unsigned long long* row = keys + (size_t)py * D.W;
 				for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
-					if ((e0 | e1 | e2) >= 0) shade_covered(tr, e1 - E.b1, e2 - E.b2, id1, row + px);
+					if ((e0 | e1 | e2) >= 0) shade_covered(tr, e1 - E.b1, e2 - E.b2, id1, row + px, tagsh);
 			}
 		}
 	}
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 //  2. chunk queue: one warp per (triangle, chunk) of at most RAD_TILE x RAD_TILE pixels, 8x4 pixels per step.
 __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
+	const uint32_t tagsh = D.tag << 24;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
 	{
 		const uint32_t nsm = min(D.ctl->q_small, D.q_sm_cap);
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 			for (int s = 0; s < msteps; s++) {
 				if (idx < npx) {
 					const int e0 = E.e0 + x * E.sx0 + y * E.sy0, e1 = E.e1 + x * E.sx1 + y * E.sy1, e2 = E.e2 + x * E.sx2 + y * E.sy2;
-					if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, id1, keys + (size_t)(py0 + y) * D.W + (px0 + x));
+					if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, id1, keys + (size_t)(py0 + y) * D.W + (px0 + x), tagsh);
 				}
 				idx += 8; x += r8; y += q8;
 				if (x >= w8) { x -= w8; y++; }
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 				int e0 = E.e0, e1 = E.e1, e2 = E.e2;
 				unsigned long long* row = keys + (size_t)py * D.W;
 				for (int px = lx; px <= px1; px += 8, e0 += 8 * E.sx0, e1 += 8 * E.sx1, e2 += 8 * E.sx2)
-					if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, r.id1, row + px);
+					if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, r.id1, row + px, tagsh);
 			}
 			continue;
 		}
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 			long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
 			unsigned long long* row = keys + (size_t)py * D.W;
 			for (int px = lx; px <= px1; px += 8, e0 += 8 * E.sx0, e1 += 8 * E.sx1, e2 += 8 * E.sx2)
-				if ((e0 | e1 | e2) >= 0) shade_covered(w, e1 - E.b1, e2 - E.b2, r.id1, row + px);
+				if ((e0 | e1 | e2) >= 0) shade_covered(w, e1 - E.b1, e2 - E.b2, r.id1, row + px, tagsh);
 		}
 	}
 }
@@ -522,17 +524,16 @@ __global__ void queue_reset_kernel(RadDev D, int first_group) {
 	}
 }
 
-// keys -> item buffer (id+1, 0 = empty).  With `reset` the keys are cleared for the next batch, so no
-// separate clear pass is needed in the steady state.  Also recycles the tile queue.
-__global__ void __launch_bounds__(256) resolve_kernel(RadDev D, int reset) {
+// keys -> item buffer (id+1, 0 = empty).  A key belongs to this render iff its top byte equals the launch's epoch tag
+// (see RadDev::tag), so nothing is ever cleared in the steady state.  Also recycles the queues.
+__global__ void __launch_bounds__(256) resolve_kernel(RadDev D) {
 	const uint32_t slot = D.h0 + blockIdx.y;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small)) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; }
-	unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
+	const unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
 	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.RES; i += gridDim.x * blockDim.x) {
 		const unsigned long long k = keys[i];
-		items[i] = k == RAD_CLEAR_KEY ? 0u : (uint32_t)(k & 0xFFFFFFFFull);
-		if (reset) keys[i] = RAD_CLEAR_KEY;
+		items[i] = (uint32_t)(k >> 56) == D.tag ? (uint32_t)(k & 0xFFFFFFFFull) : 0u;
 	}
 }
 
@@ -540,9 +541,9 @@ __global__ void __launch_bounds__(256) clear_keys_kernel(unsigned long long* __r
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) keys[i] = RAD_CLEAR_KEY;
 }
 
-__global__ void read_depth_kernel(const unsigned long long* __restrict__ keys, uint32_t* __restrict__ out, uint32_t n) {
+__global__ void read_depth_kernel(const unsigned long long* __restrict__ keys, uint32_t* __restrict__ out, uint32_t n, uint32_t tag) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) { unsigned long long k = keys[i]; out[i] = k == RAD_CLEAR_KEY ? 0xFFFFFFu : (uint32_t)(k >> 32); }
+	if (i < n) { unsigned long long k = keys[i]; out[i] = (uint32_t)(k >> 56) == tag ? (uint32_t)(k >> 32) & 0xFFFFFFu : 0xFFFFFFu; }
 }
 
 } // namespace
@@ -595,8 +596,8 @@ static void launch_chunks(rad_ctx* c, uint32_t kbase) {
 }
 
 void rad_launch_raster_setup_only(rad_ctx* c) {
-	if (c->keys_dirty) rad_launch_clear_keys(c);
 	if (c->d.h1 == c->d.h0) return;
+	c->d.tag = rad_next_tag(c);               // staged path: every slot has its own key buffer, one tag for the render
 	launch_setup(c, 0, queue_group(c->d), 0);
 }
 
@@ -624,13 +625,13 @@ void rad_launch_process_group(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbas
 // steady state (rad_shoot): per L2-sized group of hemicubes  set-up -> chunks -> fused resolve+ProcessHemicube, the
 // group's key buffers being reused by the next group
 void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::function<void(int)>& mark) {
-	if (c->keys_dirty) rad_launch_clear_keys(c);
 	const uint32_t nslots = c->d.h1 - c->d.h0;
 	if (nslots == 0) return;
 	const uint32_t g = l2_group(c->d);
 	for (uint32_t s0 = 0; s0 < nslots; s0 += g) {
 		const uint32_t n = nslots - s0 < g ? nslots - s0 : g;
 		const uint32_t kbase = c->d.h0 + s0;
+		c->d.tag = rad_next_tag(c);           // the group's key buffers are recycled: new epoch instead of a clear
 		launch_setup(c, s0, n, kbase); if (mark) mark(1);
 		launch_chunks(c, kbase); if (mark) mark(2);
 		rad_launch_process_group(c, s0, n, kbase, keep_items); if (mark) mark(4);
@@ -638,15 +639,14 @@ void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::fu
 }
 void rad_launch_raster_process(rad_ctx* c, bool keep_items) { rad_launch_raster_process_marked(c, keep_items, nullptr); }
 
-void rad_launch_resolve(rad_ctx* c, bool reset) {
+void rad_launch_resolve(rad_ctx* c, bool) {
 	const RadDev& D = c->d;
 	const uint32_t nslots = D.h1 - D.h0;
 	if (nslots == 0) return;
 	uint32_t bx = (D.RES + 255) / 256;
 	if (bx > 148 * 8) bx = 148 * 8;
-	resolve_kernel<<<dim3(bx, nslots), 256, 0, c->stream>>>(D, reset ? 1 : 0);
+	resolve_kernel<<<dim3(bx, nslots), 256, 0, c->stream>>>(D);
 	c->launches++;
-	c->keys_dirty = !reset;
 }
 
 void rad_launch_clear_keys(rad_ctx* c) {
@@ -654,10 +654,18 @@ void rad_launch_clear_keys(rad_ctx* c) {
 	clear_keys_kernel<<<148 * 8, 256, 0, c->stream>>>(D.keys, (size_t)D.k * D.RES);
 	c->launches++;
 	c->keys_dirty = false;
+	c->epoch = 254;
+}
+
+// Epoch tag of the next render into a key buffer: strictly decreasing, so that every stale key (larger tag) loses
+// against any new one under atomicMin and reads back as "empty"; a real clear happens only when the tags run out.
+uint32_t rad_next_tag(rad_ctx* c) {
+	if (c->epoch == 0) rad_launch_clear_keys(c);
+	return c->epoch--;
 }
 
 void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out) {
 	const RadDev& D = c->d;
-	read_depth_kernel<<<(D.RES + 255) / 256, 256, 0, c->stream>>>(D.keys + (size_t)hi * D.RES, d_out, D.RES);
+	read_depth_kernel<<<(D.RES + 255) / 256, 256, 0, c->stream>>>(D.keys + (size_t)hi * D.RES, d_out, D.RES, D.tag);
 	c->launches++;
 }
