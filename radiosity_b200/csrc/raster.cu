@@ -573,8 +573,8 @@ static uint32_t l2_group(const RadDev& D) {
 static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 	RadDev D = c->d;
 	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
-	// one hemicube in flight (k == 1): latency matters, keep the per-lane pixel loops short and let the chunk warps share the rest
-	if (!c->inline_area_forced) D.inline_area = (uint64_t)D.P * n < (1u << 16) ? 16u : 64u;
+	// only bboxes of a few pixels are walked by the set-up lane itself; everything else goes through the balanced queues
+	if (!c->inline_area_forced) D.inline_area = 8u;
 	const uint32_t bx = (D.P + 127) / 128;
 	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
 	const dim3 gs(bx, RAD_NFACES, n), gp(bx, 1, n);
