@@ -322,20 +322,23 @@ template <bool SPLIT_FACES, int MINB>
 __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 	__shared__ float s_mvp[RAD_NFACES][16];
 	const uint32_t slot = D.h0 + blockIdx.z;
+	// all independent global loads first (quad, emitter, matrices): one exposed memory latency instead of three
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = p < D.P;
+	Quad q;
+	if (live) q = load_quad(D, p);
+	float mv = 0.0f;
+	if (threadIdx.x < RAD_NFACES * 16) mv = D.mvp[(size_t)slot * RAD_NFACES * 16 + threadIdx.x];
 	const RadEmitter em = D.em[slot];
 	if (!em.valid) return;
 	const int f_begin = SPLIT_FACES ? blockIdx.y : 0, f_end = SPLIT_FACES ? blockIdx.y + 1 : RAD_NFACES;
-	if (threadIdx.x < RAD_NFACES * 16) (&s_mvp[0][0])[threadIdx.x] = D.mvp[(size_t)slot * RAD_NFACES * 16 + threadIdx.x];
+	if (threadIdx.x < RAD_NFACES * 16) (&s_mvp[0][0])[threadIdx.x] = mv;
 	__syncthreads();
 
-	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool live = p < D.P;
 	const int lane = threadIdx.x & 31;
 	const int N = (int)D.N;
 	const float hw = (float)N * 0.5f;
 	unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
-	Quad q;
-	if (live) q = load_quad(D, p);
 	const uint32_t id1 = p + 1;
 
 	// Conservative patch-level culling (wide margins; the exact tests below decide everything that survives):
