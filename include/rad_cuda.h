@@ -119,6 +119,14 @@ int rad_shoot(rad_ctx* ctx, uint32_t n_batches, int stop_test, rad_stats* out);
 int rad_save_state(rad_ctx* ctx);
 int rad_restore_state(rad_ctx* ctx);
 
+/* ---- display stage (the step after the path) ------------------------------------------------------
+ * Colors::smoothShadePatch for every patch (Colors.cpp:198-261, loop at Main.cpp:1323-1341): vertex colour = mean over the
+ * patch and three of its 8 neighbours of colour (.) (I + B).  nb8 = int32[P*8] neighbour ids (Patch::neighbours,
+ * index 0 = top-left, clockwise; a patch without a neighbour points at itself, Patch.h:50).
+ * colors12_out = float[P*12] in the reference's VBO order (lb, rb, rt, lt per patch, Colors.cpp:256-259). */
+int rad_upload_neighbours(rad_ctx* ctx, const int32_t* nb8, uint32_t P);
+int rad_shade_vertices(rad_ctx* ctx, float* colors12_out, float* gpu_ms_out /* may be NULL */);
+
 /* parity / debugging seams: the `P` preview key and FBO2BMP (FormFactors.cpp:143-171) */
 int rad_read_itembuffer(rad_ctx* ctx, uint32_t hi, uint32_t* ids_out /* W*H */);
 int rad_read_depthbuffer(rad_ctx* ctx, uint32_t hi, uint32_t* depth24_out /* W*H, valid after rad_render_hemicubes */);

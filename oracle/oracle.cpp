@@ -846,6 +846,27 @@ void orc_raster_stats(unsigned P, const float* verts, unsigned shooter, unsigned
 	g_stats = NULL;
 }
 
+// Display stage: Colors::smoothShadePatch (Colors.cpp:198-261) for every patch.  Vertex colour = mean over
+// the patch and three of its 8 neighbours of colour (.) (I + B); output order lb, rb, rt, lt (Colors.cpp:256-259).
+// neighbours: int[P*8], index 0 = top-left, clockwise (Patch.h:50).
+void orc_smooth_shade(unsigned P, const float* color3, const float* rad3, const float* illum3, const int* nb8, float* out12) {
+	static const int corner[4][3] = { { 5, 6, 7 }, { 3, 4, 5 }, { 1, 2, 3 }, { 7, 0, 1 } };   // lb, rb, rt, lt — in the reference's summation order
+	for (unsigned i = 0; i < P; i++) {
+		for (int c = 0; c < 4; c++) {
+			V3 acc = mulv(v3(color3[3 * i], color3[3 * i + 1], color3[3 * i + 2]),
+			              add(v3(illum3[3 * i], illum3[3 * i + 1], illum3[3 * i + 2]), v3(rad3[3 * i], rad3[3 * i + 1], rad3[3 * i + 2])));
+			for (int j = 0; j < 3; j++) {
+				const unsigned n = (unsigned)nb8[8 * (size_t)i + corner[c][j]];
+				V3 t = mulv(v3(color3[3 * n], color3[3 * n + 1], color3[3 * n + 2]),
+				            add(v3(illum3[3 * n], illum3[3 * n + 1], illum3[3 * n + 2]), v3(rad3[3 * n], rad3[3 * n + 1], rad3[3 * n + 2])));
+				acc = add(acc, t);
+			}
+			acc = divf(acc, 4);
+			out12[12 * (size_t)i + 3 * c] = acc.x; out12[12 * (size_t)i + 3 * c + 1] = acc.y; out12[12 * (size_t)i + 3 * c + 2] = acc.z;
+		}
+	}
+}
+
 int orc_max_threads() {
 #ifdef _OPENMP
 	return omp_get_max_threads();

@@ -45,6 +45,7 @@ def lib():
         L.orc_shoot.argtypes = [_u32, _vp, _vp, _vp, _vp, _u32, _u32, _u32, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_int, _vp, ctypes.POINTER(ctypes.c_float)]
         L.orc_shoot.restype = _u32
+        L.orc_smooth_shade.argtypes = [_u32, _vp, _vp, _vp, _vp, _vp]
         _orc = L
     return _orc
 
@@ -73,6 +74,8 @@ def ref():
         L.refp_color.argtypes = [_u32]; L.refp_color.restype = _u32
         L.refp_color_index.argtypes = [_u32]; L.refp_color_index.restype = _u32
         L.refp_sizeof_patch.restype = _u32
+        L.refp_smooth_shade.argtypes = [_vp]
+        L.refp_scene_set_illumination.argtypes = [_vp]
         _ref = L
     return _ref
 
@@ -161,6 +164,15 @@ def shoot(verts, color, rad, illum, side, k, n_batches, select_mode=0, via_codec
     n = lib().orc_shoot(verts.size // 12, _ptr(verts), _ptr(color), _ptr(rad), _ptr(illum), side, k, n_batches, select_mode,
                         1 if via_codec else 0, 1 if stop_test else 0, threads, _ptr(sched), ctypes.byref(last))
     return rad, illum, sched, n, last.value
+
+
+def smooth_shade(color, rad, illum, nb8):
+    color = np.ascontiguousarray(color, np.float32); rad = np.ascontiguousarray(rad, np.float32)
+    illum = np.ascontiguousarray(illum, np.float32); nb8 = np.ascontiguousarray(nb8, np.int32)
+    P = color.size // 3
+    out = np.zeros((P, 12), np.float32)
+    lib().orc_smooth_shade(P, _ptr(color), _ptr(rad), _ptr(illum), _ptr(nb8), _ptr(out))
+    return out
 
 
 def max_threads():

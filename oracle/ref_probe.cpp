@@ -167,6 +167,18 @@ void refp_colors_setup(unsigned patches, unsigned* out11) {
 unsigned refp_color(unsigned colorIndex) { return Colors::color(colorIndex); }
 unsigned refp_color_index(unsigned color) { return (unsigned)Colors::index(color); }
 
+// display stage: Colors::smoothShadePatch for every patch (Colors.cpp:198-261, called from Main.cpp:1323-1341)
+void refp_smooth_shade(float* out12) {
+	unsigned P = g_scene->getPatchesCount();
+	Patch** pp = g_scene->getPatches();
+	for (unsigned i = 0; i < P; i++) Colors::smoothShadePatch(out12 + 12 * (size_t)i, pp[i]);
+}
+void refp_scene_set_illumination(const float* il3) {
+	unsigned P = g_scene->getPatchesCount();
+	Patch** pp = g_scene->getPatches();
+	for (unsigned i = 0; i < P; i++) pp[i]->illumination = Vector3f(il3[3*i], il3[3*i+1], il3[3*i+2]);
+}
+
 unsigned refp_sizeof_patch() { return (unsigned)sizeof(Patch); }
 
 } // extern "C"

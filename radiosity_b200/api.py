@@ -50,6 +50,8 @@ CUDA_SIGNATURES = {
     "rad_shoot": (ctypes.c_int, [_vp, _u32, ctypes.c_int, _P(RadStats)]),
     "rad_save_state": (ctypes.c_int, [_vp]),
     "rad_restore_state": (ctypes.c_int, [_vp]),
+    "rad_upload_neighbours": (ctypes.c_int, [_vp, _vp, _u32]),
+    "rad_shade_vertices": (ctypes.c_int, [_vp, _vp, _P(_f32)]),
     "rad_read_itembuffer": (ctypes.c_int, [_vp, _u32, _vp]),
     "rad_read_depthbuffer": (ctypes.c_int, [_vp, _u32, _vp]),
     "rad_read_formfactors": (ctypes.c_int, [_vp, _u32, _vp]),
@@ -125,6 +127,8 @@ def host_lib():
         lib.radhost_solver_error.argtypes = [_vp]; lib.radhost_solver_error.restype = ctypes.c_char_p
         lib.radhost_solver_pass_counter.argtypes = [_vp]; lib.radhost_solver_pass_counter.restype = _u32
         lib.radhost_solver_running.argtypes = [_vp]
+        lib.radhost_scene_smooth_shade.argtypes = [_vp, _vp]
+        lib.radhost_solver_shade.argtypes = [_vp, _vp]
         lib.radhost_sizeof_patch.restype = _u32
         _host = lib
     return _host
@@ -172,6 +176,12 @@ class Scene:
     def neighbours(self):
         out = np.zeros((self.P, 8), np.int32)
         self.lib.radhost_scene_neighbours(self.h, _ptr(out))
+        return out
+
+    def smooth_shade(self):
+        """Colors::smoothShadePatch for every patch on the host (reference API) -> float[P,12]"""
+        out = np.zeros((self.P, 12), np.float32)
+        self.lib.radhost_scene_smooth_shade(self.h, _ptr(out))
         return out
 
     def select(self, count):
@@ -305,6 +315,16 @@ class Context:
         out = np.zeros(16, np.float32)
         self._ck(self.lib.rad_read_mvp(self.h, hi, face, _ptr(out)), "rad_read_mvp")
         return out
+
+    def upload_neighbours(self, nb8):
+        nb8 = np.ascontiguousarray(nb8, dtype=np.int32)
+        self._ck(self.lib.rad_upload_neighbours(self.h, _ptr(nb8), nb8.size // 8), "rad_upload_neighbours")
+
+    def shade_vertices(self):
+        """display stage on the device -> (float[P,12] vertex colours, gpu ms)"""
+        out = np.zeros((self.P, 12), np.float32); ms = _f32()
+        self._ck(self.lib.rad_shade_vertices(self.h, _ptr(out), ctypes.byref(ms)), "rad_shade_vertices")
+        return out, ms.value
 
     def bench_process(self, repeat=20):
         ms = _f32()

@@ -19,6 +19,10 @@ __global__ void split_quads_kernel(const float4* __restrict__ q, float4* __restr
 		v0[i] = q[3 * (size_t)i]; v1[i] = q[3 * (size_t)i + 1]; v2[i] = q[3 * (size_t)i + 2];
 	}
 }
+__global__ void nb_to_planes_kernel(const int32_t* __restrict__ nb8, int32_t* __restrict__ planes, uint32_t P) {
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
+		for (int j = 0; j < 8; j++) planes[(size_t)j * P + i] = nb8[8 * (size_t)i + j];
+}
 uint32_t grid_for(uint32_t P) { uint32_t b = (P + 255) / 256; return b > 148 * 8 ? 148 * 8 : (b ? b : 1); }
 } // namespace
 
@@ -31,4 +35,7 @@ void rad_launch_planes_to_aos3(rad_ctx* c, const float* planes, float* aos, uint
 void rad_launch_split_quads(rad_ctx* c, const float* verts12, uint32_t P) {
 	split_quads_kernel<<<grid_for(P), 256, 0, c->stream>>>(reinterpret_cast<const float4*>(verts12), const_cast<float4*>(c->d.v0),
 	                                                        const_cast<float4*>(c->d.v1), const_cast<float4*>(c->d.v2), P);
+}
+void rad_launch_nb_to_planes(rad_ctx* c, const int32_t* nb8, uint32_t P) {
+	nb_to_planes_kernel<<<grid_for(P), 256, 0, c->stream>>>(nb8, c->d.nb, P);
 }

@@ -67,7 +67,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	rad_ctx* c = new rad_ctx();
 	c->cfg = *cfg;
 	c->have_ff = c->have_scene = c->emitters_ready = c->rendered = c->processed = c->keys_dirty = false;
-	c->parity = 0; c->selkey_valid = false;
+	c->parity = 0; c->selkey_valid = false; c->have_nb = false;
 	c->graph_exec = nullptr; c->graph_batches = 0; c->graph_keep_items = false;
 	c->h_stage = nullptr; c->h_stage_bytes = 0; c->d_stage = nullptr; c->d_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
@@ -95,7 +95,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(D.keys, (size_t)D.k * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
 	A(dalloc(D.F, (size_t)D.k * Pm)); A(dalloc(D.dB, 3 * Pm));
 	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.ctl, 1));
-	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap));
+	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap)); A(dalloc(D.nb, 8 * Pm)); A(dalloc(D.shade_e, 3 * Pm));
 	A(dalloc(D.ework, Pm < 64 ? (size_t)64 : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * 64)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * 64)); A(dalloc(proj, 16));
 	#undef A
 	if (!ok) {
@@ -129,7 +129,7 @@ int rad_destroy(rad_ctx* c) {
 	cudaFree((void*)D.v0); cudaFree((void*)D.v1); cudaFree((void*)D.v2); cudaFree((void*)D.color);
 	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
 	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.ctl);
-	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
+	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.nb); cudaFree(D.shade_e); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->saved) cudaFree(c->saved);
 	if (c->d_stage) cudaFree(c->d_stage);
@@ -473,6 +473,38 @@ int rad_profile_batch(rad_ctx* c, float* ms6) {
 	for (cudaEvent_t e : ev) cudaEventDestroy(e);
 	c->emitters_ready = c->rendered = c->processed = false;
 	return r;
+}
+
+// ---- display stage ----------------------------------------------------------------------------------
+int rad_upload_neighbours(rad_ctx* c, const int32_t* nb8, uint32_t P) {
+	if (!c || !nb8) return RAD_E_ARG;
+	if (!c->have_scene || P != c->d.P) { c->err = "rad_upload_neighbours: upload the scene first (same P)"; return RAD_E_STATE; }
+	cudaSetDevice(c->cfg.device);
+	for (size_t i = 0; i < (size_t)P * 8; i++)
+		if (nb8[i] < 0 || (uint32_t)nb8[i] >= P) { c->err = "rad_upload_neighbours: neighbour id out of range"; return RAD_E_ARG; }
+	int r = stage_dev(c, (size_t)P * 12 * 4); if (r) return r;
+	memcpy(c->h_stage, nb8, (size_t)P * 32);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, c->h_stage, (size_t)P * 32, cudaMemcpyHostToDevice, c->stream));
+	rad_launch_nb_to_planes(c, reinterpret_cast<const int32_t*>(c->d_stage), P);
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	c->have_nb = true;
+	return RAD_OK;
+}
+
+int rad_shade_vertices(rad_ctx* c, float* colors12_out, float* gpu_ms_out) {
+	if (!c || !colors12_out) return RAD_E_ARG;
+	if (!c->have_scene || !c->have_nb) { c->err = "rad_shade_vertices: upload the scene and the neighbours first"; return RAD_E_STATE; }
+	cudaSetDevice(c->cfg.device);
+	const size_t P = c->d.P;
+	int r = stage_dev(c, P * 12 * 4); if (r) return r;
+	RAD_CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+	rad_launch_shade(c, c->d_stage);
+	RAD_CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_stage, P * 48, cudaMemcpyDeviceToHost, c->stream));
+	if ((r = sync_check(c))) return r;
+	memcpy(colors12_out, c->h_stage, P * 48);
+	if (gpu_ms_out) cudaEventElapsedTime(gpu_ms_out, c->ev0, c->ev1);
+	return RAD_OK;
 }
 
 // ---- device-side state snapshot (benchmarks restart from the same state without host traffic) ----

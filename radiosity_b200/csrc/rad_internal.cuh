@@ -71,6 +71,8 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	uint32_t* ework;              // [max(P,64)] scratch (emitter id staging)
 	unsigned long long* cand0; unsigned long long* cand1;   // top-k tournament candidates, ceil(P/2048)*64 keys each
 	const float* proj;            // [16]
+	int32_t* nb;                  // [8][P] neighbour ids (display stage), plane j = neighbour j
+	float* shade_e;               // [3][P] colour (.) (I + B) scratch of the display stage
 };
 
 struct rad_ctx {
@@ -79,6 +81,7 @@ struct rad_ctx {
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1;
 	std::string err;
+	bool have_nb;
 	bool have_ff, have_scene, emitters_ready, rendered, processed, keys_dirty;
 	uint32_t parity;              // selkey ping-pong for k==1
 	bool selkey_valid;            // selkey[parity] holds the argmax of the current B
@@ -120,6 +123,8 @@ void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out);
 void rad_launch_aos3_to_planes(rad_ctx* c, const float* aos, float* planes, uint32_t P);   // layout.cu
 void rad_launch_planes_to_aos3(rad_ctx* c, const float* planes, float* aos, uint32_t P);
 void rad_launch_split_quads(rad_ctx* c, const float* verts12, uint32_t P);
+void rad_launch_nb_to_planes(rad_ctx* c, const int32_t* nb8, uint32_t P);
+void rad_launch_shade(rad_ctx* c, float* out12);   // shade.cu
 
 #define RAD_CUDA_TRY(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
 	(c)->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return RAD_E_CUDA; } } while (0)

@@ -4,6 +4,8 @@
 #include "Transform.h"
 #include <vector>
 #include <cstring>
+#include <map>
+#include <stdint.h>
 
 RadiositySolver::RadiositySolver() : passCounter(0), computeRadiosity(true), scene(NULL), ctx(NULL) {}
 RadiositySolver::~RadiositySolver() { if (ctx) rad_destroy(ctx); }
@@ -53,8 +55,27 @@ bool RadiositySolver::init(ModelContainer& s, int device, unsigned int selectMod
 	std::vector<float> color, rad, illum;
 	gatherState(s, color, rad, illum);
 	if (rad_upload_scene(ctx, s.getVertices(), color.data(), rad.data(), illum.data(), P) != RAD_OK) return fail("rad_upload_scene");
+	// neighbour ids for the display stage (Patch::neighbours -> scene indices)
+	{
+		std::map<Patch*, int> index;
+		Patch** pp = s.getPatches();
+		for (unsigned int i = 0; i < P; i++) index[pp[i]] = (int)i;
+		std::vector<int32_t> nb(8 * (size_t)P);
+		for (unsigned int i = 0; i < P; i++)
+			for (int j = 0; j < 8; j++) {
+				std::map<Patch*, int>::const_iterator it = index.find(pp[i]->neighbours[j]);
+				nb[8 * (size_t)i + j] = it == index.end() ? (int)i : it->second;
+			}
+		if (rad_upload_neighbours(ctx, nb.data(), P) != RAD_OK) return fail("rad_upload_neighbours");
+	}
 	passCounter = 0;
 	computeRadiosity = true;
+	return true;
+}
+
+bool RadiositySolver::shadeVertices(float* colors12) {
+	if (!ctx) { err = "RadiositySolver::shadeVertices: not initialised"; return false; }
+	if (rad_shade_vertices(ctx, colors12, NULL) != RAD_OK) return fail("rad_shade_vertices");
 	return true;
 }
 

@@ -20,6 +20,8 @@ public:
 	bool syncToScene();
 	// push Patch::radiosity / Patch::illumination to the device again (after editing patches on the host)
 	bool syncFromScene();
+	// display stage on the device: Colors::smoothShadePatch for every patch (Main.cpp:1323-1341); out = float[P*12]
+	bool shadeVertices(float* colors12);
 
 	rad_ctx* context() { return ctx; }
 	const std::string& error() const { return err; }

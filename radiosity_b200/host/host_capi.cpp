@@ -9,6 +9,7 @@
 #include "Camera.h"
 #include "Transform.h"
 #include "Radiosity.h"
+#include "Colors.h"
 
 extern "C" {
 
@@ -124,6 +125,14 @@ rad_ctx* radhost_solver_ctx(void* s) { return ((RadiositySolver*)s)->context(); 
 const char* radhost_solver_error(void* s) { return ((RadiositySolver*)s)->error().c_str(); }
 unsigned radhost_solver_pass_counter(void* s) { return ((RadiositySolver*)s)->passCounter; }
 int radhost_solver_running(void* s) { return ((RadiositySolver*)s)->computeRadiosity ? 1 : 0; }
+
+// Colors::smoothShadePatch over the whole scene on the host (reference API) and on the device (RadiositySolver)
+void radhost_scene_smooth_shade(void* sv, float* out12) {
+	ModelContainer* s = (ModelContainer*)sv;
+	Patch** pp = s->getPatches();
+	for (unsigned i = 0; i < s->getPatchesCount(); i++) Colors::smoothShadePatch(out12 + 12 * (size_t)i, pp[i]);
+}
+int radhost_solver_shade(void* s, float* out12) { return ((RadiositySolver*)s)->shadeVertices(out12) ? 0 : -1; }
 
 unsigned radhost_sizeof_patch() { return (unsigned)sizeof(Patch); }
 

@@ -69,7 +69,12 @@ def main():
                     R.refp_select(k, vp(ids), vp(nul))
                     rs[f"seed{seed}_k{k}"] = {"ids": ids.tolist(), "null": nul.tolist()}
             s["select_seeded"] = rs
-            R.refp_scene_set_radiosity(vp(r))
+            # display stage: Colors::smoothShadePatch on a seeded state
+            rad = seeded_radiosity(P, 3) * np.float32(7); ill = seeded_radiosity(P, 4)
+            R.refp_scene_set_radiosity(vp(rad)); R.refp_scene_set_illumination(vp(ill))
+            sh = np.zeros((P, 12), np.float32); R.refp_smooth_shade(vp(sh))
+            s["smooth_shade_sha256"] = sha(sh)
+            R.refp_scene_set_radiosity(vp(r)); R.refp_scene_set_illumination(vp(il))
         if area == 0.5:
             mv = {}
             for p in (0, 100, 320, 323, 400, 501):

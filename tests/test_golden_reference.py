@@ -67,6 +67,17 @@ def test_select_fresh_and_seeded(orc, api, golden, area):
         assert ids.tolist() == exp["ids"] and nul.tolist() == exp["null"], key
 
 
+def test_display_stage_smooth_shade(orc, api, golden, area):
+    """SURVEY §8f-3: Colors::smoothShadePatch — oracle restatement and host library against the reference's own code."""
+    g = golden["reference"]["scenes"][repr(area)]
+    s = api.Scene(area)
+    v, _, c, r, il = s.arrays()
+    rad = seeded_radiosity(s.P, 3) * np.float32(7); ill = seeded_radiosity(s.P, 4)
+    assert sha(orc.smooth_shade(c, rad, ill, s.neighbours())) == g["smooth_shade_sha256"]
+    s.set_state(rad, ill)
+    assert sha(s.smooth_shade()) == g["smooth_shade_sha256"]
+
+
 def test_known_answers_from_survey(golden):
     sc = golden["reference"]["scenes"]
     assert sc["0.5"]["select_fresh"]["10"]["ids"] == [323, 321, 320, 322, 0, 0, 0, 0, 0, 0]

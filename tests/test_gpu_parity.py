@@ -301,6 +301,30 @@ def test_partition_mode_equals_single_context(api, orc, box):
         h.close()
 
 
+def test_display_stage_on_device(api, orc, golden):
+    """K5: Colors::smoothShadePatch on the GPU — bit-identical to the reference-pinned oracle, before and after shooting."""
+    from util import sha
+    area = 0.014
+    s = api.Scene(area)
+    v, _, c, r, il = s.arrays()
+    nb = s.neighbours()
+    ctx = api.context_for_scene(s, 64, 1)
+    with pytest.raises(api.RadError):
+        ctx.shade_vertices()                            # neighbours not uploaded yet
+    ctx.upload_neighbours(nb)
+    rad = seeded_radiosity(s.P, 3) * np.float32(7); ill = seeded_radiosity(s.P, 4)
+    ctx.upload_state(rad, ill)
+    got, ms = ctx.shade_vertices()
+    assert sha(got) == golden["reference"]["scenes"][repr(area)]["smooth_shade_sha256"]      # == the reference's own output
+    ctx.upload_state(r, il)
+    ctx.shoot(50)
+    rad2, ill2 = ctx.download_state()
+    got, ms = ctx.shade_vertices()
+    assert (got.view(np.uint32) == orc.smooth_shade(c, rad2, ill2, nb).view(np.uint32)).all()
+    assert got.max() > 0 and ms > 0
+    ctx.close()
+
+
 def test_cpp_solver_and_driver(api, orc, box):
     """The C++ host API (RadiositySolver = headless OnIdle) and the `radiosity` command-line driver."""
     v, c, r, il = box
@@ -317,6 +341,9 @@ def test_cpp_solver_and_driver(api, orc, box):
     orad, oillum, *_ = orc.shoot(v, c, r, il, 64, 1, 20)
     assert rel_l2(rad, orad) < 1e-5 and rel_l2(illum, oillum) < 1e-6
     assert lib.radhost_solver_pass_counter(s) == 20
+    shade = np.zeros((scene.P, 12), np.float32)
+    assert lib.radhost_solver_shade(s, shade.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert (shade.view(np.uint32) == scene.smooth_shade().view(np.uint32)).all()      # device display stage == host Colors::smoothShadePatch
     lib.radhost_solver_free(s)
     exe = os.path.join(ROOT, "radiosity_b200", "radiosity")
     p = subprocess.run([exe, "area", "0.5", "hemicube", "64", "hemicubes", "1", "shoots", "10", "shots", "20"], capture_output=True, text=True, timeout=120)
