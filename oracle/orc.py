@@ -74,6 +74,8 @@ def ref():
         L.refp_color.argtypes = [_u32]; L.refp_color.restype = _u32
         L.refp_color_index.argtypes = [_u32]; L.refp_color_index.restype = _u32
         L.refp_sizeof_patch.restype = _u32
+        L.refp_save_rr.argtypes = [ctypes.c_char_p]
+        L.refp_load_rr.argtypes = [ctypes.c_char_p]; L.refp_load_rr.restype = _u32
         L.refp_smooth_shade.argtypes = [_vp]
         L.refp_scene_set_illumination.argtypes = [_vp]
         _ref = L

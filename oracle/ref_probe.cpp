@@ -179,6 +179,45 @@ void refp_scene_set_illumination(const float* il3) {
 	for (unsigned i = 0; i < P; i++) pp[i]->illumination = Vector3f(il3[3*i], il3[3*i+1], il3[3*i+2]);
 }
 
+// a `.rr` file exactly as the reference's SaveToFile body writes it (Main.cpp:1596-1632), with the reference's own Patch
+// class and this build's ABI (LP64: 8-byte count, sizeof(Patch) = 184)
+int refp_save_rr(const char* path) {
+	FILE* fp = fopen(path, "wb");
+	if (!fp) return 0;
+	unsigned long count = g_scene->getPatchesCount();
+	Patch** patches = g_scene->getPatches();
+	Patch* data = new Patch[count];
+	for (unsigned long i = 0; i < count; i++) data[i] = (*patches[i]);
+	std::map<Patch*, unsigned long> where;
+	for (unsigned long j = 0; j < count; j++) where[patches[j]] = j;
+	for (unsigned long i = 0; i < count; i++)
+		for (unsigned int n = 0; n < 8; n++) {
+			std::map<Patch*, unsigned long>::iterator it = where.find(patches[i]->neighbours[n]);
+			if (it != where.end()) { data[i].relativeNeighbours[n] = it->second; data[i].neighbours[n] = NULL; }
+		}
+	size_t w = fwrite(&count, sizeof(unsigned long), 1, fp);
+	w += fwrite(data, sizeof(Patch), count, fp);
+	fclose(fp);
+	delete[] data;
+	return w == 1 + count;
+}
+// LoadingModel round trip with the reference's own classes (LoadFromFile body, Main.cpp:1492-1519)
+unsigned refp_load_rr(const char* path) {
+	FILE* fp = fopen(path, "rb");
+	if (!fp) return 0;
+	unsigned long count = 0;
+	if (fread(&count, sizeof(unsigned long), 1, fp) != 1) { fclose(fp); return 0; }
+	Patch* data = new Patch[count];
+	size_t rd = fread(data, sizeof(Patch), count, fp);
+	fclose(fp);
+	if (rd != count) { delete[] data; return 0; }
+	delete g_scene;
+	g_scene = new ModelContainer();
+	g_scene->addModel(new LoadingModel(data, count));
+	delete[] data;
+	return g_scene->getPatchesCount();
+}
+
 unsigned refp_sizeof_patch() { return (unsigned)sizeof(Patch); }
 
 } // extern "C"

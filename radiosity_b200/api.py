@@ -129,6 +129,8 @@ def host_lib():
         lib.radhost_solver_running.argtypes = [_vp]
         lib.radhost_scene_smooth_shade.argtypes = [_vp, _vp]
         lib.radhost_solver_shade.argtypes = [_vp, _vp]
+        lib.radhost_scene_save.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int]
+        lib.radhost_scene_load.argtypes = [_vp, ctypes.c_char_p]
         lib.radhost_sizeof_patch.restype = _u32
         _host = lib
     return _host
@@ -177,6 +179,17 @@ class Scene:
         out = np.zeros((self.P, 8), np.int32)
         self.lib.radhost_scene_neighbours(self.h, _ptr(out))
         return out
+
+    def save(self, path, fmt=0):
+        """SaveToFile (.rr checkpoint): fmt 0 portable, 1 reference Win32 layout, 2 reference LP64 layout"""
+        if not self.lib.radhost_scene_save(self.h, os.fsencode(path), fmt):
+            raise RadError(f"cannot write {path}")
+
+    def load(self, path):
+        """LoadFromFile: replaces the scene by the checkpoint's patches (LoadingModel)"""
+        if not self.lib.radhost_scene_load(self.h, os.fsencode(path)):
+            raise RadError(f"cannot read {path}")
+        self.P = int(self.lib.radhost_scene_patch_count(self.h))
 
     def smooth_shade(self):
         """Colors::smoothShadePatch for every patch on the host (reference API) -> float[P,12]"""

@@ -5,6 +5,8 @@
 //   device <n>    CUDA device ordinal
 //   obj <path>    load a Wavefront OBJ scene instead of the built-in Cornell box
 //   dump <path>   write "id Bx By Bz Ix Iy Iz" per patch when done
+//   save <path>   checkpoint the scene + energies when done (portable .rr, SceneFile.h; the reference's Ctrl+S)
+//   load <path>   resume from a checkpoint instead of building a scene (the reference's Ctrl+O; also reads its raw dumps)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -15,11 +17,12 @@
 #include "Config.h"
 #include "ModelContainer.h"
 #include "Radiosity.h"
+#include "SceneFile.h"
 
 int main(int argc, const char** argv) {
 	if ((argc - 1) % 2 > 0) { std::cerr << "Wrong number of arguments (expected key value pairs)" << std::endl; return -1; }
 	long shots = -1; int device = 0; unsigned int select = RAD_SELECT_REFERENCE;
-	const char* obj = NULL; const char* dump = NULL;
+	const char* obj = NULL; const char* dump = NULL; const char* save = NULL; const char* load = NULL;
 	for (int i = 1; i < argc; i += 2) {
 		const char* k = argv[i]; const char* v = argv[i + 1];
 		if (!strcmp(k, "area")) Config::setMaxPatchArea(atof(v));
@@ -31,13 +34,16 @@ int main(int argc, const char** argv) {
 		else if (!strcmp(k, "select")) select = !strcmp(v, "topk") ? RAD_SELECT_TOPK : RAD_SELECT_REFERENCE;
 		else if (!strcmp(k, "obj")) obj = v;
 		else if (!strcmp(k, "dump")) dump = v;
+		else if (!strcmp(k, "save")) save = v;
+		else if (!strcmp(k, "load")) load = v;
 	}
 	Config::freeze();
 
 	ModelContainer scene;
-	if (obj) { if (!scene.load(std::string(obj))) { std::cerr << "Unable to load '" << obj << "'" << std::endl; return -1; } }
+	if (load) { if (!LoadFromFile(std::string(load), scene)) { std::cerr << "Unable to load checkpoint '" << load << "'" << std::endl; return -1; } }
+	else if (obj) { if (!scene.load(std::string(obj))) { std::cerr << "Unable to load '" << obj << "'" << std::endl; return -1; } }
 	else scene.load();
-	scene.maxPatchArea = Config::MAX_PATCH_AREA();
+	if (!load) scene.maxPatchArea = Config::MAX_PATCH_AREA();
 	std::cout << "patches: " << scene.getPatchesCount() << ", hemicube " << Config::HEMICUBE_W() << ", atlas "
 	          << Config::PATCHVIEW_TEX_W() << "x" << Config::PATCHVIEW_TEX_H() << " x " << Config::HEMICUBES_CNT() << std::endl;
 
@@ -57,6 +63,7 @@ int main(int argc, const char** argv) {
 	std::cout << "Done in " << secs << " seconds, " << cycles << " cycles" << std::endl;   // Main.cpp:1299
 	std::cout << "gpu time " << gpu_ms << " ms, " << std::setprecision(6) << (cycles / (gpu_ms * 1e-3)) << " hemicubes/s" << std::endl;
 	if (!solver.syncToScene()) { std::cerr << solver.error() << std::endl; return -1; }
+	if (save && !SaveToFile(std::string(save), scene)) { std::cerr << "Unable to write '" << save << "'" << std::endl; return -1; }
 	if (dump) {
 		std::ofstream out(dump);
 		Patch** pp = scene.getPatches();

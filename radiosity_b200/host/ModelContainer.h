@@ -18,6 +18,7 @@ public:
 
 	int addModel(Model* m);                 // takes ownership; returns its index
 	void removeModel(int i);
+	unsigned int getModelsCount() const { return (unsigned int)models.size(); }
 	void updateData();                      // (re)builds vertices / indices / patches
 
 	float* getVertices();                   // float[P*12], 4 unshared vertices per patch

@@ -10,6 +10,7 @@
 #include "Transform.h"
 #include "Radiosity.h"
 #include "Colors.h"
+#include "SceneFile.h"
 
 extern "C" {
 
@@ -133,6 +134,9 @@ void radhost_scene_smooth_shade(void* sv, float* out12) {
 	for (unsigned i = 0; i < s->getPatchesCount(); i++) Colors::smoothShadePatch(out12 + 12 * (size_t)i, pp[i]);
 }
 int radhost_solver_shade(void* s, float* out12) { return ((RadiositySolver*)s)->shadeVertices(out12) ? 0 : -1; }
+
+int radhost_scene_save(void* s, const char* path, int format) { return SaveToFile(std::string(path), *(ModelContainer*)s, (RRFormat)format) ? 1 : 0; }
+int radhost_scene_load(void* s, const char* path) { return LoadFromFile(std::string(path), *(ModelContainer*)s) ? 1 : 0; }
 
 unsigned radhost_sizeof_patch() { return (unsigned)sizeof(Patch); }
 

@@ -119,6 +119,13 @@ def main():
         R.refp_scene_get(vp(v), None, vp(c), vp(r), None)
         ref.setdefault("obj", {})[repr(area)] = {"P": P, "verts_sha256": sha(v), "color_sum": float(c.sum()), "rad_sum": float(r.sum())}
 
+    # `.rr` checkpoint written by the reference's own Patch class / SaveToFile body (LP64 ABI) on a seeded state
+    P = int(R.refp_scene_build(0.5))
+    rad = seeded_radiosity(P, 1); ill = seeded_radiosity(P, 2)
+    R.refp_scene_set_radiosity(vp(rad)); R.refp_scene_set_illumination(vp(ill))
+    assert R.refp_save_rr(os.path.join(ROOT, "tests", "golden", "ref_area0.5_lp64.rr").encode())
+    ref["rr"] = {"file": "ref_area0.5_lp64.rr", "P": P, "bytes": 8 + 184 * P, "rad_sha256": sha(rad), "illum_sha256": sha(ill)}
+
     # ---- oracle regression (NOT reference outputs) ----
     reg = g["oracle_regression"]
     v, c, r, il = orc.scene_cornell(0.5)
