@@ -71,7 +71,8 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->graph_exec = nullptr; c->graph_batches = 0; c->graph_keep_items = false;
 	c->h_stage = nullptr; c->h_stage_bytes = 0; c->d_stage = nullptr; c->d_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
-	c->launches = 0; c->epoch = 254;
+	c->launches = 0; c->epoch = 254; c->multi_graph = true;
+	if (const char* e = getenv("RAD_MULTI_GRAPH")) c->multi_graph = atoi(e) != 0;
 	c->split_limit = 1u << 22; c->inline_area_forced = false; c->setup_minb = 4;
 	if (const char* e = getenv("RAD_SETUP_MINB")) c->setup_minb = atoi(e);   // tuning knob
 	if (const char* e = getenv("RAD_SPLIT_LIMIT")) c->split_limit = strtoull(e, nullptr, 10);   // tuning knob
@@ -80,7 +81,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
 	D.P = 0; D.h0 = 0; D.h1 = D.k;
 	D.reflectivity = cfg->reflectivity;
-	D.q_tri_cap = 1u << 22; D.q_ent_cap = 1u << 23; D.q_sm_cap = 1u << 22;
+	D.q_tri_cap = 1u << 21; D.q_ent_cap = 1u << 23; D.q_sm_cap = 3u << 21;   // three small-queue regions of 2 M records
 	D.kbase = 0; D.inline_area = 64;
 	if (const char* e = getenv("RAD_INLINE_AREA")) { const int v = atoi(e); if (v >= 1 && v <= 4096) { D.inline_area = (uint32_t)v; c->inline_area_forced = true; } }   // tuning knob
 	const size_t Pm = cfg->max_patches;
@@ -339,11 +340,38 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 	RAD_CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
 	uint32_t done = 0; bool stopped = false;
 	if (c->world > 1) {
+		// sharded batches: the same CUDA-graph replay as on one GPU, the ncclAllReduce of every batch captured inside it
+		// (RAD_MULTI_GRAPH=0 falls back to direct launches)
+		const uint32_t GB = 8;
+		if (c->multi_graph && c->nccl_comm && n_batches >= GB) {
+			if (!c->graph_exec || c->graph_batches != GB || c->graph_keep_items != keep) {
+				drop_graph(c);
+				cudaGraph_t g = nullptr;
+				const uint32_t l0 = c->launches;
+				RAD_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+				rad_launch_clear_keys(c);
+				for (uint32_t b = 0; b < GB; b++) if ((r = enqueue_batch_multi(c, keep))) { cudaGraph_t junk; cudaStreamEndCapture(c->stream, &junk); return r; }
+				c->graph_epoch_after = c->epoch;
+				RAD_CUDA_TRY(c, cudaStreamEndCapture(c->stream, &g));
+				RAD_CUDA_TRY(c, cudaGraphInstantiate(&c->graph_exec, g, 0));
+				cudaGraphDestroy(g);
+				c->graph_batches = GB; c->graph_keep_items = keep;
+				c->graph_launches = c->launches - l0; c->launches = l0;
+				c->graph_parity0 = c->parity;
+			}
+			while (n_batches - done >= GB && !stopped) {
+				RAD_CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
+				launches += c->graph_launches;
+				done += GB;
+				c->epoch = c->graph_epoch_after;
+				if (stop_test) { RadControl t; if ((r = read_ctl(c, &t))) return r; stopped = t.stopped != 0; }
+			}
+		}
 		for (; done < n_batches && !stopped; done++) {
 			if ((r = enqueue_batch_multi(c, keep))) return r;
 			if (stop_test) { RadControl t; if ((r = read_ctl(c, &t))) return r; stopped = t.stopped != 0; }
 		}
-		launches = c->launches;
+		launches += c->launches;
 	} else {
 		if (c->d.k == 1 && !c->selkey_valid) rad_launch_argmax(c);
 		// steady state: a CUDA graph of GB batches (even, so that the k==1 key ping-pong returns to its start)

@@ -28,13 +28,13 @@ struct RadControl {               // small device-resident control block
 	uint32_t q_tris;              // tile queue: triangles parked
 	uint32_t q_entries;           // tile queue: (triangle, tile) entries
 	uint32_t q_overflow;
-	uint32_t q_small;             // small-triangle queue: records (one quarter warp each)
+	uint32_t q_small[3];          // small-triangle queues by walk length (<= 4, <= 16, <= 64 steps): records, one quarter warp each
 	uint32_t stopped;             // |lastEnergy| < 0.1 seen
 	float last_energy_len;
 	uint32_t batches_done;
 	uint32_t shots_done;
 	uint32_t pad;                 // triangles parked by the last batch (statistics)
-	uint32_t pad2[3];
+	uint32_t pad2[1];
 };
 
 struct RadEmitter {               // per hemicube slot
@@ -92,7 +92,7 @@ struct rad_ctx {
 	float* h_stage; size_t h_stage_bytes;      // pinned
 	float* d_stage; size_t d_stage_bytes;      // device mirror of the staging buffer
 	// multi-GPU
-	int rank, world; void* nccl_comm; bool partition_only;
+	int rank, world; void* nccl_comm; bool partition_only; bool multi_graph;
 	uint32_t launches;            // kernels launched since last reset
 	uint32_t graph_epoch_after;   // epoch value after one replay of the captured graph
 	uint32_t epoch;               // next key epoch tag (254 .. 1, decreasing; 0 = clear the key buffers first)
