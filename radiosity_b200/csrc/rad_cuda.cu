@@ -81,7 +81,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
 	D.P = 0; D.h0 = 0; D.h1 = D.k;
 	D.reflectivity = cfg->reflectivity;
-	D.q_tri_cap = 1u << 21; D.q_ent_cap = 1u << 23; D.q_sm_cap = 3u << 21;   // three small-queue regions of 2 M records
+	D.q_tri_cap = 1u << 22; D.q_ent_cap = 1u << 23; D.q_sm_cap = 1u << 22;
 	D.kbase = 0; D.inline_area = 64;
 	if (const char* e = getenv("RAD_INLINE_AREA")) { const int v = atoi(e); if (v >= 1 && v <= 4096) { D.inline_area = (uint32_t)v; c->inline_area_forced = true; } }   // tuning knob
 	const size_t Pm = cfg->max_patches;

@@ -28,13 +28,13 @@ struct RadControl {               // small device-resident control block
 	uint32_t q_tris;              // tile queue: triangles parked
 	uint32_t q_entries;           // tile queue: (triangle, tile) entries
 	uint32_t q_overflow;
-	uint32_t q_small[3];          // small-triangle queues by walk length (<= 4, <= 16, <= 64 steps): records, one quarter warp each
+	uint32_t q_small;             // small-triangle queue: records (one quarter warp each)
 	uint32_t stopped;             // |lastEnergy| < 0.1 seen
 	float last_energy_len;
 	uint32_t batches_done;
 	uint32_t shots_done;
 	uint32_t pad;                 // triangles parked by the last batch (statistics)
-	uint32_t pad2[1];
+	uint32_t pad2[3];
 };
 
 struct RadEmitter {               // per hemicube slot

@@ -287,21 +287,12 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 		r.px0 = tr.bx & 0xFFFF; r.px1 = tr.bx >> 16; r.py0 = tr.by & 0xFFFF; r.py1 = tr.by >> 16;
 	}
 	if (ms) {
-		// three size classes so that the four triangles sharing a warp in raster_queue_kernel walk similar step counts
-		const int steps = (bw * bh + 7) >> 3;
-		const int cls = !small ? -1 : (steps <= 4 ? 0 : (steps <= 16 ? 1 : 2));
-		const uint32_t region = D.q_sm_cap / 3;
-		#pragma unroll
-		for (int k = 0; k < 3; k++) {
-			const unsigned mk_ = __ballot_sync(FULL, cls == k);
-			if (mk_ == 0) continue;
-			uint32_t sbase = 0;
-			if (lane == 0) sbase = atomicAdd(&D.ctl->q_small[k], (uint32_t)__popc(mk_));
-			sbase = __shfl_sync(FULL, sbase, 0);
-			if (cls == k) {
-				const uint32_t si = sbase + __popc(mk_ & ((1u << lane) - 1u));
-				if (si < region) D.q_sm[(size_t)k * region + si] = r; else D.ctl->q_overflow = 1;
-			}
+		uint32_t sbase = 0;
+		if (lane == 0) sbase = atomicAdd(&D.ctl->q_small, (uint32_t)__popc(ms));
+		sbase = __shfl_sync(FULL, sbase, 0);
+		if (small) {
+			const uint32_t si = sbase + __popc(ms & ((1u << lane) - 1u));
+			if (si < D.q_sm_cap) D.q_sm[si] = r; else D.ctl->q_overflow = 1;
 		}
 	}
 	if (mb == 0) return;
@@ -453,10 +444,9 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
 	const uint32_t tagsh = D.tag << 24;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-	for (int cls = 0; cls < 3; cls++) {
-		const uint32_t region = D.q_sm_cap / 3;
-		const uint32_t nsm = min(D.ctl->q_small[cls], region);
-		const RadBigTri* __restrict__ qsm = D.q_sm + (size_t)cls * region;
+	{
+		const uint32_t nsm = min(D.ctl->q_small, D.q_sm_cap);
+		const RadBigTri* __restrict__ qsm = D.q_sm;
 		const int sub = lane >> 3, l8 = lane & 7;
 		for (uint32_t base = gw * 4; base < nsm; base += nw * 4) {
 			const uint32_t i = base + sub;
@@ -533,8 +523,8 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 // recycles the chunk queue between hemicube groups of one batch (see rad_launch_raster)
 __global__ void queue_reset_kernel(RadDev D, int first_group) {
 	if (threadIdx.x == 0) {
-		D.ctl->pad = (first_group ? 0u : D.ctl->pad) + D.ctl->q_tris + D.ctl->q_small[0] + D.ctl->q_small[1] + D.ctl->q_small[2];
-		D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small[0] = D.ctl->q_small[1] = D.ctl->q_small[2] = 0;
+		D.ctl->pad = (first_group ? 0u : D.ctl->pad) + D.ctl->q_tris + D.ctl->q_small;
+		D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0;
 	}
 }
 
@@ -542,7 +532,7 @@ __global__ void queue_reset_kernel(RadDev D, int first_group) {
 // (see RadDev::tag), so nothing is ever cleared in the steady state.  Also recycles the queues.
 __global__ void __launch_bounds__(256) resolve_kernel(RadDev D) {
 	const uint32_t slot = D.h0 + blockIdx.y;
-	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small[0] | D.ctl->q_small[1] | D.ctl->q_small[2])) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small[0] + D.ctl->q_small[1] + D.ctl->q_small[2]; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small[0] = D.ctl->q_small[1] = D.ctl->q_small[2] = 0; }
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small)) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; }
 	const unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
 	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.RES; i += gridDim.x * blockDim.x) {
@@ -571,7 +561,7 @@ void rad_launch_camera(rad_ctx* c, int sel_parity) {
 // parked both of its triangles (in practice well under half of them do)
 static uint32_t queue_group(const RadDev& D) {
 	const uint32_t nslots = D.h1 - D.h0;
-	uint64_t g = (uint64_t)min(D.q_tri_cap, D.q_sm_cap / 3) / (2ull * (D.P ? D.P : 1));
+	uint64_t g = (uint64_t)min(D.q_tri_cap, D.q_sm_cap) / (2ull * (D.P ? D.P : 1));
 	if (g < 1) g = 1;
 	return g > nslots ? nslots : (uint32_t)g;
 }
