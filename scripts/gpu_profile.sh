@@ -14,6 +14,6 @@ import json
 for f in ("bench_config2","bench_config2_k1","bench_reference"):
     try:
         d=json.load(open(f"gpurun_out/{f}.json")); print(f, round(d["value"],1), d["unit"], "ms/step", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"],1), d.get("cpu_baseline"))
-        if "kernels" in d: print("  ", {k:(round(v["ms_per_launch"],4),round(v["share"],3)) for k,v in d["kernels"].items()}, "K2 Gpix/s", round(d["process_hemicube"]["gpix_per_s"],1), round(d["process_hemicube"]["frac"],3))
+        if "kernels" in d: print("  ", {k:(round(v["ms_per_batch"],4),round(v["share"],3)) for k,v in d["kernels"].items()}, "K2 Gpix/s", round(d["process_hemicube"]["gpix_per_s"],1), round(d["process_hemicube"]["frac"],3))
     except Exception as e: print(f, "ERR", e)
 PY
