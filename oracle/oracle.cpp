@@ -762,14 +762,21 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 	const float reflectivity = 0.3f;   // Patch.h:13
 	// the reference replicates the one-hemicube table k times (FormFactors.cpp:317-323); only the literal kernel
 	// restatement needs the copies, every other consumer indexes the first one
-	std::vector<float> ff((size_t)RES * (via_codec ? k : 1));
-	formfactors(N, via_codec ? k : 1, ff.data());
-	std::vector<uint64_t> keys(RES);
-	std::vector<std::vector<uint64_t> > tkeys(threads > 1 && k > 1 ? threads : 0);
-	for (size_t t = 0; t < tkeys.size(); t++) tkeys[t].resize(RES);
-	std::vector<uint32_t> atlas((size_t)RES * k);
-	std::vector<float> F(P, 0.0f), Fall;
-	if (threads > 1 && k > 1 && !via_codec) Fall.assign((size_t)P * k, 0.0f);
+	// work buffers live across calls (a caller that shoots batch by batch must not pay table construction and page
+	// faults every time — this is the CPU baseline of bench.py)
+	static std::vector<float> ff; static unsigned ff_N = 0, ff_k = 0;
+	const unsigned ffk = via_codec ? k : 1;
+	if (ff_N != N || ff_k != ffk) { ff.resize((size_t)RES * ffk); formfactors(N, ffk, ff.data()); ff_N = N; ff_k = ffk; }
+	static std::vector<uint64_t> keys; keys.resize(RES);
+	static std::vector<std::vector<uint64_t> > tkeys;
+	const size_t nt = threads > 1 && k > 1 ? (size_t)threads : 0;
+	if (tkeys.size() < nt) tkeys.resize(nt);
+	for (size_t t = 0; t < nt; t++) tkeys[t].resize(RES);
+	// the k-hemicube atlas is only needed by the reference-format path; otherwise every thread keeps one hemicube of ids
+	static std::vector<uint32_t> atlas; atlas.resize((size_t)RES * (via_codec ? k : std::max<size_t>(1, nt)));
+	static std::vector<float> F, Fall;
+	F.assign(P, 0.0f);
+	if (!via_codec) Fall.assign((size_t)P * k, 0.0f);
 	std::vector<unsigned> em(k); std::vector<int> isnull(k);
 	std::vector<V3> snap_rad(k);
 	Codec codec; codec_setup(codec, P);
@@ -780,8 +787,9 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 	float last_len = 0;
 	for (unsigned shoot = 0; shoot < n_batches; shoot++) {
 		orc_select(P, rad3, k, select_mode, em.data(), isnull.data());                                    // S1
-		for (unsigned hi = 0; hi < k; hi++)                                                               // glClear (rendered slots are fully rewritten below)
-			if (isnull[hi]) std::fill(atlas.begin() + (size_t)RES * hi, atlas.begin() + (size_t)RES * (hi + 1), 0u);
+		if (via_codec)
+			for (unsigned hi = 0; hi < k; hi++)                                                           // glClear (rendered slots are fully rewritten below)
+				if (isnull[hi]) std::fill(atlas.begin() + (size_t)RES * hi, atlas.begin() + (size_t)RES * (hi + 1), 0u);
 		for (unsigned hi = 0; hi < k; hi++) {                                                             // S2 (snapshots)
 			if (schedule) schedule[(size_t)shoot * k + hi] = isnull[hi] ? 0xFFFFFFFFu : em[hi];
 			if (!isnull[hi]) snap_rad[hi] = v3(rad3[3 * em[hi]], rad3[3 * em[hi] + 1], rad3[3 * em[hi] + 2]);
@@ -793,13 +801,14 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 		for (int hi = 0; hi < (int)k; hi++) {
 			if (isnull[hi]) continue;
 			uint64_t* kk = keys.data();
+			size_t tid = 0;
 #ifdef _OPENMP
-			if (par_hemi) kk = tkeys[omp_get_thread_num()].data();
+			if (par_hemi) { tid = (size_t)omp_get_thread_num(); kk = tkeys[tid].data(); }
 #endif
 			render_hemicube_keys(P, verts, em[hi], (int)N, kk, par_hemi ? 1 : threads);
-			uint32_t* a = atlas.data() + (size_t)RES * hi;
+			uint32_t* a = atlas.data() + (size_t)RES * (via_codec ? (size_t)hi : tid);
 			for (unsigned i = 0; i < RES; i++) a[i] = kk[i] == kClearKey ? 0u : (uint32_t)(kk[i] & 0xFFFFFFFFu);
-			if (!via_codec && par_hemi) process_hemicube_ids(a, ff.data(), W, H, wx, P, Fall.data() + (size_t)P * hi);
+			if (!via_codec) process_hemicube_ids(a, ff.data(), W, H, wx, P, Fall.data() + (size_t)P * hi);
 		}
 		unsigned nrec = 0;
 		if (via_codec) {
@@ -810,8 +819,7 @@ unsigned orc_shoot(unsigned P, const float* verts, const float* color3, float* r
 			if (isnull[hi]) continue;
 			float* Fh = F.data();
 			if (via_codec) orc_gather_records(P, nrec, rec_h.data(), rec_i.data(), rec_e.data(), hi, F.data());
-			else if (par_hemi) Fh = Fall.data() + (size_t)P * hi;
-			else process_hemicube_ids(atlas.data() + (size_t)RES * hi, ff.data(), W, H, wx, P, F.data());
+			else Fh = Fall.data() + (size_t)P * hi;
 			V3 ec = v3(color3[3 * em[hi]], color3[3 * em[hi] + 1], color3[3 * em[hi] + 2]);
 			for (unsigned i = 0; i < P; i++) {
 				// p->radiosity += p_tmp_radiosities[hi] * p_tmp_formfactors[i] * p->getReflectivity() * p_emitters[hi]->getColor();
