@@ -128,7 +128,7 @@ __device__ __forceinline__ CV xform(const float* __restrict__ m, V3 p) {
 	c.w = ((m[3] * p.x + m[7] * p.y) + m[11] * p.z) + m[15];
 	return c;
 }
-__device__ __forceinline__ CV clip_lerp(const CV& in, const CV& out, float din, float dout) {
+__device__ __noinline__ CV clip_lerp(const CV& in, const CV& out, float din, float dout) {
 	float t = din / (din - dout);
 	CV r;
 	r.x = in.x + t * (out.x - in.x);
@@ -400,8 +400,8 @@ __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 			for (int i = 0; i < 4; i++) pv[i] = project(c[i], hw, ox, oy);
 		}
 		const bool any_clip = __any_sync(FULL, nin > 0 && nin < 4);
-		#pragma unroll
-		for (int t = 0; t < 2; t++) {          // triangles (0,1,2) and (0,2,3), ModelContainer.cpp:112-117
+		#pragma unroll 1
+		for (int t = 0; t < 2; t++) {          // not unrolled: keeps the kernel inside the instruction cache          // triangles (0,1,2) and (0,2,3), ModelContainer.cpp:112-117
 			Tri tr; int area = 0;
 			if (nin == 4) area = setup_tri(pv[0], pv[t + 1], pv[t + 2], scx, scy, scw, sch, tr);
 			emit_tri(D, tr, area, id1, slot, lane, keys);
@@ -578,7 +578,7 @@ static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 	RadDev D = c->d;
 	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
 	// only bboxes of a few pixels are walked by the set-up lane itself; everything else goes through the balanced queues
-	if (!c->inline_area_forced) D.inline_area = 8u;
+	if (!c->inline_area_forced) D.inline_area = D.P >= 65536u ? 64u : 8u;   // micro-triangle scenes: the queues' per-triangle overhead is not worth it
 	const uint32_t bx = (D.P + 127) / 128;
 	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
 	const dim3 gs(bx, RAD_NFACES, n), gp(bx, 1, n);
