@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t key_id(unsigned long long k, uint32_t tag) {
 template <bool FROM_KEYS>
 __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) {
 	const uint32_t slot = D.h0 + blockIdx.y;
-	if (FROM_KEYS && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small)) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; }
+	if (FROM_KEYS && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small | D.ctl->n_pairs)) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; D.ctl->n_pairs = 0; }
 	if (!D.em[slot].valid) return;
 	const int lane = threadIdx.x & 31;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;

@@ -57,6 +57,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	*out = nullptr;
 	if (cfg->hemicube_side < 16 || cfg->hemicube_side > 2048 || cfg->hemicube_side % 16) { g_create_err = "rad_create: hemicube_side must be a multiple of 16 in [16, 2048]"; return RAD_E_ARG; }
 	if (cfg->hemicubes < 1 || cfg->hemicubes > 64) { g_create_err = "rad_create: hemicubes must be in [1, 64]"; return RAD_E_ARG; }
+	if (cfg->max_patches > (1u << 23)) { g_create_err = "rad_create: max_patches must be <= 8388608"; return RAD_E_ARG; }
 	if (cfg->max_patches < 1) { g_create_err = "rad_create: max_patches must be >= 1"; return RAD_E_ARG; }
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -81,7 +82,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
 	D.P = 0; D.h0 = 0; D.h1 = D.k;
 	D.reflectivity = cfg->reflectivity;
-	D.q_tri_cap = 1u << 22; D.q_ent_cap = 1u << 23; D.q_sm_cap = 1u << 22;
+	D.q_tri_cap = 1u << 22; D.q_ent_cap = 1u << 23; D.q_sm_cap = 1u << 22; D.pairs_cap = 1u << 24;
 	D.kbase = 0; D.inline_area = 64;
 	if (const char* e = getenv("RAD_INLINE_AREA")) { const int v = atoi(e); if (v >= 1 && v <= 4096) { D.inline_area = (uint32_t)v; c->inline_area_forced = true; } }   // tuning knob
 	const size_t Pm = cfg->max_patches;
@@ -96,7 +97,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(D.keys, (size_t)D.k * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
 	A(dalloc(D.F, (size_t)D.k * Pm)); A(dalloc(D.dB, 3 * Pm));
 	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.ctl, 1));
-	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap)); A(dalloc(D.nb, 8 * Pm)); A(dalloc(D.shade_e, 3 * Pm));
+	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap)); A(dalloc(D.pairs, (size_t)D.pairs_cap)); A(dalloc(D.nb, 8 * Pm)); A(dalloc(D.shade_e, 3 * Pm));
 	A(dalloc(D.ework, Pm < 64 ? (size_t)64 : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * 64)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * 64)); A(dalloc(proj, 16));
 	#undef A
 	if (!ok) {
@@ -130,7 +131,7 @@ int rad_destroy(rad_ctx* c) {
 	cudaFree((void*)D.v0); cudaFree((void*)D.v1); cudaFree((void*)D.v2); cudaFree((void*)D.color);
 	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
 	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.ctl);
-	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.nb); cudaFree(D.shade_e); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
+	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.pairs); cudaFree(D.nb); cudaFree(D.shade_e); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->saved) cudaFree(c->saved);
 	if (c->d_stage) cudaFree(c->d_stage);

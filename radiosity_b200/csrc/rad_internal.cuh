@@ -34,7 +34,8 @@ struct RadControl {               // small device-resident control block
 	uint32_t batches_done;
 	uint32_t shots_done;
 	uint32_t pad;                 // triangles parked by the last batch (statistics)
-	uint32_t pad2[3];
+	uint32_t n_pairs;             // (patch, face) pairs that survived the conservative culls
+	uint32_t pad2[2];
 };
 
 struct RadEmitter {               // per hemicube slot
@@ -44,6 +45,7 @@ struct RadEmitter {               // per hemicube slot
 	float color[3];               // emitter colour (Main.cpp:1274)
 	float eye[3];                 // patch centre (hemicube eye) and un-normalised patch normal: conservative culling only
 	float nrm[3];
+	float ax[9];                  // orthonormal shooter frame s, t, f (rows) for the conservative culls
 };
 
 struct RadDev {                   // device pointers + sizes, passed by value to kernels
@@ -67,6 +69,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	RadControl* ctl;
 	RadBigTri* q_tri; RadQueueEntry* q_ent;
 	uint32_t q_tri_cap, q_ent_cap;
+	uint32_t* pairs; uint32_t pairs_cap;  // compacted (patch | face << 23 | local slot << 26) work list of the exact set-up stage
 	RadBigTri* q_sm; uint32_t q_sm_cap;   // small-triangle queue (bbox steps <= RAD_SMALL_STEPS, int32 walk)
 	uint32_t* ework;              // [max(P,64)] scratch (emitter id staging)
 	unsigned long long* cand0; unsigned long long* cand1;   // top-k tournament candidates, ceil(P/2048)*64 keys each

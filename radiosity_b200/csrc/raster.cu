@@ -5,11 +5,13 @@
 //
 // Pipeline per batch (all on the context's stream):
 //   camera_kernel        k x 5 lanes: radiosity snapshot, emitter colour, the five MVPs
-//   raster_setup_kernel  one lane per (patch[,face]): vertex transform, near-plane clip, viewport,
-//                        8-bit sub-pixel snap, back-face cull, scissored bbox; then two tiers:
-//                          small bbox (<= 32 px) -> the owning lane walks it alone
-//                          anything larger       -> parked in the chunk queue (bbox-relative 32x32 pixel chunks,
-//                                                   queue slots claimed with one atomic per warp)
+//   raster_cull_kernel   one lane per (patch, hemicube): conservative back-face / horizon / per-face frustum culls in
+//                        the shooter's frame; surviving (patch, face) pairs are compacted (one atomic per warp)
+//   raster_setup_kernel  one lane per surviving pair: vertex transform, near-plane clip, viewport, 8-bit sub-pixel
+//                        snap, exact back-face cull, scissored bbox; then
+//                          tiny bbox       -> the owning lane walks it alone
+//                          anything larger -> parked in the small / chunk queues (slots claimed with one atomic
+//                                             per warp and queue)
 //   raster_queue_kernel  persistent warps drain the two queues: small triangles four per warp (a quarter warp each,
 //                        8x1 pixel rows, int32 walk), chunks one warp each, 8x4 pixels per step
 //   resolve_kernel       64-bit keys -> uint32 item buffer (id+1), keys reset for the next batch
@@ -108,6 +110,13 @@ __global__ void camera_kernel(RadDev D, int sel_parity) {
 			e.eye[0] = (q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f; e.eye[1] = (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f; e.eye[2] = (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f;
 			const V3 n = rcross(vsub(q.b, q.a), vsub(q.d, q.a));
 			e.nrm[0] = n.x; e.nrm[1] = n.y; e.nrm[2] = n.z;
+			// orthonormal shooter frame for the conservative culls: s = n x u, t = u, f = n (u = v4 - v1 lies in the patch plane)
+			const V3 u = vsub(q.d, q.a);
+			const V3 sx = rcross(u, n);               // rcross(a, b) = b x a  ->  n x u
+			const float ls = rsqrtf(fmaxf(sx.x * sx.x + sx.y * sx.y + sx.z * sx.z, 1e-30f)), lt = rsqrtf(fmaxf(u.x * u.x + u.y * u.y + u.z * u.z, 1e-30f)), lf = rsqrtf(fmaxf(n.x * n.x + n.y * n.y + n.z * n.z, 1e-30f));
+			e.ax[0] = sx.x * ls; e.ax[1] = sx.y * ls; e.ax[2] = sx.z * ls;
+			e.ax[3] = u.x * lt; e.ax[4] = u.y * lt; e.ax[5] = u.z * lt;
+			e.ax[6] = n.x * lf; e.ax[7] = n.y * lf; e.ax[8] = n.z * lf;
 		} else e.valid = 0;
 		D.em[h] = e;
 		s_e = e;
@@ -317,58 +326,100 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 		}
 }
 
-// grid: x = patch chunk, y = face (SPLIT) or 1, z = local hemicube slot
-template <bool SPLIT_FACES, int MINB>
-__global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
-	__shared__ float s_mvp[RAD_NFACES][16];
+// ---- stage 1: conservative culling, one lane per (patch, hemicube) ---------------------------------------------------
+// Emits the (patch, face) pairs that MAY produce pixels.  Every test has a wide margin (1e-3 of the distance to the eye,
+// ~6 degrees for facing) and only ever drops work that the exact stage would drop too:
+//  - both triangles clearly face away from the eye: the exact path would get a negative window-space area on every face;
+//  - per face, all four vertices clearly outside one side plane of the face's 90-degree frustum, or clearly below the
+//    shooter's horizon (clipped by the near plane on FRONT, projected below the scissor on the four side faces).
+// The frusta are evaluated in the shooter's orthonormal frame (s = n x u, t = u, f = n; Camera.cpp:19-52): FRONT looks
+// along +f, UP/DOWN along +-t, LEFT/RIGHT along +-s, and the scissored half of every side face is the f >= 0 half.
+// grid: x = patch chunk, z = local hemicube slot
+__global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D) {
 	const uint32_t slot = D.h0 + blockIdx.z;
-	// all independent global loads first (quad, emitter, matrices): one exposed memory latency instead of three
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool live = p < D.P;
 	Quad q;
 	if (live) q = load_quad(D, p);
-	float mv = 0.0f;
-	if (threadIdx.x < RAD_NFACES * 16) mv = D.mvp[(size_t)slot * RAD_NFACES * 16 + threadIdx.x];
 	const RadEmitter em = D.em[slot];
 	if (!em.valid) return;
-	const int f_begin = SPLIT_FACES ? blockIdx.y : 0, f_end = SPLIT_FACES ? blockIdx.y + 1 : RAD_NFACES;
-	if (threadIdx.x < RAD_NFACES * 16) (&s_mvp[0][0])[threadIdx.x] = mv;
-	__syncthreads();
-
 	const int lane = threadIdx.x & 31;
-	const int N = (int)D.N;
-	const float hw = (float)N * 0.5f;
-	unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
-	const uint32_t id1 = p + 1;
-
-	// Conservative patch-level culling (wide margins; the exact tests below decide everything that survives):
-	//  - both triangles clearly face away from the eye (more than ~6 degrees past edge-on): the exact path would
-	//    compute a negative window-space area for them on every face;
-	//  - all four vertices clearly below the shooter's horizon plane: clipped by the near plane on FRONT and
-	//    projected below the scissor on the four side faces.
-	bool culled = !live;
+	unsigned faces = 0;                           // bit f set: face f needs the exact stage
 	if (live) {
-		const V3 eye = mk(em.eye[0], em.eye[1], em.eye[2]), ns = mk(em.nrm[0], em.nrm[1], em.nrm[2]);
+		const V3 eye = mk(em.eye[0], em.eye[1], em.eye[2]);
 		const V3 da = vsub(eye, q.a);
 		const V3 n1 = rcross(vsub(q.b, q.a), vsub(q.c, q.a)), n2 = rcross(vsub(q.c, q.a), vsub(q.d, q.a));
 		const float d2 = da.x * da.x + da.y * da.y + da.z * da.z;
 		const float s1 = n1.x * da.x + n1.y * da.y + n1.z * da.z, s2 = n2.x * da.x + n2.y * da.y + n2.z * da.z;
 		const float m1 = 0.01f * (n1.x * n1.x + n1.y * n1.y + n1.z * n1.z) * d2, m2 = 0.01f * (n2.x * n2.x + n2.y * n2.y + n2.z * n2.z) * d2;
 		const bool back = (s1 < 0.0f && s1 * s1 > m1 || m1 == 0.0f) && (s2 < 0.0f && s2 * s2 > m2 || m2 == 0.0f) && (m1 > 0.0f || m2 > 0.0f);
-		const float ns2 = ns.x * ns.x + ns.y * ns.y + ns.z * ns.z;
-		bool below = true;
-		const V3* vv[4] = { &q.a, &q.b, &q.c, &q.d };
-		#pragma unroll
-		for (int i = 0; i < 4; i++) {
-			const V3 r = vsub(*vv[i], eye);
-			const float h = r.x * ns.x + r.y * ns.y + r.z * ns.z;
-			below = below && h < 0.0f && h * h > 1e-6f * ns2 * (r.x * r.x + r.y * r.y + r.z * r.z);
+		if (!back) {
+			// out[k]: bit v set if vertex v is clearly outside plane k.  planes: 0 c>=0 | 1..4 FRONT c-a,c+a,c-b,c+b |
+			// 5..7 UP b-a,b+a,b-c | 8..10 DOWN -b-a,-b+a,-b-c | 11..13 LEFT a-b,a+b,a-c | 14..16 RIGHT -a-b,-a+b,-a-c
+			unsigned out[17];
+			#pragma unroll
+			for (int k = 0; k < 17; k++) out[k] = 0;
+			const V3* vv[4] = { &q.a, &q.b, &q.c, &q.d };
+			#pragma unroll
+			for (int v = 0; v < 4; v++) {
+				const V3 r = vsub(*vv[v], eye);
+				const float a = r.x * em.ax[0] + r.y * em.ax[1] + r.z * em.ax[2];
+				const float b = r.x * em.ax[3] + r.y * em.ax[4] + r.z * em.ax[5];
+				const float c = r.x * em.ax[6] + r.y * em.ax[7] + r.z * em.ax[8];
+				const float tol = 4e-6f * (r.x * r.x + r.y * r.y + r.z * r.z);       // (2e-3 |r|)^2
+				const float h[17] = { c, c - a, c + a, c - b, c + b, b - a, b + a, b - c, -b - a, -b + a, -b - c, a - b, a + b, a - c, -a - b, -a + b, -a - c };
+				#pragma unroll
+				for (int k = 0; k < 17; k++) if (h[k] < 0.0f && h[k] * h[k] > tol) out[k] |= 1u << v;
+			}
+			const bool below = out[0] == 15u;
+			if (!below) {
+				if (!(out[5] == 15u || out[6] == 15u || out[7] == 15u)) faces |= 1u;          // UP
+				if (!(out[8] == 15u || out[9] == 15u || out[10] == 15u)) faces |= 2u;         // DOWN
+				if (!(out[11] == 15u || out[12] == 15u || out[13] == 15u)) faces |= 4u;       // LEFT
+				if (!(out[14] == 15u || out[15] == 15u || out[16] == 15u)) faces |= 8u;       // RIGHT
+				if (!(out[1] == 15u || out[2] == 15u || out[3] == 15u || out[4] == 15u)) faces |= 16u;   // FRONT
+			}
 		}
-		culled = back || below;
 	}
-	if (!__any_sync(FULL, !culled)) return;
+	// pairs of one face are written as one contiguous run per warp; ONE atomic per warp claims the space
+	unsigned mf[RAD_NFACES]; int total = 0;
+	#pragma unroll
+	for (int f = 0; f < RAD_NFACES; f++) { mf[f] = __ballot_sync(FULL, (faces >> f) & 1u); total += __popc(mf[f]); }
+	if (total == 0) return;
+	uint32_t base = 0;
+	if (lane == 0) base = atomicAdd(&D.ctl->n_pairs, (uint32_t)total);
+	base = __shfl_sync(FULL, base, 0);
+	if (base + total > D.pairs_cap) { if (lane == 0) D.ctl->q_overflow = 1; return; }
+	#pragma unroll
+	for (int f = 0; f < RAD_NFACES; f++) {
+		if ((faces >> f) & 1u) D.pairs[base + __popc(mf[f] & ((1u << lane) - 1u))] = p | ((uint32_t)f << 23) | ((slot - D.h0) << 26);
+		base += __popc(mf[f]);
+	}
+}
 
-	for (int f = f_begin; f < f_end; f++) {
+// ---- stage 2: exact set-up, one lane per surviving (patch, face) pair ----------------------------------------------------
+__global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
+	const uint32_t npairs = min(D.ctl->n_pairs, D.pairs_cap);
+	const int lane = threadIdx.x & 31;
+	const int N = (int)D.N;
+	const float hw = (float)N * 0.5f;
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < npairs; i0 += stride) {
+		const uint32_t i = i0 + lane;
+		const bool live = i < npairs;
+		const uint32_t e = live ? D.pairs[i] : 0u;
+		const uint32_t p = e & 0x7FFFFFu, slot = D.h0 + (e >> 26);
+		const int f = (int)((e >> 23) & 7u);
+		Quad q; float m[16];
+		if (live) {
+			q = load_quad(D, p);
+			const float4* mp = reinterpret_cast<const float4*>(D.mvp + ((size_t)slot * RAD_NFACES + f) * 16);
+			const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+			m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+			m[8] = m2.x; m[9] = m2.y; m[10] = m2.z; m[11] = m2.w; m[12] = m3.x; m[13] = m3.y; m[14] = m3.z; m[15] = m3.w;
+		}
+		unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
+		const uint32_t id1 = p + 1;
 		// viewport origin and scissor of this face (Main.cpp:314-389)
 		int vpx, vpy, scx, scy, scw, sch;
 		switch (f) {
@@ -380,10 +431,10 @@ __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 		}
 		const float ox = (float)vpx + hw, oy = (float)vpy + hw;
 		CV c[4]; float dn[4]; int nin = 0;
-		if (!culled) {
-			c[0] = xform(s_mvp[f], q.a); c[1] = xform(s_mvp[f], q.b); c[2] = xform(s_mvp[f], q.c); c[3] = xform(s_mvp[f], q.d);
+		if (live) {
+			c[0] = xform(m, q.a); c[1] = xform(m, q.b); c[2] = xform(m, q.c); c[3] = xform(m, q.d);
 			#pragma unroll
-			for (int i = 0; i < 4; i++) { dn[i] = c[i].z + c[i].w; nin += dn[i] >= 0.0f; }
+			for (int k = 0; k < 4; k++) { dn[k] = c[k].z + c[k].w; nin += dn[k] >= 0.0f; }
 			// exact trivial reject of the whole quad (all four inside the near plane, so w > 0): wholly beyond one
 			// viewport edge means no snapped vertex can bring a pixel centre inside the scissor
 			if (nin == 4 && ((c[0].x > c[0].w && c[1].x > c[1].w && c[2].x > c[2].w && c[3].x > c[3].w) ||
@@ -397,11 +448,11 @@ __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 		PV pv[4];
 		if (nin == 4) {
 			#pragma unroll
-			for (int i = 0; i < 4; i++) pv[i] = project(c[i], hw, ox, oy);
+			for (int k = 0; k < 4; k++) pv[k] = project(c[k], hw, ox, oy);
 		}
 		const bool any_clip = __any_sync(FULL, nin > 0 && nin < 4);
 		#pragma unroll 1
-		for (int t = 0; t < 2; t++) {          // not unrolled: keeps the kernel inside the instruction cache          // triangles (0,1,2) and (0,2,3), ModelContainer.cpp:112-117
+		for (int t = 0; t < 2; t++) {          // triangles (0,1,2) and (0,2,3), ModelContainer.cpp:112-117
 			Tri tr; int area = 0;
 			if (nin == 4) area = setup_tri(pv[0], pv[t + 1], pv[t + 2], scx, scy, scw, sch, tr);
 			emit_tri(D, tr, area, id1, slot, lane, keys);
@@ -524,7 +575,7 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 __global__ void queue_reset_kernel(RadDev D, int first_group) {
 	if (threadIdx.x == 0) {
 		D.ctl->pad = (first_group ? 0u : D.ctl->pad) + D.ctl->q_tris + D.ctl->q_small;
-		D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0;
+		D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; D.ctl->n_pairs = 0;
 	}
 }
 
@@ -532,7 +583,7 @@ __global__ void queue_reset_kernel(RadDev D, int first_group) {
 // (see RadDev::tag), so nothing is ever cleared in the steady state.  Also recycles the queues.
 __global__ void __launch_bounds__(256) resolve_kernel(RadDev D) {
 	const uint32_t slot = D.h0 + blockIdx.y;
-	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small)) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; }
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small)) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; D.ctl->n_pairs = 0; }
 	const unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
 	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.RES; i += gridDim.x * blockDim.x) {
@@ -561,7 +612,7 @@ void rad_launch_camera(rad_ctx* c, int sel_parity) {
 // parked both of its triangles (in practice well under half of them do)
 static uint32_t queue_group(const RadDev& D) {
 	const uint32_t nslots = D.h1 - D.h0;
-	uint64_t g = (uint64_t)min(D.q_tri_cap, D.q_sm_cap) / (2ull * (D.P ? D.P : 1));
+	uint64_t g = (uint64_t)min(min(D.q_tri_cap, D.q_sm_cap) / 2u, D.pairs_cap / 5u) / (D.P ? D.P : 1);
 	if (g < 1) g = 1;
 	return g > nslots ? nslots : (uint32_t)g;
 }
@@ -579,18 +630,12 @@ static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
 	// only bboxes of a few pixels are walked by the set-up lane itself; everything else goes through the balanced queues
 	if (!c->inline_area_forced) D.inline_area = D.P >= 65536u ? 64u : 8u;   // micro-triangle scenes: the queues' per-triangle overhead is not worth it
-	const uint32_t bx = (D.P + 127) / 128;
-	// few patches: one lane per (patch, face) for latency; many patches: one lane per patch walks its 5 faces
-	const dim3 gs(bx, RAD_NFACES, n), gp(bx, 1, n);
-	if ((uint64_t)D.P * n < c->split_limit) {
-		if (c->setup_minb >= 8) raster_setup_kernel<true, 8><<<gs, 128, 0, c->stream>>>(D);
-		else if (c->setup_minb >= 6) raster_setup_kernel<true, 6><<<gs, 128, 0, c->stream>>>(D);
-		else raster_setup_kernel<true, 4><<<gs, 128, 0, c->stream>>>(D);
-	} else {
-		if (c->setup_minb >= 6) raster_setup_kernel<false, 6><<<gp, 128, 0, c->stream>>>(D);
-		else raster_setup_kernel<false, 3><<<gp, 128, 0, c->stream>>>(D);
-	}
-	c->launches++;
+	raster_cull_kernel<<<dim3((D.P + 255) / 256, 1, n), 256, 0, c->stream>>>(D);
+	// exact stage: persistent grid over the surviving pairs (their number is only known on the device)
+	uint64_t want = ((uint64_t)D.P * n * 2 + 127) / 128;      // typically ~1 of 5 (patch, face) pairs survives
+	const uint32_t blocks = (uint32_t)(want < 148 ? 148 : (want > 148 * 16 ? 148 * 16 : want));
+	raster_setup_kernel<<<blocks, 128, 0, c->stream>>>(D);
+	c->launches += 2;
 }
 static void launch_chunks(rad_ctx* c, uint32_t kbase) {
 	RadDev D = c->d;
