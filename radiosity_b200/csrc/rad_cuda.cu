@@ -74,15 +74,22 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
 	c->launches = 0; c->epoch = 254; c->multi_graph = true;
 	if (const char* e = getenv("RAD_MULTI_GRAPH")) c->multi_graph = atoi(e) != 0;
-	c->split_limit = 1u << 22; c->inline_area_forced = false; c->setup_minb = 4;
-	if (const char* e = getenv("RAD_SETUP_MINB")) c->setup_minb = atoi(e);   // tuning knob
-	if (const char* e = getenv("RAD_SPLIT_LIMIT")) c->split_limit = strtoull(e, nullptr, 10);   // tuning knob
+	c->inline_area_forced = false; c->l2_group_mb = 1u << 20;   // default: the whole batch in one group (measured faster than L2-sized groups)
+	if (const char* e = getenv("RAD_L2_GROUP_MB")) { const int v = atoi(e); if (v >= 1) c->l2_group_mb = (uint32_t)v; }   // tuning knob
 	RadDev& D = c->d;
 	memset(&D, 0, sizeof(D));
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
 	D.P = 0; D.h0 = 0; D.h1 = D.k;
 	D.reflectivity = cfg->reflectivity;
-	D.q_tri_cap = 1u << 22; D.q_ent_cap = 1u << 23; D.q_sm_cap = 1u << 22; D.pairs_cap = 1u << 24;
+	// work lists sized for a whole batch at once when it fits: 2 triangle records and 5 (patch, face) pairs per patch and hemicube
+	// is the worst case the grouping in raster.cu plans with (the real load is a fraction of it)
+	{
+		const uint64_t want = 2ull * cfg->max_patches * cfg->hemicubes;
+		const uint32_t rec = (uint32_t)(want < (1u << 20) ? (1u << 20) : (want > (1u << 24) ? (1u << 24) : want));
+		const uint64_t wantp = 5ull * cfg->max_patches * cfg->hemicubes;
+		D.q_tri_cap = rec; D.q_sm_cap = rec; D.q_ent_cap = 2u * rec;
+		D.pairs_cap = (uint32_t)(wantp < (1u << 20) ? (1u << 20) : (wantp > (1u << 26) ? (1u << 26) : wantp));
+	}
 	D.kbase = 0; D.inline_area = 64;
 	if (const char* e = getenv("RAD_INLINE_AREA")) { const int v = atoi(e); if (v >= 1 && v <= 4096) { D.inline_area = (uint32_t)v; c->inline_area_forced = true; } }   // tuning knob
 	const size_t Pm = cfg->max_patches;

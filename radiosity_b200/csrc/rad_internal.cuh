@@ -100,8 +100,7 @@ struct rad_ctx {
 	uint32_t graph_epoch_after;   // epoch value after one replay of the captured graph
 	uint32_t epoch;               // next key epoch tag (254 .. 1, decreasing; 0 = clear the key buffers first)
 	bool inline_area_forced;      // RAD_INLINE_AREA set: do not auto-tune the inline tier
-	int setup_minb;               // min resident CTAs/SM the set-up kernel variant was compiled for (register cap)
-	uint64_t split_limit;         // P * hemicubes below which the set-up kernel runs one lane per (patch, face)
+	uint32_t l2_group_mb;         // key-buffer footprint (MB) of one hemicube group of the fused path
 };
 
 // ---- launchers (each enqueues on ctx->stream and bumps ctx->launches) -------------------------

@@ -616,10 +616,12 @@ static uint32_t queue_group(const RadDev& D) {
 	if (g < 1) g = 1;
 	return g > nslots ? nslots : (uint32_t)g;
 }
-// fused steady state: additionally keep the group's 64-bit key buffers (8 B/pixel) inside the 126 MB L2, so that the
-// rasteriser's atomics and the fused ProcessHemicube pass never touch HBM for them
-static uint32_t l2_group(const RadDev& D) {
-	uint64_t g = (64ull << 20) / ((uint64_t)D.RES * 8ull);
+// fused steady state: optional cap on the group's key-buffer footprint (RAD_L2_GROUP_MB).  Keeping a group's 64-bit keys
+// inside the 126 MB L2 was measured SLOWER than rendering the whole batch at once (fewer, larger launches win), so the
+// default is no cap
+static uint32_t l2_group(const rad_ctx* c) {
+	const RadDev& D = c->d;
+	uint64_t g = ((uint64_t)c->l2_group_mb << 20) / ((uint64_t)D.RES * 8ull);
 	if (g < 1) g = 1;
 	const uint32_t q = queue_group(D);
 	return g > q ? q : (uint32_t)g;
@@ -676,7 +678,7 @@ void rad_launch_process_group(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbas
 void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::function<void(int)>& mark) {
 	const uint32_t nslots = c->d.h1 - c->d.h0;
 	if (nslots == 0) return;
-	const uint32_t g = l2_group(c->d);
+	const uint32_t g = l2_group(c);
 	for (uint32_t s0 = 0; s0 < nslots; s0 += g) {
 		const uint32_t n = nslots - s0 < g ? nslots - s0 : g;
 		const uint32_t kbase = c->d.h0 + s0;
