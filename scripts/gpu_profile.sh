@@ -7,8 +7,8 @@ timeout 300 python bench.py --workload config2_k1 --steps 5 --no-cpu-baseline > 
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_config2.csv python scripts/prof_batches.py --workload config2 --batches 2 --process-reps 2 2>&1 | tail -1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_config2_k1.csv python scripts/prof_batches.py --workload config2_k1 --batches 40 2>&1 | tail -1
-ncu --set full --clock-control none --import-source on -k regex:"raster_|process_kernel" -s 9 -c 6 -f -o gpurun_out/prof_config2 python scripts/prof_batches.py --workload config2 --batches 2 --process-reps 2 2>&1 | tail -1
-ncu --set full --clock-control none --import-source on -k regex:"process_kernel" -s 8 -c 2 -f -o gpurun_out/prof_process python scripts/prof_batches.py --workload config2 --batches 1 --process-reps 3 2>&1 | tail -1
+ncu --set full --clock-control none --import-source on -k regex:"raster_|process_kernel" -s 4 -c 4 -f -o gpurun_out/prof_config2 python scripts/prof_batches.py --workload config2 --batches 2 --process-reps 2 2>&1 | tail -1
+ncu --set full --clock-control none --import-source on -k regex:"process_kernel" -s 2 -c 2 -f -o gpurun_out/prof_process python scripts/prof_batches.py --workload config2 --batches 1 --process-reps 3 2>&1 | tail -1
 python - <<'PY'
 import json
 for f in ("bench_config2","bench_config2_k1","bench_reference"):
