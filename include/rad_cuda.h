@@ -138,6 +138,11 @@ int rad_write_itembuffer(rad_ctx* ctx, uint32_t hi, const uint32_t* ids /* W*H *
 /* ProcessHemicube in isolation over all k item buffers, `repeat` launches timed with CUDA events on
  * the context's stream; *ms_per_launch = average.  (BASELINE.json: "ProcessHemicube Gpix/s vs HBM") */
 int rad_bench_process(rad_ctx* ctx, uint32_t repeat, float* ms_per_launch);
+/* 64-bit atomicMin roofline of this GPU for the rasteriser's access pattern (SURVEY.md §8d asks for a measured L2-atomic
+ * peak): `count` fire-and-forget RED.MIN.64 over the context's key buffers; pattern 0 = raster-like (each quarter warp
+ * walks 8 consecutive pixels x 8 rows of a randomly placed 8x8 box), 1 = fully coalesced (32 consecutive pixels per warp),
+ * 2 = fully scattered (every lane its own random pixel).  *gops_out = 1e9 atomics per second. */
+int rad_bench_atomics(rad_ctx* ctx, uint32_t pattern, uint64_t count, float* gops_out);
 /* per-kernel CUDA-event timing of one un-graphed batch: ms[0]=select+camera ms[1]=raster setup+small
  * ms[2]=raster tiles ms[3]=resolve ms[4]=process ms[5]=apply.  Runs and applies one batch. */
 int rad_profile_batch(rad_ctx* ctx, float* ms6);

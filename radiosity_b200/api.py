@@ -58,6 +58,7 @@ CUDA_SIGNATURES = {
     "rad_read_mvp": (ctypes.c_int, [_vp, _u32, _u32, _vp]),
     "rad_write_itembuffer": (ctypes.c_int, [_vp, _u32, _vp]),
     "rad_bench_process": (ctypes.c_int, [_vp, _u32, _P(_f32)]),
+    "rad_bench_atomics": (ctypes.c_int, [_vp, _u32, ctypes.c_uint64, _P(_f32)]),
     "rad_profile_batch": (ctypes.c_int, [_vp, _vp]),
     "rad_nccl_unique_id": (ctypes.c_int, [_vp]),
     "rad_comm_init": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
@@ -343,6 +344,12 @@ class Context:
         ms = _f32()
         self._ck(self.lib.rad_bench_process(self.h, repeat, ctypes.byref(ms)), "rad_bench_process")
         return ms.value
+
+    def bench_atomics(self, pattern=0, count=1 << 26):
+        """measured RED.MIN.64 rate (1e9 atomics/s) for pattern 0 raster-like, 1 coalesced, 2 scattered"""
+        g = _f32()
+        self._ck(self.lib.rad_bench_atomics(self.h, pattern, count, ctypes.byref(g)), "rad_bench_atomics")
+        return g.value
 
     def profile_batch(self):
         ms = np.zeros(6, np.float32)

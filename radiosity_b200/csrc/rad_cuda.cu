@@ -488,6 +488,24 @@ int rad_bench_process(rad_ctx* c, uint32_t repeat, float* ms_per_launch) {
 	return RAD_OK;
 }
 
+int rad_bench_atomics(rad_ctx* c, uint32_t pattern, uint64_t count, float* gops_out) {
+	if (!c || !gops_out || pattern > 2) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	const uint32_t blocks = 148 * 16, threads = blocks * 128;
+	uint32_t steps = (uint32_t)((count + threads - 1) / threads);
+	steps = (steps + 7) / 8 * 8;
+	if (steps < 8) steps = 8;
+	rad_launch_atomic_bench(c, pattern, 8, blocks);                       // warm-up
+	RAD_CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+	rad_launch_atomic_bench(c, pattern, steps, blocks);
+	RAD_CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+	rad_launch_clear_keys(c);                                             // the benchmark scribbles over the key buffers
+	int r = sync_check(c); if (r) return r;
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+	*gops_out = (float)((double)threads * steps / (ms * 1e-3) / 1e9);
+	return RAD_OK;
+}
+
 int rad_profile_batch(rad_ctx* c, float* ms6) {
 	int r = need_ready(c, "rad_profile_batch"); if (r) return r;
 	if (!ms6) return RAD_E_ARG;

@@ -122,6 +122,7 @@ void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB
 void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update
 void rad_launch_argmax(rad_ctx* c);                 // k==1: prime selkey[parity] from the current B
 void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out);
+void rad_launch_atomic_bench(rad_ctx* c, uint32_t pattern, uint32_t steps, uint32_t blocks);   // raster.cu
 void rad_launch_aos3_to_planes(rad_ctx* c, const float* aos, float* planes, uint32_t P);   // layout.cu
 void rad_launch_planes_to_aos3(rad_ctx* c, const float* planes, float* aos, uint32_t P);
 void rad_launch_split_quads(rad_ctx* c, const float* verts12, uint32_t P);

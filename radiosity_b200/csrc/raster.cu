@@ -601,7 +601,30 @@ __global__ void read_depth_kernel(const unsigned long long* __restrict__ keys, u
 	if (i < n) { unsigned long long k = keys[i]; out[i] = (uint32_t)(k >> 56) == tag ? (uint32_t)(k >> 32) & 0xFFFFFFu : 0xFFFFFFu; }
 }
 
+// L2 atomic roofline micro-benchmark (rad_bench_atomics): the rasteriser's RED.MIN.64 with nothing around it
+__global__ void __launch_bounds__(128) atomic_bench_kernel(unsigned long long* __restrict__ keys, uint32_t W, uint32_t H, uint32_t nslots,
+                                                            uint32_t pattern, uint32_t steps) {
+	const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+	const size_t RES = (size_t)W * H;
+	uint32_t h = (pattern == 2 ? gt : (pattern == 1 ? gt >> 5 : gt >> 3)) * 2654435761u + 12345u;
+	for (uint32_t s = 0; s < steps; s += 8) {
+		h = h * 1664525u + 1013904223u;
+		const uint32_t slot = (h >> 8) % nslots;
+		uint32_t x = (h >> 3) % (W - 40), y = (h >> 17) % (H - 8);
+		x += pattern == 1 ? lane : (pattern == 0 ? (lane & 7) : 0);
+		unsigned long long* a = keys + slot * RES + (size_t)y * W + x;
+		#pragma unroll
+		for (int r = 0; r < 8; r++) atomicMin(a + (size_t)r * W, ((unsigned long long)(0xFE000000u | (h & 0xFFFFFFu)) << 32) | gt);
+	}
+}
+
 } // namespace
+
+void rad_launch_atomic_bench(rad_ctx* c, uint32_t pattern, uint32_t steps, uint32_t blocks) {
+	const RadDev& D = c->d;
+	atomic_bench_kernel<<<blocks, 128, 0, c->stream>>>(D.keys, D.W, D.H, D.k, pattern, steps);
+	c->launches++;
+}
 
 void rad_launch_camera(rad_ctx* c, int sel_parity) {
 	camera_kernel<<<c->d.k, 32, 0, c->stream>>>(c->d, sel_parity);
