@@ -272,6 +272,8 @@ def main():
         ctx.upload_neighbours(scene.neighbours())
         ctx.shade_vertices()
         k5_ms = min(ctx.shade_vertices()[1] for _ in range(5))
+        # measured RED.MIN.64 roofline for the rasteriser's access pattern over this context's key buffers (k x RES x 8 B)
+        red_peak = max(ctx.bench_atomics(0, 1 << 27) for _ in range(2))
         clk.mark_end()
     clocks = clk.summary()
 
@@ -301,6 +303,12 @@ def main():
                         "achieved_gbs": float(b / (ms * 1e-3) / 1e9) if ms > 0 and b > 0 else None}
         kern["raster (K1: raster_setup + raster_queue)"]["setup_ms"] = float(stage[1])
         kern["raster (K1: raster_setup + raster_queue)"]["queue_ms"] = float(stage[2])
+        # every non-empty pixel needed at least one RED.MIN.64 (oracle statistics: 1.1 covered fragments per pixel on this scene)
+        red_rate = nslots * RES / (float(stage[2]) * 1e-3) / 1e9 if stage[2] > 0 else 0.0
+        kern["raster (K1: raster_setup + raster_queue)"]["atomic_roofline"] = {
+            "bound": "l2_atomic", "unit": "1e9 RED.MIN.64/s", "achieved_lower_bound": red_rate, "peak": red_peak, "frac": red_rate / red_peak if red_peak else None,
+            "key_footprint_mb": k * RES * 8 / 1e6,
+            "note": "peak = rad_bench_atomics(pattern 0: quarter warps walking random 8x8 boxes) over the same key buffers; achieved = atlas pixels of a batch / raster_queue time"}
         dom = max(kern, key=lambda n_: kern[n_]["ms_per_batch"])
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
