@@ -22,6 +22,21 @@ struct RadBigTri {                // one screen-space triangle parked for tile p
 	int px0, py0, px1, py1;       // pixel bbox already clipped to the face scissor
 };
 struct RadQueueEntry { uint32_t tri; uint16_t tx, ty; };
+// One small screen-space QUAD (both triangles of a patch, (0,1,2) and (0,2,3), sharing one bbox walk) parked for the
+// quarter-warp walk of raster_queue_kernel; 64 B = four 16-byte loads.  Vertex coordinates are relative to the centre of
+// the bbox origin pixel (the set-up kernel guarantees they fit int16 and that every edge function fits int32).
+// A lone triangle is stored with v3 = v0 and invB = 0: its second triangle is degenerate and never covers a pixel.
+struct __align__(16) RadSmallQuad {
+	short x0, y0, x1, y1, x2, y2, x3, y3;   // snapped window coordinates (8 sub-pixel bits) - origin pixel centre
+	float Z0, Z1, Z2, Z3;                   // window depth of the four vertices
+	float invA, invB;                       // 1 / (2 * area) of triangles (0,1,2) and (0,2,3)
+	uint32_t id1;                           // patch id + 1
+	uint16_t slot;                          // hemicube slot (atlas index)
+	uint16_t rcpw;                          // ceil(32768 / w): (l * rcpw) >> 15 == l / w exactly for l <= 8, w <= 255
+	uint16_t px0, py0;                      // bbox origin (already clipped to the face scissor)
+	uint8_t w, h;                           // bbox size in pixels (w * h <= 8 * RAD_SMALL_STEPS)
+	uint16_t pad0; uint32_t pad1[2];
+};
 
 struct RadControl {               // small device-resident control block
 	unsigned long long selkey[2]; // k==1 selection: (E bits << 32 | id), ping-pong by batch parity
@@ -70,7 +85,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	RadBigTri* q_tri; RadQueueEntry* q_ent;
 	uint32_t q_tri_cap, q_ent_cap;
 	uint32_t* pairs; uint32_t pairs_cap;  // compacted (patch | face << 23 | local slot << 26) work list of the exact set-up stage
-	RadBigTri* q_sm; uint32_t q_sm_cap;   // small-triangle queue (bbox steps <= RAD_SMALL_STEPS, int32 walk)
+	RadSmallQuad* q_sm; uint32_t q_sm_cap;   // small-quad queue (bbox steps <= RAD_SMALL_STEPS, int32 walk)
 	uint32_t* ework;              // [max(P,64)] scratch (emitter id staging)
 	unsigned long long* cand0; unsigned long long* cand1;   // top-k tournament candidates, ceil(P/2048)*64 keys each
 	const float* proj;            // [16]

@@ -50,12 +50,13 @@ __device__ __forceinline__ void mat_product(float* __restrict__ out, const float
 }
 
 struct Quad { V3 a, b, c, d; };
-__device__ __forceinline__ Quad load_quad(const RadDev& D, uint32_t p) {
-	float4 q0 = __ldg(D.v0 + p), q1 = __ldg(D.v1 + p), q2 = __ldg(D.v2 + p);
+__device__ __forceinline__ Quad load_quad(const float4* __restrict__ v0, const float4* __restrict__ v1, const float4* __restrict__ v2, uint32_t p) {
+	float4 q0 = __ldg(v0 + p), q1 = __ldg(v1 + p), q2 = __ldg(v2 + p);
 	Quad q;
 	q.a = mk(q0.x, q0.y, q0.z); q.b = mk(q0.w, q1.x, q1.y); q.c = mk(q1.z, q1.w, q2.x); q.d = mk(q2.y, q2.z, q2.w);
 	return q;
 }
+__device__ __forceinline__ Quad load_quad(const RadDev& D, uint32_t p) { return load_quad(D.v0, D.v1, D.v2, p); }
 
 // face order in the atlas = p_patchlook_perm (Main.h:210-211): UP, DOWN, LEFT, RIGHT, FRONT
 // MVP = Perspective * LookAt(eye, target + eye, up), column-major m[c*4+r]
@@ -162,6 +163,7 @@ __device__ __forceinline__ int edge_bias(int ax, int ay, int bx, int by) {
 struct Tri {                 // screen-space triangle ready for coverage
 	int X0, Y0, X1, Y1, X2, Y2;
 	float z0, dz1, dz2, inv_area;
+	float z1, z2;            // raw depths of vertices 1 and 2 (set-up kernel only: small-quad records keep the raw values)
 	int bx;                  // px0 | px1 << 16
 	int by;                  // py0 | py1 << 16
 };
@@ -245,7 +247,7 @@ __device__ __forceinline__ int setup_tri(const PV& a, const PV& b, const PV& c, 
 	const int py0 = max((miny - 128 + 255) >> 8, scy), py1 = min((maxy - 128) >> 8, scy + sch - 1);
 	if (px0 > px1 || py0 > py1) return 0;
 	t.X0 = a.X; t.Y0 = a.Y; t.X1 = b.X; t.Y1 = b.Y; t.X2 = c.X; t.Y2 = c.Y;
-	t.z0 = a.Z; t.dz1 = b.Z - a.Z; t.dz2 = c.Z - a.Z;
+	t.z0 = a.Z; t.dz1 = b.Z - a.Z; t.dz2 = c.Z - a.Z; t.z1 = b.Z; t.z2 = c.Z;
 	t.inv_area = 1.0f / (float)area2;
 	t.bx = px0 | (px1 << 16); t.by = py0 | (py1 << 16);
 	return (px1 - px0 + 1) * (py1 - py0 + 1);
@@ -253,58 +255,101 @@ __device__ __forceinline__ int setup_tri(const PV& a, const PV& b, const PV& c, 
 
 #define FULL 0xFFFFFFFFu
 
-// One triangle per lane (area == 0: none).  Small bboxes are walked by the owning lane; everything else is parked
-// in the chunk queue — bbox-relative chunks of RAD_TILE x RAD_TILE pixels, one warp each in raster_queue_kernel —
-// so that no warp of the set-up kernel ever carries a long pixel loop (load balance).  Queue slots are claimed
-// with one atomic per warp.
+// Small-quad record (RadSmallQuad, packed by hand into four 16-byte words so that it never touches local memory):
+// vertices relative to the centre of the bbox origin pixel (int16 by the fits32 bound).
+struct SmallRec { uint4 a, b, c, d; };
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ SmallRec make_small(int X0, int Y0, int X1, int Y1, int X2, int Y2, int X3, int Y3,
+                                                float Z0, float Z1, float Z2, float Z3, float invA, float invB,
+                                                uint32_t id1, uint32_t slot, int px0, int py0, int bw, int bh) {
+	const int cx = px0 * 256 + 128, cy = py0 * 256 + 128;
+	SmallRec r;
+	r.a = make_uint4(pack16(X0 - cx, Y0 - cy), pack16(X1 - cx, Y1 - cy), pack16(X2 - cx, Y2 - cy), pack16(X3 - cx, Y3 - cy));
+	r.b = make_uint4(__float_as_uint(Z0), __float_as_uint(Z1), __float_as_uint(Z2), __float_as_uint(Z3));
+	r.c = make_uint4(__float_as_uint(invA), __float_as_uint(invB), id1, pack16((int)slot, (32768 + bw - 1) / bw));
+	r.d = make_uint4(pack16(px0, py0), (uint32_t)bw | ((uint32_t)bh << 8), 0u, 0u);
+	return r;
+}
+__device__ __forceinline__ int radius_about(int cx, int cy, int X, int Y) { return max(abs(X - cx), abs(Y - cy)); }
+
+// Warp-collective append to the small-quad queue: ONE atomic per warp.
+__device__ __forceinline__ void push_small(const RadDev& D, bool take, const SmallRec& r, int lane) {
+	const unsigned ms = __ballot_sync(FULL, take);
+	if (ms == 0) return;
+	uint32_t sbase = 0;
+	if (lane == 0) sbase = atomicAdd(&D.ctl->q_small, (uint32_t)__popc(ms));
+	sbase = __shfl_sync(FULL, sbase, 0);
+	if (take) {
+		const uint32_t si = sbase + __popc(ms & ((1u << lane) - 1u));
+		if (si < D.q_sm_cap) {
+			uint4* dst = reinterpret_cast<uint4*>(D.q_sm + si);
+			dst[0] = r.a; dst[1] = r.b; dst[2] = r.c; dst[3] = r.d;
+		} else D.ctl->q_overflow = 1;
+	}
+}
+
+// Both triangles of an unclipped, front-facing patch whose common bbox is small: parked as ONE record, walked once.
+// Returns true when the quad was taken (the caller then skips its two triangles).
+__device__ __forceinline__ bool emit_quad(const RadDev& D, const Tri& ta, const Tri& tb, int areaA, int areaB, int X3, int Y3, float Z3,
+                                          uint32_t id1, uint32_t slot, int lane) {
+	bool take = false;
+	int px0 = 0, py0 = 0, bw = 1, bh = 1;
+	if (areaA > 0 && areaB > 0) {
+		px0 = min(ta.bx & 0xFFFF, tb.bx & 0xFFFF); py0 = min(ta.by & 0xFFFF, tb.by & 0xFFFF);
+		bw = max(ta.bx >> 16, tb.bx >> 16) - px0 + 1; bh = max(ta.by >> 16, tb.by >> 16) - py0 + 1;
+		if (bw * bh > (int)D.inline_area && bw * bh <= 8 * RAD_SMALL_STEPS && bw <= 255 && bh <= 255) {   // w, h are bytes in the record
+			const int cx = px0 * 256 + 128, cy = py0 * 256 + 128;
+			const int r = max(max(radius_about(cx, cy, ta.X0, ta.Y0), radius_about(cx, cy, ta.X1, ta.Y1)), max(radius_about(cx, cy, ta.X2, ta.Y2), radius_about(cx, cy, X3, Y3)));
+			take = (long long)r * (long long)(r + (max(bw, bh) + 8) * 256) < (1ll << 29);
+		}
+	}
+	if (!__any_sync(FULL, take)) return false;
+	SmallRec r;
+	if (take) r = make_small(ta.X0, ta.Y0, ta.X1, ta.Y1, ta.X2, ta.Y2, X3, Y3, ta.z0, ta.z1, ta.z2, Z3, ta.inv_area, tb.inv_area, id1, slot, px0, py0, bw, bh);
+	push_small(D, take, r, lane);
+	return take;
+}
+
+// One triangle per lane (area == 0: none).  Small bboxes are walked by the owning lane; everything else is parked:
+// short int32-safe walks in the small-quad queue (as a quad whose second triangle is degenerate), the rest in the chunk
+// queue — bbox-relative chunks of RAD_TILE x RAD_TILE pixels, one warp each in raster_queue_kernel — so that no warp of
+// the set-up kernel ever carries a long pixel loop (load balance).  Queue slots are claimed with one atomic per warp.
 __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
                                          unsigned long long* __restrict__ keys) {
 	const uint32_t tagsh = D.tag << 24;
-	if (area > 0 && area <= (int)D.inline_area) {
+	const int bw = (tr.bx >> 16) - (tr.bx & 0xFFFF) + 1, bh = (tr.by >> 16) - (tr.by & 0xFFFF) + 1;
+	// tiny bbox: walked here by the owning lane (int32 edge functions; the rare tiny bbox of a triangle whose vertices lie
+	// far away goes to the chunk queue, which has the int64 walk)
+	const bool tiny = area > 0 && area <= (int)D.inline_area && fits32(tr, tr.bx & 0xFFFF, tr.by & 0xFFFF, max(bw, bh));
+	if (tiny) {
 		const int px0 = tr.bx & 0xFFFF, px1 = tr.bx >> 16, py0 = tr.by & 0xFFFF, py1 = tr.by >> 16;
-		if (fits32(tr, px0, py0, max(px1 - px0, py1 - py0))) {
-			EdgeSet32 E; edges_at32(tr, px0, py0, E);
-			for (int py = py0; py <= py1; py++, E.e0 += E.sy0, E.e1 += E.sy1, E.e2 += E.sy2) {
-				int e0 = E.e0, e1 = E.e1, e2 = E.e2;
-				unsigned long long* row = keys + (size_t)py * D.W;
-				for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
-					if ((e0 | e1 | e2) >= 0) shade_covered32(tr, e1 - E.b1, e2 - E.b2, id1, row + px, tagsh);
-			}
-		} else {
-			EdgeSet E; edges_at(tr, px0, py0, E);
-			for (int py = py0; py <= py1; py++, E.e0 += E.sy0, E.e1 += E.sy1, E.e2 += E.sy2) {
-				long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
-				unsigned long long* row = keys + (size_t)py * D.W;
-				for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
-					if ((e0 | e1 | e2) >= 0) shade_covered(tr, e1 - E.b1, e2 - E.b2, id1, row + px, tagsh);
-			}
+		EdgeSet32 E; edges_at32(tr, px0, py0, E);
+		for (int py = py0; py <= py1; py++, E.e0 += E.sy0, E.e1 += E.sy1, E.e2 += E.sy2) {
+			int e0 = E.e0, e1 = E.e1, e2 = E.e2;
+			unsigned long long* row = keys + (size_t)py * D.W;
+			for (int px = px0; px <= px1; px++, e0 += E.sx0, e1 += E.sx1, e2 += E.sx2)
+				if ((e0 | e1 | e2) >= 0) shade_covered32(tr, e1 - E.b1, e2 - E.b2, id1, row + px, tagsh);
 		}
 	}
-	// everything else is parked: triangles whose bbox walk is short and fits int32 go to the small queue (a quarter
-	// warp each in raster_queue_kernel), the rest to the chunk queue
-	const int bw = (tr.bx >> 16) - (tr.bx & 0xFFFF) + 1, bh = (tr.by >> 16) - (tr.by & 0xFFFF) + 1;
-	const bool parked = area > (int)D.inline_area;
-	const bool small = parked && bw * bh <= 8 * RAD_SMALL_STEPS && fits32(tr, tr.bx & 0xFFFF, tr.by & 0xFFFF, max(bw, bh) + 8);   // +8: lanes start up to 7 px right of the origin
+	const bool parked = area > 0 && !tiny;
+	const bool small = parked && bw * bh <= 8 * RAD_SMALL_STEPS && bw <= 255 && bh <= 255 && fits32(tr, tr.bx & 0xFFFF, tr.by & 0xFFFF, max(bw, bh) + 8);   // +8: lanes start up to 7 px right of the origin
 	const bool big = parked && !small;
 	const unsigned ms = __ballot_sync(FULL, small), mb = __ballot_sync(FULL, big);
 	if ((ms | mb) == 0) return;
+	if (ms) {
+		SmallRec q;
+		if (small) q = make_small(tr.X0, tr.Y0, tr.X1, tr.Y1, tr.X2, tr.Y2, tr.X0, tr.Y0, tr.z0, tr.z1, tr.z2, tr.z0, tr.inv_area, 0.0f,
+		                          id1, slot, tr.bx & 0xFFFF, tr.by & 0xFFFF, bw, bh);
+		push_small(D, small, q, lane);
+	}
+	if (mb == 0) return;
 	RadBigTri r;
-	if (parked) {
+	if (big) {
 		r.X0 = tr.X0; r.Y0 = tr.Y0; r.X1 = tr.X1; r.Y1 = tr.Y1; r.X2 = tr.X2; r.Y2 = tr.Y2;
 		r.z0 = tr.z0; r.dz1 = tr.dz1; r.dz2 = tr.dz2; r.inv_area = tr.inv_area;
 		r.id1 = id1; r.slot = slot;
 		r.px0 = tr.bx & 0xFFFF; r.px1 = tr.bx >> 16; r.py0 = tr.by & 0xFFFF; r.py1 = tr.by >> 16;
 	}
-	if (ms) {
-		uint32_t sbase = 0;
-		if (lane == 0) sbase = atomicAdd(&D.ctl->q_small, (uint32_t)__popc(ms));
-		sbase = __shfl_sync(FULL, sbase, 0);
-		if (small) {
-			const uint32_t si = sbase + __popc(ms & ((1u << lane) - 1u));
-			if (si < D.q_sm_cap) D.q_sm[si] = r; else D.ctl->q_overflow = 1;
-		}
-	}
-	if (mb == 0) return;
 	int ncx = 0, ncy = 0, nent = 0;
 	if (big) { ncx = (bw - 1) / RAD_TILE + 1; ncy = (bh - 1) / RAD_TILE + 1; nent = ncx * ncy; }
 	int pre = nent;                               // inclusive warp scan of the entry counts
@@ -398,7 +443,60 @@ __global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D) {
 }
 
 // ---- stage 2: exact set-up, one lane per surviving (patch, face) pair ----------------------------------------------------
-__global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
+struct FaceWin { int scx, scy, scw, sch; float ox, oy; };
+// viewport origin and scissor of a face (Main.cpp:314-389)
+__device__ __forceinline__ FaceWin face_window(int f, int N) {
+	int vpx, vpy; FaceWin w;
+	switch (f) {
+	case 0: vpx = 0; vpy = N; w.scx = 0; w.scy = N; w.scw = N; w.sch = N / 2; break;
+	case 1: vpx = N; vpy = N / 2; w.scx = N; w.scy = N; w.scw = N; w.sch = N / 2; break;
+	case 2: vpx = -(N / 2); vpy = 0; w.scx = 0; w.scy = 0; w.scw = N / 2; w.sch = N; break;
+	case 3: vpx = N + N / 2; vpy = 0; w.scx = N + N / 2; w.scy = 0; w.scw = N / 2; w.sch = N; break;
+	default: vpx = N / 2; vpy = 0; w.scx = N / 2; w.scy = 0; w.scw = N; w.sch = N; break;
+	}
+	const float hw = (float)N * 0.5f;
+	w.ox = (float)vpx + hw; w.oy = (float)vpy + hw;
+	return w;
+}
+__device__ __forceinline__ void load_mvp(const float* __restrict__ mvp, uint32_t slot, int f, float* __restrict__ m) {
+	const float4* mp = reinterpret_cast<const float4*>(mvp + ((size_t)slot * RAD_NFACES + f) * 16);
+	const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+	m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+	m[8] = m2.x; m[9] = m2.y; m[10] = m2.z; m[11] = m2.w; m[12] = m3.x; m[13] = m3.y; m[14] = m3.z; m[15] = m3.w;
+}
+
+// Rare path, out of line: triangle t (0: (0,1,2), 1: (0,2,3)) of a patch that crosses the near plane (z + w >= 0).  The
+// patch is transformed again here so that the common path does not keep its clip-space vertices alive.  New vertices
+// are interpolated from the inside vertex; vertex order as produced by walking the edges 0-1, 1-2, 2-0; the clipped
+// polygon (3 or 4 vertices) is drawn as the fan (0,1,2), (0,2,3): sub selects the fan triangle.
+__device__ __noinline__ int clip_tri(const float4* __restrict__ v0, const float4* __restrict__ v1, const float4* __restrict__ v2,
+                                      const float* __restrict__ mvp, uint32_t h0, int N, uint32_t pair, int t, int sub, Tri* out) {
+	const uint32_t p = pair & 0x7FFFFFu, slot = h0 + (pair >> 26);
+	const int f = (int)((pair >> 23) & 7u);
+	const float hw = (float)N * 0.5f;
+	const FaceWin fw = face_window(f, N);
+	float m[16]; load_mvp(mvp, slot, f, m);
+	const Quad q = load_quad(v0, v1, v2, p);
+	const CV in0 = xform(m, q.a), in1 = xform(m, t ? q.c : q.b), in2 = xform(m, t ? q.d : q.c);
+	const float d0 = in0.z + in0.w, d1 = in1.z + in1.w, d2 = in2.z + in2.w;
+	CV p0, p1, p2, p3; int n = 0;
+	switch ((d0 >= 0.0f ? 1 : 0) | (d1 >= 0.0f ? 2 : 0) | (d2 >= 0.0f ? 4 : 0)) {
+	case 7: p0 = in0; p1 = in1; p2 = in2; n = 3; break;
+	case 1: p0 = in0; p1 = clip_lerp(in0, in1, d0, d1); p2 = clip_lerp(in0, in2, d0, d2); n = 3; break;
+	case 2: p0 = clip_lerp(in1, in0, d1, d0); p1 = in1; p2 = clip_lerp(in1, in2, d1, d2); n = 3; break;
+	case 4: p0 = clip_lerp(in2, in1, d2, d1); p1 = in2; p2 = clip_lerp(in2, in0, d2, d0); n = 3; break;
+	case 3: p0 = in0; p1 = in1; p2 = clip_lerp(in1, in2, d1, d2); p3 = clip_lerp(in0, in2, d0, d2); n = 4; break;
+	case 6: p0 = clip_lerp(in1, in0, d1, d0); p1 = in1; p2 = in2; p3 = clip_lerp(in2, in0, d2, d0); n = 4; break;
+	case 5: p0 = in0; p1 = clip_lerp(in0, in1, d0, d1); p2 = clip_lerp(in2, in1, d2, d1); p3 = in2; n = 4; break;
+	default: break;
+	}
+	if (n < 3 + sub) return 0;
+	const PV a = project(p0, hw, fw.ox, fw.oy), b = project(sub ? p2 : p1, hw, fw.ox, fw.oy), cc = project(sub ? p3 : p2, hw, fw.ox, fw.oy);
+	return setup_tri(a, b, cc, fw.scx, fw.scy, fw.scw, fw.sch, *out);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 	const uint32_t npairs = min(D.ctl->n_pairs, D.pairs_cap);
 	const int lane = threadIdx.x & 31;
 	const int N = (int)D.N;
@@ -410,86 +508,65 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RadDev D) {
 		const uint32_t e = live ? D.pairs[i] : 0u;
 		const uint32_t p = e & 0x7FFFFFu, slot = D.h0 + (e >> 26);
 		const int f = (int)((e >> 23) & 7u);
-		Quad q; float m[16];
+		const FaceWin fw = face_window(f, N);
+		// transform; nin = vertices inside the near plane (4: the common, unclipped case; 1..3: clip path; 0: nothing)
+		PV pv[4]; int nin = 0;
 		if (live) {
-			q = load_quad(D, p);
-			const float4* mp = reinterpret_cast<const float4*>(D.mvp + ((size_t)slot * RAD_NFACES + f) * 16);
-			const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
-			m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
-			m[8] = m2.x; m[9] = m2.y; m[10] = m2.z; m[11] = m2.w; m[12] = m3.x; m[13] = m3.y; m[14] = m3.z; m[15] = m3.w;
-		}
-		unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
-		const uint32_t id1 = p + 1;
-		// viewport origin and scissor of this face (Main.cpp:314-389)
-		int vpx, vpy, scx, scy, scw, sch;
-		switch (f) {
-		case 0: vpx = 0; vpy = N; scx = 0; scy = N; scw = N; sch = N / 2; break;
-		case 1: vpx = N; vpy = N / 2; scx = N; scy = N; scw = N; sch = N / 2; break;
-		case 2: vpx = -(N / 2); vpy = 0; scx = 0; scy = 0; scw = N / 2; sch = N; break;
-		case 3: vpx = N + N / 2; vpy = 0; scx = N + N / 2; scy = 0; scw = N / 2; sch = N; break;
-		default: vpx = N / 2; vpy = 0; scx = N / 2; scy = 0; scw = N; sch = N; break;
-		}
-		const float ox = (float)vpx + hw, oy = (float)vpy + hw;
-		CV c[4]; float dn[4]; int nin = 0;
-		if (live) {
+			float m[16]; load_mvp(D.mvp, slot, f, m);
+			const Quad q = load_quad(D, p);
+			CV c[4];
 			c[0] = xform(m, q.a); c[1] = xform(m, q.b); c[2] = xform(m, q.c); c[3] = xform(m, q.d);
 			#pragma unroll
-			for (int k = 0; k < 4; k++) { dn[k] = c[k].z + c[k].w; nin += dn[k] >= 0.0f; }
+			for (int k = 0; k < 4; k++) nin += (c[k].z + c[k].w) >= 0.0f;
 			// exact trivial reject of the whole quad (all four inside the near plane, so w > 0): wholly beyond one
 			// viewport edge means no snapped vertex can bring a pixel centre inside the scissor
 			if (nin == 4 && ((c[0].x > c[0].w && c[1].x > c[1].w && c[2].x > c[2].w && c[3].x > c[3].w) ||
 			                 (c[0].x < -c[0].w && c[1].x < -c[1].w && c[2].x < -c[2].w && c[3].x < -c[3].w) ||
 			                 (c[0].y > c[0].w && c[1].y > c[1].w && c[2].y > c[2].w && c[3].y > c[3].w) ||
 			                 (c[0].y < -c[0].w && c[1].y < -c[1].w && c[2].y < -c[2].w && c[3].y < -c[3].w))) nin = 0;
+			if (nin == 4) {
+				#pragma unroll
+				for (int k = 0; k < 4; k++) pv[k] = project(c[k], hw, fw.ox, fw.oy);
+			}
 		}
 		if (!__any_sync(FULL, nin > 0)) continue;
-
-		// common case: nothing crosses the near plane -> project the four vertices once
-		PV pv[4];
+		unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
+		const uint32_t id1 = p + 1;
+		const bool clipped = nin > 0 && nin < 4;
+		// unclipped patch: both triangles are set up together; a small common bbox is parked as ONE quad record
+		Tri trA, trB; int areaA = 0, areaB = 0;
 		if (nin == 4) {
-			#pragma unroll
-			for (int k = 0; k < 4; k++) pv[k] = project(c[k], hw, ox, oy);
+			areaA = setup_tri(pv[0], pv[1], pv[2], fw.scx, fw.scy, fw.scw, fw.sch, trA);
+			areaB = setup_tri(pv[0], pv[2], pv[3], fw.scx, fw.scy, fw.scw, fw.sch, trB);
 		}
-		const bool any_clip = __any_sync(FULL, nin > 0 && nin < 4);
+		if (emit_quad(D, trA, trB, areaA, areaB, pv[3].X, pv[3].Y, pv[3].Z, id1, slot, lane)) { areaA = 0; areaB = 0; }
+		// triangles (0,1,2) and (0,2,3) (ModelContainer.cpp:112-117) on their own, then — rare — the clipped fans
+		const int nt = __any_sync(FULL, clipped) ? 6 : 2;
 		#pragma unroll 1
-		for (int t = 0; t < 2; t++) {          // triangles (0,1,2) and (0,2,3), ModelContainer.cpp:112-117
-			Tri tr; int area = 0;
-			if (nin == 4) area = setup_tri(pv[0], pv[t + 1], pv[t + 2], scx, scy, scw, sch, tr);
-			emit_tri(D, tr, area, id1, slot, lane, keys);
-			if (!any_clip) continue;
-			// rare: the triangle crosses the near plane (z + w >= 0).  New vertices are interpolated from the inside
-			// vertex; vertex order as produced by walking the edges 0-1, 1-2, 2-0.
-			CV p0, p1, p2, p3; int n = 0;
-			if (nin > 0 && nin < 4) {
-				const CV in0 = c[0], in1 = c[t + 1], in2 = c[t + 2];
-				const float d0 = dn[0], d1 = dn[t + 1], d2 = dn[t + 2];
-				switch ((d0 >= 0.0f ? 1 : 0) | (d1 >= 0.0f ? 2 : 0) | (d2 >= 0.0f ? 4 : 0)) {
-				case 7: p0 = in0; p1 = in1; p2 = in2; n = 3; break;
-				case 1: p0 = in0; p1 = clip_lerp(in0, in1, d0, d1); p2 = clip_lerp(in0, in2, d0, d2); n = 3; break;
-				case 2: p0 = clip_lerp(in1, in0, d1, d0); p1 = in1; p2 = clip_lerp(in1, in2, d1, d2); n = 3; break;
-				case 4: p0 = clip_lerp(in2, in1, d2, d1); p1 = in2; p2 = clip_lerp(in2, in0, d2, d0); n = 3; break;
-				case 3: p0 = in0; p1 = in1; p2 = clip_lerp(in1, in2, d1, d2); p3 = clip_lerp(in0, in2, d0, d2); n = 4; break;
-				case 6: p0 = clip_lerp(in1, in0, d1, d0); p1 = in1; p2 = in2; p3 = clip_lerp(in2, in0, d2, d0); n = 4; break;
-				case 5: p0 = in0; p1 = clip_lerp(in0, in1, d0, d1); p2 = clip_lerp(in2, in1, d2, d1); p3 = in2; n = 4; break;
-				default: break;
-				}
-			}
-			for (int sub = 0; sub < 2; sub++) {
-				if (!__any_sync(FULL, n >= 3 + sub)) break;
-				area = 0;
-				if (n >= 3 + sub) {
-					const PV a = project(p0, hw, ox, oy), b = project(sub ? p2 : p1, hw, ox, oy), cc = project(sub ? p3 : p2, hw, ox, oy);
-					area = setup_tri(a, b, cc, scx, scy, scw, sch, tr);
-				}
-				emit_tri(D, tr, area, id1, slot, lane, keys);
-			}
+		for (int t = 0; t < nt; t++) {
+			Tri tr = t ? trB : trA; int area = t == 0 ? areaA : (t == 1 ? areaB : 0);
+			if (t >= 2 && clipped) { Tri ct; area = clip_tri(D.v0, D.v1, D.v2, D.mvp, D.h0, N, e, (t - 2) >> 1, (t - 2) & 1, &ct); if (area > 0) tr = ct; }
+			if (__any_sync(FULL, area > 0)) emit_tri(D, tr, area, id1, slot, lane, keys);
 		}
 	}
 }
 
+// biased edge function of (a -> b) at the origin (vertices are origin-relative) and its per-pixel steps; same integers
+// as edges_at32
+__device__ __forceinline__ void edge_origin(int ax, int ay, int bx, int by, int& e, int& sx, int& sy, int& bias) {
+	const int dx = bx - ax, dy = by - ay;
+	bias = (dy < 0 || (dy == 0 && dx < 0)) ? 0 : -1;
+	e = dx * (-ay) - dy * (-ax) + bias;
+	sx = -dy * 256; sy = dx * 256;
+}
+
 // persistent warps drain both queues.
-//  1. small queue: FOUR triangles per warp step, one quarter warp (8 lanes) each, walking the bbox in 8x1 pixel rows
-//     with int32 incremental edge functions (guaranteed to fit by the set-up kernel);
+//  1. small-quad queue: FOUR records per warp step, one quarter warp (8 lanes) each.  A record holds both triangles of a
+//     patch, A = (0,1,2) and B = (0,2,3); the common bbox is walked ONCE as one linear run of w*h pixels, 8 per step,
+//     with the five distinct int32 edge functions (the diagonal is shared: B's edge (0->2) is minus A's edge (2->0)).
+//     A pixel belongs to A or to B (never both: they lie on opposite sides of the diagonal and the top-left rule gives
+//     the diagonal itself to exactly one) and takes its depth from that triangle's plane — the same integers and the
+//     same float operations as two separate triangle walks, in about half the pixel visits;
 //  2. chunk queue: one warp per (triangle, chunk) of at most RAD_TILE x RAD_TILE pixels, 8x4 pixels per step.
 __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
@@ -497,31 +574,59 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
 	{
 		const uint32_t nsm = min(D.ctl->q_small, D.q_sm_cap);
-		const RadBigTri* __restrict__ qsm = D.q_sm;
+		const uint4* __restrict__ qsm = reinterpret_cast<const uint4*>(D.q_sm);
 		const int sub = lane >> 3, l8 = lane & 7;
+		const int W = (int)D.W;
 		for (uint32_t base = gw * 4; base < nsm; base += nw * 4) {
 			const uint32_t i = base + sub;
-			// the bbox is walked as ONE linear run of w*h pixels, 8 per step, so narrow boxes do not waste lanes
-			int npx = 0, w8 = 1, px0 = 0, py0 = 0, q8 = 0, r8 = 0;
-			Tri w; EdgeSet32 E; uint32_t id1 = 0; unsigned long long* keys = nullptr;
+			int npx = 0, w8 = 1, q8 = 0, r8 = 0, x = 0, y = 0;
+			int a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0;                         // biased edge values at the bbox origin
+			int a0x = 0, a1x = 0, a2x = 0, b0x = 0, b1x = 0, a0y = 0, a1y = 0, a2y = 0, b0y = 0, b1y = 0;
+			int bA1 = 0, bA2 = 0, bB1 = 0, bB2 = 0;
+			float Z0 = 0, dA1 = 0, dA2 = 0, dB2 = 0, invA = 0, invB = 0;
+			uint32_t id1 = 0; unsigned long long* kp = nullptr;
 			if (i < nsm) {
-				const RadBigTri r = qsm[i];
-				w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
-				w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
-				px0 = r.px0; py0 = r.py0; id1 = r.id1;
-				w8 = r.px1 - r.px0 + 1;
-				npx = w8 * (r.py1 - r.py0 + 1);
-				q8 = 8 / w8; r8 = 8 - q8 * w8;
-				keys = D.keys + (size_t)(r.slot - D.kbase) * D.RES;
-				edges_at32(w, px0, py0, E);               // biased edge values at the bbox origin; per-pixel steps in sx / sy
+				const uint4 r0 = __ldg(qsm + 4 * (size_t)i), r1 = __ldg(qsm + 4 * (size_t)i + 1), r2 = __ldg(qsm + 4 * (size_t)i + 2);
+				const uint2 r3 = __ldg(reinterpret_cast<const uint2*>(qsm + 4 * (size_t)i + 3));
+				const int x0 = (int)(r0.x << 16) >> 16, y0 = (int)r0.x >> 16, x1 = (int)(r0.y << 16) >> 16, y1 = (int)r0.y >> 16;
+				const int x2 = (int)(r0.z << 16) >> 16, y2 = (int)r0.z >> 16, x3 = (int)(r0.w << 16) >> 16, y3 = (int)r0.w >> 16;
+				int bA0, bB0;
+				edge_origin(x1, y1, x2, y2, a0, a0x, a0y, bA0);      // A: edges (1->2), (2->0), (0->1)
+				edge_origin(x2, y2, x0, y0, a1, a1x, a1y, bA1);
+				edge_origin(x0, y0, x1, y1, a2, a2x, a2y, bA2);
+				edge_origin(x2, y2, x3, y3, b0, b0x, b0y, bB0);      // B: edges (2->3), (3->0), (0->2)
+				edge_origin(x3, y3, x0, y0, b1, b1x, b1y, bB1);
+				{ const int dx = x2 - x0, dy = y2 - y0; bB2 = (dy < 0 || (dy == 0 && dx < 0)) ? 0 : -1; }
+				Z0 = __uint_as_float(r1.x);
+				dA1 = __uint_as_float(r1.y) - Z0; dA2 = __uint_as_float(r1.z) - Z0; dB2 = __uint_as_float(r1.w) - Z0;
+				invA = __uint_as_float(r2.x); invB = __uint_as_float(r2.y);
+				id1 = r2.z;
+				const uint32_t slot = r2.w & 0xFFFFu, rcpw = r2.w >> 16;
+				const int px0 = (int)(r3.x & 0xFFFFu), py0 = (int)(r3.x >> 16);
+				w8 = (int)(r3.y & 0xFFu);
+				npx = w8 * (int)((r3.y >> 8) & 0xFFu);
+				q8 = (int)((8u * rcpw) >> 15); r8 = 8 - q8 * w8;          // 8 / w, 8 % w
+				y = (int)(((uint32_t)l8 * rcpw) >> 15); x = l8 - y * w8;   // this lane's first pixel of the linear run
+				kp = D.keys + (size_t)(slot - D.kbase) * D.RES + (size_t)py0 * D.W + px0;
 			}
 			int msteps = (npx + 7) >> 3;
 			msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 8)); msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 16));
-			int idx = l8, y = l8 / w8, x = l8 - y * w8;
+			int idx = l8;
 			for (int s = 0; s < msteps; s++) {
 				if (idx < npx) {
-					const int e0 = E.e0 + x * E.sx0 + y * E.sy0, e1 = E.e1 + x * E.sx1 + y * E.sy1, e2 = E.e2 + x * E.sx2 + y * E.sy2;
-					if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, id1, keys + (size_t)(py0 + y) * D.W + (px0 + x), tagsh);
+					const int e0 = a0 + x * a0x + y * a0y, e1 = a1 + x * a1x + y * a1y, e2 = a2 + x * a2x + y * a2y;
+					const int f0 = b0 + x * b0x + y * b0y, f1 = b1 + x * b1x + y * b1y;
+					const int e1u = e1 - bA1;                        // unbiased A edge (2->0) == minus B's edge (0->2)
+					const int f2 = bB2 - e1u;
+					const bool inA = (e0 | e1 | e2) >= 0, inB = (f0 | f1 | f2) >= 0;
+					if (inA || inB) {
+						const float inv = inA ? invA : invB;
+						const float l1 = (float)(inA ? e1u : f1 - bB1) * inv, l2 = (float)(inA ? e2 - bA2 : -e1u) * inv;
+						float z = (Z0 + l1 * (inA ? dA1 : dA2)) + l2 * (inA ? dA2 : dB2);
+						z = fminf(fmaxf(z, 0.0f), 1.0f);
+						const uint32_t dq = __float2uint_rn(z * 16777215.0f);
+						if (dq < 0xFFFFFFu) atomicMin(kp + (y * W + x), ((unsigned long long)(tagsh | dq) << 32) | id1);
+					}
 				}
 				idx += 8; x += r8; y += q8;
 				if (x >= w8) { x -= w8; y++; }
@@ -659,7 +764,10 @@ static void launch_setup(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase) {
 	// exact stage: persistent grid over the surviving pairs (their number is only known on the device)
 	uint64_t want = ((uint64_t)D.P * n * 2 + 127) / 128;      // typically ~1 of 5 (patch, face) pairs survives
 	const uint32_t blocks = (uint32_t)(want < 148 ? 148 : (want > 148 * 16 ? 148 * 16 : want));
-	raster_setup_kernel<<<blocks, 128, 0, c->stream>>>(D);
+	static const int minb = [] { const char* e = getenv("RAD_SETUP_MINB"); const int v = e ? atoi(e) : 3; return v < 3 ? 3 : (v > 5 ? 5 : v); }();   // tuning knob: resident CTAs per SM the set-up kernel is compiled for
+	if (minb == 3) raster_setup_kernel<3><<<blocks, 128, 0, c->stream>>>(D);
+	else if (minb == 4) raster_setup_kernel<4><<<blocks, 128, 0, c->stream>>>(D);
+	else raster_setup_kernel<5><<<blocks, 128, 0, c->stream>>>(D);
 	c->launches += 2;
 }
 static void launch_chunks(rad_ctx* c, uint32_t kbase) {

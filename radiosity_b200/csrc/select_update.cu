@@ -163,6 +163,21 @@ __global__ void set_emitters_kernel(RadDev D, const uint32_t* __restrict__ ids, 
 // MODE 0: single GPU — reference association B += d_0, += d_1, ...   (reads F of all k slots)
 // MODE 1: multi GPU, local part — dB = sum of this rank's slots      (B untouched)
 // MODE 2: multi GPU, final part — B += dB (after the all-reduce), emitter update
+// F_h[i] of kFBatch consecutive slots: all the (independent) loads are issued before anything depends on them — the
+// kernel is a latency chain otherwise — then the slots are zeroed for the next batch (fill_n(p_tmp_formfactors, 0),
+// Main.cpp:1278).  Invalid (NULL) emitters are not read.
+constexpr int kFBatch = 16;
+__device__ __forceinline__ void take_F(const RadDev& D, const RadEmitter* s_em, uint32_t hb, uint32_t hend, uint32_t P, uint32_t i, float* f) {
+	#pragma unroll
+	for (int j = 0; j < kFBatch; j++) {
+		const uint32_t h = hb + j;
+		f[j] = (h < hend && s_em[h].valid) ? __ldcs(D.F + (size_t)h * P + i) : 0.0f;
+	}
+	#pragma unroll
+	for (int j = 0; j < kFBatch; j++)
+		if (f[j] != 0.0f) D.F[(size_t)(hb + j) * P + i] = 0.0f;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, int parity) {
 	extern __shared__ RadEmitter s_em[];
@@ -176,29 +191,35 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
 		if (MODE == 1) {
 			float dx = 0.0f, dy = 0.0f, dz = 0.0f;
-			for (uint32_t h = D.h0; h < D.h1; h++) {
-				if (!s_em[h].valid) continue;
-				float* fp = D.F + (size_t)h * P + i;
-				const float f = *fp;
-				if (f != 0.0f) *fp = 0.0f;
-				dx += ((s_em[h].S[0] * f) * rho) * s_em[h].color[0];
-				dy += ((s_em[h].S[1] * f) * rho) * s_em[h].color[1];
-				dz += ((s_em[h].S[2] * f) * rho) * s_em[h].color[2];
+			for (uint32_t hb = D.h0; hb < D.h1; hb += kFBatch) {
+				float f[kFBatch];
+				take_F(D, s_em, hb, D.h1, P, i, f);
+				#pragma unroll
+				for (int j = 0; j < kFBatch; j++) {
+					const uint32_t h = hb + j;
+					if (h >= D.h1 || !s_em[h].valid) continue;
+					dx += ((s_em[h].S[0] * f[j]) * rho) * s_em[h].color[0];
+					dy += ((s_em[h].S[1] * f[j]) * rho) * s_em[h].color[1];
+					dz += ((s_em[h].S[2] * f[j]) * rho) * s_em[h].color[2];
+				}
 			}
 			D.dB[i] = dx; D.dB[P + i] = dy; D.dB[2 * (size_t)P + i] = dz;
 			continue;
 		}
 		float bx = D.rad[i], by = D.rad[P + i], bz = D.rad[2 * (size_t)P + i];
 		if (MODE == 0) {
-			for (uint32_t h = 0; h < k; h++) {
-				if (!s_em[h].valid) continue;
-				float* fp = D.F + (size_t)h * P + i;
-				const float f = *fp;
-				if (f != 0.0f) *fp = 0.0f;                                  // fill_n(p_tmp_formfactors, 0) (Main.cpp:1278)
-				// p->radiosity += S_h * F[i] * reflectivity * colour(emitter_h)   (Main.cpp:1274)
-				bx += ((s_em[h].S[0] * f) * rho) * s_em[h].color[0];
-				by += ((s_em[h].S[1] * f) * rho) * s_em[h].color[1];
-				bz += ((s_em[h].S[2] * f) * rho) * s_em[h].color[2];
+			for (uint32_t hb = 0; hb < k; hb += kFBatch) {
+				float f[kFBatch];
+				take_F(D, s_em, hb, k, P, i, f);
+				#pragma unroll
+				for (int j = 0; j < kFBatch; j++) {
+					const uint32_t h = hb + j;
+					if (h >= k || !s_em[h].valid) continue;
+					// p->radiosity += S_h * F[i] * reflectivity * colour(emitter_h)   (Main.cpp:1274)
+					bx += ((s_em[h].S[0] * f[j]) * rho) * s_em[h].color[0];
+					by += ((s_em[h].S[1] * f[j]) * rho) * s_em[h].color[1];
+					bz += ((s_em[h].S[2] * f[j]) * rho) * s_em[h].color[2];
+				}
 			}
 		} else {
 			bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i];
@@ -274,18 +295,24 @@ void rad_launch_set_emitters(rad_ctx* c, const uint32_t* d_ids, uint32_t n) {
 	rad_launch_camera(c);
 }
 
+// small scenes: 64-thread blocks so that the patches spread over all SMs
+static uint32_t apply_threads(uint32_t P) { return P <= 148u * 8u * 64u ? 64u : 256u; }
+
 void rad_launch_apply(rad_ctx* c, bool fuse_select) {
 	const RadDev& D = c->d;
-	apply_kernel<0><<<patch_grid(D.P, 256), 256, D.k * sizeof(RadEmitter), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
+	const uint32_t T = apply_threads(D.P);
+	apply_kernel<0><<<patch_grid(D.P, T), T, D.k * sizeof(RadEmitter), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
 	c->launches++;
 }
 void rad_launch_delta(rad_ctx* c) {
 	const RadDev& D = c->d;
-	apply_kernel<1><<<patch_grid(D.P, 256), 256, D.k * sizeof(RadEmitter), c->stream>>>(D, 0, 0);
+	const uint32_t T = apply_threads(D.P);
+	apply_kernel<1><<<patch_grid(D.P, T), T, D.k * sizeof(RadEmitter), c->stream>>>(D, 0, 0);
 	c->launches++;
 }
 void rad_launch_finish(rad_ctx* c, bool fuse_select) {
 	const RadDev& D = c->d;
-	apply_kernel<2><<<patch_grid(D.P, 256), 256, D.k * sizeof(RadEmitter), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
+	const uint32_t T = apply_threads(D.P);
+	apply_kernel<2><<<patch_grid(D.P, T), T, D.k * sizeof(RadEmitter), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
 	c->launches++;
 }
