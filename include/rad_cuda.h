@@ -48,9 +48,11 @@ enum {
 	RAD_SELECT_TOPK = 1        /* clean top-k by |B|^2 (> 0), ordered (energy desc, id asc) — documented divergence */
 };
 
+#define RAD_MAX_HEMICUBES 512   /* largest batch (k); RAD_SELECT_REFERENCE: at most 64 */
+
 typedef struct rad_config {
 	uint32_t hemicube_side;   /* N  = Config::HEMICUBE_W()  (Config.cpp:34)             */
-	uint32_t hemicubes;       /* k  = Config::HEMICUBES_CNT() (Config.cpp:10,150)       */
+	uint32_t hemicubes;       /* k  = Config::HEMICUBES_CNT() (Config.cpp:10,150), 1 .. RAD_MAX_HEMICUBES */
 	uint32_t max_patches;     /* capacity of the scene arrays                            */
 	int32_t  device;          /* CUDA device ordinal                                     */
 	uint32_t select_mode;     /* RAD_SELECT_*                                            */

@@ -56,7 +56,8 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	if (!out || !cfg) { g_create_err = "rad_create: null argument"; return RAD_E_ARG; }
 	*out = nullptr;
 	if (cfg->hemicube_side < 16 || cfg->hemicube_side > 2048 || cfg->hemicube_side % 16) { g_create_err = "rad_create: hemicube_side must be a multiple of 16 in [16, 2048]"; return RAD_E_ARG; }
-	if (cfg->hemicubes < 1 || cfg->hemicubes > 64) { g_create_err = "rad_create: hemicubes must be in [1, 64]"; return RAD_E_ARG; }
+	if (cfg->hemicubes < 1 || cfg->hemicubes > RAD_MAX_HEMICUBES) { g_create_err = "rad_create: hemicubes must be in [1, 512]"; return RAD_E_ARG; }
+	if (cfg->hemicubes > 64 && cfg->select_mode == RAD_SELECT_REFERENCE) { g_create_err = "rad_create: the reference list selection supports at most 64 hemicubes (use RAD_SELECT_TOPK)"; return RAD_E_ARG; }
 	if (cfg->max_patches > (1u << 23)) { g_create_err = "rad_create: max_patches must be <= 8388608"; return RAD_E_ARG; }
 	if (cfg->max_patches < 1) { g_create_err = "rad_create: max_patches must be >= 1"; return RAD_E_ARG; }
 	int ndev = 0;
@@ -105,7 +106,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(D.F, (size_t)D.k * Pm)); A(dalloc(D.dB, 3 * Pm));
 	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.ctl, 1));
 	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap)); A(dalloc(D.pairs, (size_t)D.pairs_cap)); A(dalloc(D.nb, 8 * Pm)); A(dalloc(D.shade_e, 3 * Pm));
-	A(dalloc(D.ework, Pm < 64 ? (size_t)64 : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * 64)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * 64)); A(dalloc(proj, 16));
+	A(dalloc(D.ework, Pm < RAD_MAX_HEMICUBES ? (size_t)RAD_MAX_HEMICUBES : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(proj, 16));
 	#undef A
 	if (!ok) {
 		g_create_err = std::string("rad_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());

@@ -50,7 +50,8 @@ struct RadControl {               // small device-resident control block
 	uint32_t shots_done;
 	uint32_t pad;                 // triangles parked by the last batch (statistics)
 	uint32_t n_pairs;             // (patch, face) pairs that survived the conservative culls
-	uint32_t pad2[2];
+	uint32_t ticket;              // blocks finished ("last block merges" pattern of the selection / update kernels)
+	uint32_t pad2;
 };
 
 struct RadEmitter {               // per hemicube slot
@@ -87,7 +88,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	uint32_t* pairs; uint32_t pairs_cap;  // compacted (patch | face << 23 | local slot << 26) work list of the exact set-up stage
 	RadSmallQuad* q_sm; uint32_t q_sm_cap;   // small-quad queue (bbox steps <= RAD_SMALL_STEPS, int32 walk)
 	uint32_t* ework;              // [max(P,64)] scratch (emitter id staging)
-	unsigned long long* cand0; unsigned long long* cand1;   // top-k tournament candidates, ceil(P/2048)*64 keys each
+	unsigned long long* cand0; unsigned long long* cand1;   // top-k tournament candidates, ceil(P/2048) * keep keys each
 	const float* proj;            // [16]
 	int32_t* nb;                  // [8][P] neighbour ids (display stage), plane j = neighbour j
 	float* shade_e;               // [3][P] colour (.) (I + B) scratch of the display stage

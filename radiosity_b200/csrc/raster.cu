@@ -742,6 +742,7 @@ static uint32_t queue_group(const RadDev& D) {
 	const uint32_t nslots = D.h1 - D.h0;
 	uint64_t g = (uint64_t)min(min(D.q_tri_cap, D.q_sm_cap) / 2u, D.pairs_cap / 5u) / (D.P ? D.P : 1);
 	if (g < 1) g = 1;
+	if (g > 64) g = 64;                       // the pair list carries the group-local slot in 6 bits
 	return g > nslots ? nslots : (uint32_t)g;
 }
 // fused steady state: optional cap on the group's key-buffer footprint (RAD_L2_GROUP_MB).  Keeping a group's 64-bit keys

@@ -20,6 +20,10 @@ namespace {
 
 #define FULL 0xFFFFFFFFu
 
+// acquire/release fence at GPU scope.  NOT __threadfence(): that is a sequentially consistent fence here (MEMBAR.SC.GPU +
+// L1 invalidate), and SC fences of different blocks serialise — 258 of them cost 70 us in the update kernel.
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 __device__ __forceinline__ float len2(float x, float y, float z) { return x * x + y * y + z * z; }   // Vector.h:356-359
 
 __device__ __forceinline__ unsigned long long warp_max(unsigned long long v) {
@@ -112,19 +116,70 @@ __global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
 	}
 }
 
-// ---- clean top-k for k > 1: tournament of block-wide bitonic sorts -----------------------------
-// key = (bits(|B|^2) << 32 | ~id): unique, and descending key order == (energy desc, id asc).  Every block sorts a
-// chunk of 2048 keys in shared memory and keeps its best 64; levels repeat (P -> P/32 -> ...) until one block is
-// left, which writes the emitter list.  Exact and deterministic; 2 launches for 16 k patches, 3 for 1 M.
-constexpr int kTopChunk = 2048, kTopKeep = 64, kTopThreads = 1024;   // one compare-exchange per thread per bitonic stage
+// ---- clean top-k for k > 1: tournament of block-wide bitonic networks ---------------------------------------------
+// key = (bits(|B|^2) << 32 | ~id): unique, and descending key order == (energy desc, id asc).  Every block takes a
+// chunk of 2048 keys (two per thread, elements t and t + 1024), sorts groups of `keep` (= k rounded up to a power of
+// two, >= 64) and then halves the number of groups by prune-and-merge rounds (a[i] = max(a[i], b[keep-1-i]) leaves a
+// bitonic run holding the best `keep` of both groups) until one group is left: the chunk's best `keep`.  Compare-
+// exchanges over a distance below 32 elements are warp shuffles, only the longer ones go through shared memory.  The
+// chunks' winners are the next level's input; the block that finishes LAST on a level with <= 2048 / keep chunks
+// merges them and writes the emitter list — one launch for 16 k patches, two for 1 M.  Exact and deterministic.
+constexpr int kTopChunk = 2048, kTopThreads = 1024;
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+	return ((unsigned long long)__shfl_xor_sync(FULL, (unsigned)(v >> 32), m) << 32) | __shfl_xor_sync(FULL, (unsigned)v, m);
+}
+// one compare-exchange stage of a bitonic network over the 2048 elements of the block: element e meets e ^ j and the
+// pair is ordered descending where (e & k) == 0 (k = 0: descending everywhere).  a0 / a1 are elements t / t + 1024.
+__device__ __forceinline__ void cmpx_stage(unsigned long long& a0, unsigned long long& a1, unsigned long long* s, int t, int j, int k) {
+	if (j == 1024) {                       // the two elements of one thread
+		const bool desc = k == 0 || (t & k) == 0;
+		const unsigned long long hi = a0 > a1 ? a0 : a1, lo = a0 > a1 ? a1 : a0;
+		a0 = desc ? hi : lo; a1 = desc ? lo : hi;
+		return;
+	}
+	unsigned long long b0, b1;
+	if (j < 32) { b0 = shfl_xor_u64(a0, j); b1 = shfl_xor_u64(a1, j); }
+	else {
+		__syncthreads();
+		s[t] = a0; s[t + 1024] = a1;
+		__syncthreads();
+		b0 = s[t ^ j]; b1 = s[(t ^ j) + 1024];
+	}
+	const bool first = (t & j) == 0;       // this element is the lower index of its pair
+	const bool d0 = k == 0 || (t & k) == 0, d1 = k == 0 || ((t + 1024) & k) == 0;
+	a0 = ((a0 > b0) == (first == d0)) ? a0 : b0;
+	a1 = ((a1 > b1) == (first == d1)) ? a1 : b1;
+}
+// best `keep` of the block's 2048 keys, sorted descending, left in elements [0, keep) (a0 of threads t < keep)
+__device__ __forceinline__ void block_topk(unsigned long long& a0, unsigned long long& a1, unsigned long long* s, int t, int keep, bool groups_sorted) {
+	if (!groups_sorted)
+		for (int k = 2; k <= keep; k <<= 1)
+			for (int j = k >> 1; j > 0; j >>= 1) cmpx_stage(a0, a1, s, t, j, k == keep ? 0 : k);   // last pass: every group descending
+	for (int g = keep; g < kTopChunk; g <<= 1) {
+		// prune: groups (L, L + g/keep) -> element i of the first takes max with element g-1-i ... of the second
+		__syncthreads();
+		s[t] = a0; s[t + 1024] = a1;
+		__syncthreads();
+		{
+			const int e0 = t, e1 = t + 1024;
+			if ((e0 & g) == 0 && (e0 & (g - 1)) < keep) { const unsigned long long o = s[(e0 | g) + (keep - 1) - 2 * (e0 & (keep - 1))]; a0 = a0 > o ? a0 : o; }
+			if ((e1 & g) == 0 && (e1 & (g - 1)) < keep) { const unsigned long long o = s[(e1 | g) + (keep - 1) - 2 * (e1 & (keep - 1))]; a1 = a1 > o ? a1 : o; }
+		}
+		for (int j = keep >> 1; j > 0; j >>= 1) cmpx_stage(a0, a1, s, t, j, 0);   // bitonic merge of the surviving runs
+	}
+}
 
 template <bool FIRST>
 __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const unsigned long long* __restrict__ in, uint32_t n_in,
-                                                                  unsigned long long* __restrict__ out, int final_level) {
+                                                                  unsigned long long* __restrict__ out, int keep, int finish) {
 	__shared__ unsigned long long s[kTopChunk];
-	const uint32_t base = blockIdx.x * kTopChunk;
-	for (int t = threadIdx.x; t < kTopChunk; t += kTopThreads) {
-		const uint32_t i = base + t;
+	__shared__ bool s_last;
+	const int t = threadIdx.x;
+	unsigned long long a[2];
+	#pragma unroll
+	for (int r = 0; r < 2; r++) {
+		const uint32_t i = blockIdx.x * kTopChunk + t + r * 1024;
 		unsigned long long key = 0ull;
 		if (i < n_in) {
 			if (FIRST) {
@@ -132,42 +187,43 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 				if (eb != 0 && eb < 0x7F800000u) key = ((unsigned long long)eb << 32) | (0xFFFFFFFFu - i);
 			} else key = in[i];
 		}
-		s[t] = key;
+		a[r] = key;
 	}
-	__syncthreads();
-	for (int k = 2; k <= kTopChunk; k <<= 1)
-		for (int j = k >> 1; j > 0; j >>= 1) {
-			for (int t = threadIdx.x; t < kTopChunk / 2; t += kTopThreads) {
-				const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
-				const unsigned long long a = s[i], b = s[l];
-				const bool desc = (i & k) == 0;
-				if ((a < b) == desc) { s[i] = b; s[l] = a; }
-			}
-			__syncthreads();
-		}
-	if (final_level) {
-		if (threadIdx.x < D.k) {
-			const unsigned long long key = s[threadIdx.x];
-			D.em[threadIdx.x].id = key ? 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull) : 0u;
-			D.em[threadIdx.x].valid = key ? 1u : 0u;
-		}
-	} else if (threadIdx.x < kTopKeep) out[(size_t)blockIdx.x * kTopKeep + threadIdx.x] = s[threadIdx.x];
+	block_topk(a[0], a[1], s, t, keep, !FIRST);   // later levels read sorted groups of `keep`
+	if (gridDim.x > 1) {
+		if (t < keep) out[(size_t)blockIdx.x * keep + t] = a[0];
+		if (!finish) return;
+		// last block of the level merges the chunks' winners (at most 2048 keys, groups of `keep` already sorted)
+		// (one fence per block, after the barrier: it is cumulative over the block's writes; a fence in every thread
+		// costs tens of microseconds on this part)
+		__syncthreads();
+		if (t == 0) { fence_acq_rel(); const uint32_t done = atomicAdd(&D.ctl->ticket, 1u); s_last = done == gridDim.x - 1; if (s_last) { D.ctl->ticket = 0; fence_acq_rel(); } }
+		__syncthreads();
+		if (!s_last) return;
+		const uint32_t nc = gridDim.x * (uint32_t)keep;
+		a[0] = (uint32_t)t < nc ? __ldcg(out + t) : 0ull;
+		a[1] = (uint32_t)t + 1024 < nc ? __ldcg(out + t + 1024) : 0ull;
+		block_topk(a[0], a[1], s, t, keep, true);
+	}
+	if ((uint32_t)t < D.k) {
+		D.em[t].id = a[0] ? 0xFFFFFFFFu - (uint32_t)(a[0] & 0xFFFFFFFFull) : 0u;
+		D.em[t].valid = a[0] ? 1u : 0u;
+	}
 }
 
 __global__ void set_emitters_kernel(RadDev D, const uint32_t* __restrict__ ids, uint32_t n) {
-	const uint32_t h = threadIdx.x;
-	if (h < D.k) { D.em[h].id = h < n ? ids[h] : 0u; D.em[h].valid = (h < n && ids[h] < D.P) ? 1u : 0u; }
+	for (uint32_t h = threadIdx.x; h < D.k; h += blockDim.x) { D.em[h].id = h < n ? ids[h] : 0u; D.em[h].valid = (h < n && ids[h] < D.P) ? 1u : 0u; }
 }
 
 // ---- K4: energy transfer + emitter update (+ fused argmax) -----------------------------------
-// MODE 0: single GPU — reference association B += d_0, += d_1, ...   (reads F of all k slots)
-// MODE 1: multi GPU, local part — dB = sum of this rank's slots      (B untouched)
-// MODE 2: multi GPU, final part — B += dB (after the all-reduce), emitter update
+// what K4 needs of an emitter, 32 B = two 16-byte shared-memory loads per (patch, hemicube)
+struct EmLite { float S0, S1, S2; uint32_t valid; float c0, c1, c2; uint32_t id; };
+
 // F_h[i] of kFBatch consecutive slots: all the (independent) loads are issued before anything depends on them — the
 // kernel is a latency chain otherwise — then the slots are zeroed for the next batch (fill_n(p_tmp_formfactors, 0),
 // Main.cpp:1278).  Invalid (NULL) emitters are not read.
 constexpr int kFBatch = 16;
-__device__ __forceinline__ void take_F(const RadDev& D, const RadEmitter* s_em, uint32_t hb, uint32_t hend, uint32_t P, uint32_t i, float* f) {
+__device__ __forceinline__ void take_F(const RadDev& D, const EmLite* s_em, uint32_t hb, uint32_t hend, uint32_t P, uint32_t i, float* f) {
 	#pragma unroll
 	for (int j = 0; j < kFBatch; j++) {
 		const uint32_t h = hb + j;
@@ -177,73 +233,98 @@ __device__ __forceinline__ void take_F(const RadDev& D, const RadEmitter* s_em, 
 	for (int j = 0; j < kFBatch; j++)
 		if (f[j] != 0.0f) D.F[(size_t)(hb + j) * P + i] = 0.0f;
 }
-
-template <int MODE>
-__global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, int parity) {
-	extern __shared__ RadEmitter s_em[];
-	for (uint32_t h = threadIdx.x; h < D.k; h += blockDim.x) s_em[h] = D.em[h];
-	__syncthreads();
-	const uint32_t P = D.P, k = D.k;
-	const float rho = D.reflectivity;
-	int last_h = -1; uint32_t nvalid = 0;
-	for (uint32_t h = 0; h < k; h++) if (s_em[h].valid) { last_h = (int)h; nvalid++; }
-	unsigned long long best = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-		if (MODE == 1) {
-			float dx = 0.0f, dy = 0.0f, dz = 0.0f;
-			for (uint32_t hb = D.h0; hb < D.h1; hb += kFBatch) {
-				float f[kFBatch];
-				take_F(D, s_em, hb, D.h1, P, i, f);
-				#pragma unroll
-				for (int j = 0; j < kFBatch; j++) {
-					const uint32_t h = hb + j;
-					if (h >= D.h1 || !s_em[h].valid) continue;
-					dx += ((s_em[h].S[0] * f[j]) * rho) * s_em[h].color[0];
-					dy += ((s_em[h].S[1] * f[j]) * rho) * s_em[h].color[1];
-					dz += ((s_em[h].S[2] * f[j]) * rho) * s_em[h].color[2];
+// B += sum over slots [hb0, hend) of ((S_h * F_h[i]) * rho) (.) c_h, in slot order   (Main.cpp:1274)
+__device__ __forceinline__ void gather_transfer(const RadDev& D, const EmLite* s_em, uint32_t hb0, uint32_t hend, uint32_t P, uint32_t i, float rho,
+                                                float& bx, float& by, float& bz) {
+	for (uint32_t hb = hb0; hb < hend; hb += kFBatch) {
+		float f[kFBatch];
+		take_F(D, s_em, hb, hend, P, i, f);
+		#pragma unroll
+		for (int j = 0; j < kFBatch; j++) {
+			const uint32_t h = hb + j;
+			if (h < hend) {
+				const EmLite e = s_em[h];
+				if (e.valid) {
+					bx += ((e.S0 * f[j]) * rho) * e.c0;
+					by += ((e.S1 * f[j]) * rho) * e.c1;
+					bz += ((e.S2 * f[j]) * rho) * e.c2;
 				}
 			}
+		}
+	}
+}
+// emitter h of the batch: lastEnergy (before the subtraction, Main.cpp:1292), I += S, B -= S   (Main.cpp:1286-1295)
+__device__ __forceinline__ void emitter_update(const RadDev& D, const EmLite& e, bool is_last, uint32_t P, float& bx, float& by, float& bz) {
+	if (is_last) {
+		const float l = sqrtf(len2(bx, by, bz));
+		D.ctl->last_energy_len = l;
+		if ((double)l < 0.1) D.ctl->stopped = 1;                    // Main.cpp:1298
+	}
+	D.illum[e.id] += e.S0; D.illum[P + e.id] += e.S1; D.illum[2 * (size_t)P + e.id] += e.S2;
+	bx -= e.S0; by -= e.S1; bz -= e.S2;
+}
+
+// MODE 0: single GPU — reference association B += d_0, += d_1, ...   (reads F of all k slots)
+// MODE 1: multi GPU, local part — dB = sum of this rank's slots      (B untouched)
+// MODE 2: multi GPU, final part — B += dB (after the all-reduce), emitter update
+// "Is this patch an emitter of the batch" is answered in O(1): for every chunk of blockDim consecutive patches the block
+// first drops the emitters that fall into the chunk into a shared-memory table (k / blockDim entries per thread), so
+// the patch pass never compares against all k emitters.
+template <int MODE>
+__global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, int parity) {
+	extern __shared__ float4 s_raw[];
+	EmLite* s_em = reinterpret_cast<EmLite*>(s_raw);
+	__shared__ int s_slot[256];            // first emitter slot of each patch of the current chunk (INT_MAX: none)
+	__shared__ int s_last_h, s_dups; __shared__ uint32_t s_nvalid;
+	const uint32_t P = D.P, k = D.k;
+	if (threadIdx.x == 0) { s_last_h = -1; s_dups = 0; s_nvalid = 0; }
+	__syncthreads();
+	for (uint32_t h = threadIdx.x; h < k; h += blockDim.x) {
+		const RadEmitter e = D.em[h];
+		EmLite l; l.S0 = e.S[0]; l.S1 = e.S[1]; l.S2 = e.S[2]; l.valid = (e.valid && e.id < P) ? 1u : 0u; l.c0 = e.color[0]; l.c1 = e.color[1]; l.c2 = e.color[2]; l.id = e.id;
+		s_em[h] = l;
+		if (MODE != 1 && l.valid) { atomicMax(&s_last_h, (int)h); atomicAdd(&s_nvalid, 1u); }
+	}
+	__syncthreads();
+	const float rho = D.reflectivity;
+	unsigned long long best = 0;
+	for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < P; i0 += gridDim.x * blockDim.x) {
+		const uint32_t i = i0 + threadIdx.x;
+		if (MODE != 1) {
+			__syncthreads();
+			s_slot[threadIdx.x] = 0x7FFFFFFF;
+			__syncthreads();
+			for (uint32_t h = threadIdx.x; h < k; h += blockDim.x)
+				if (s_em[h].valid && s_em[h].id - i0 < blockDim.x) { if (atomicMin(&s_slot[s_em[h].id - i0], (int)h) != 0x7FFFFFFF) s_dups = 1; }
+			__syncthreads();
+		}
+		if (i >= P) continue;
+		if (MODE == 1) {
+			float dx = 0.0f, dy = 0.0f, dz = 0.0f;
+			gather_transfer(D, s_em, D.h0, D.h1, P, i, rho, dx, dy, dz);
 			D.dB[i] = dx; D.dB[P + i] = dy; D.dB[2 * (size_t)P + i] = dz;
 			continue;
 		}
 		float bx = D.rad[i], by = D.rad[P + i], bz = D.rad[2 * (size_t)P + i];
-		if (MODE == 0) {
-			for (uint32_t hb = 0; hb < k; hb += kFBatch) {
-				float f[kFBatch];
-				take_F(D, s_em, hb, k, P, i, f);
-				#pragma unroll
-				for (int j = 0; j < kFBatch; j++) {
-					const uint32_t h = hb + j;
-					if (h >= k || !s_em[h].valid) continue;
-					// p->radiosity += S_h * F[i] * reflectivity * colour(emitter_h)   (Main.cpp:1274)
-					bx += ((s_em[h].S[0] * f[j]) * rho) * s_em[h].color[0];
-					by += ((s_em[h].S[1] * f[j]) * rho) * s_em[h].color[1];
-					bz += ((s_em[h].S[2] * f[j]) * rho) * s_em[h].color[2];
+		if (MODE == 0) gather_transfer(D, s_em, 0, k, P, i, rho, bx, by, bz);
+		else { bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i]; }
+		const int h = s_slot[threadIdx.x];
+		if (h != 0x7FFFFFFF) {
+			emitter_update(D, s_em[h], h == s_last_h, P, bx, by, bz);
+			if (s_dups)                     // a patch listed twice (only rad_set_emitters can do that): all of them, in slot order
+				for (uint32_t g = (uint32_t)h + 1; g < k; g++) {
+					const EmLite o = s_em[g];
+					if (o.valid && o.id == i) emitter_update(D, o, (int)g == s_last_h, P, bx, by, bz);
 				}
-			}
-		} else {
-			bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i];
-		}
-		// emitters: lastEnergy, I += S, B -= S   (Main.cpp:1286-1295)
-		for (uint32_t h = 0; h < k; h++) {
-			if (!s_em[h].valid || s_em[h].id != i) continue;
-			if ((int)h == last_h) {
-				const float l = sqrtf(len2(bx, by, bz));
-				D.ctl->last_energy_len = l;
-				if ((double)l < 0.1) D.ctl->stopped = 1;                    // Main.cpp:1298
-			}
-			D.illum[i] += s_em[h].S[0]; D.illum[P + i] += s_em[h].S[1]; D.illum[2 * (size_t)P + i] += s_em[h].S[2];
-			bx -= s_em[h].S[0]; by -= s_em[h].S[1]; bz -= s_em[h].S[2];
 		}
 		D.rad[i] = bx; D.rad[P + i] = by; D.rad[2 * (size_t)P + i] = bz;
 		if (fuse_select) best = max(best, energy_key_last(len2(bx, by, bz), i));
 	}
-	if (MODE != 1) {
-		if (blockIdx.x == 0 && threadIdx.x == 0) { D.ctl->batches_done += 1; D.ctl->shots_done += nvalid; }
-		if (fuse_select) {
-			best = block_max(best);
-			if (threadIdx.x == 0 && best) atomicMax(&D.ctl->selkey[parity ^ 1], best);
-		}
+	if (MODE == 1) return;
+	if (blockIdx.x == 0 && threadIdx.x == 0) { D.ctl->batches_done += 1; D.ctl->shots_done += s_nvalid; }
+	if (fuse_select) {
+		best = block_max(best);
+		if (threadIdx.x == 0 && best) atomicMax(&D.ctl->selkey[parity ^ 1], best);
 	}
 }
 
@@ -272,18 +353,20 @@ void rad_launch_select(rad_ctx* c) {
 		select_reference_kernel<<<1, 1024, 0, c->stream>>>(D);
 		c->launches++;
 	} else {
+		int keep = 64;
+		while ((uint32_t)keep < D.k) keep <<= 1;
 		uint32_t n = D.P;
 		const unsigned long long* in = nullptr;
 		unsigned long long* out = D.cand0;
 		bool first = true;
 		for (;;) {
 			const uint32_t nb = (n + kTopChunk - 1) / kTopChunk;
-			const int fin = nb == 1;
-			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, fin);
-			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, fin);
+			const int fin = nb * (uint32_t)keep <= (uint32_t)kTopChunk;       // the level's last block can finish the selection
+			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin);
+			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin);
 			c->launches++;
 			if (fin) break;
-			n = nb * kTopKeep; in = out; out = out == D.cand0 ? D.cand1 : D.cand0; first = false;
+			n = nb * keep; in = out; out = out == D.cand0 ? D.cand1 : D.cand0; first = false;
 		}
 	}
 	rad_launch_camera(c);
@@ -301,18 +384,18 @@ static uint32_t apply_threads(uint32_t P) { return P <= 148u * 8u * 64u ? 64u : 
 void rad_launch_apply(rad_ctx* c, bool fuse_select) {
 	const RadDev& D = c->d;
 	const uint32_t T = apply_threads(D.P);
-	apply_kernel<0><<<patch_grid(D.P, T), T, D.k * sizeof(RadEmitter), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
+	apply_kernel<0><<<patch_grid(D.P, T), T, D.k * sizeof(EmLite), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
 	c->launches++;
 }
 void rad_launch_delta(rad_ctx* c) {
 	const RadDev& D = c->d;
 	const uint32_t T = apply_threads(D.P);
-	apply_kernel<1><<<patch_grid(D.P, T), T, D.k * sizeof(RadEmitter), c->stream>>>(D, 0, 0);
+	apply_kernel<1><<<patch_grid(D.P, T), T, D.k * sizeof(EmLite), c->stream>>>(D, 0, 0);
 	c->launches++;
 }
 void rad_launch_finish(rad_ctx* c, bool fuse_select) {
 	const RadDev& D = c->d;
 	const uint32_t T = apply_threads(D.P);
-	apply_kernel<2><<<patch_grid(D.P, T), T, D.k * sizeof(RadEmitter), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
+	apply_kernel<2><<<patch_grid(D.P, T), T, D.k * sizeof(EmLite), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
 	c->launches++;
 }

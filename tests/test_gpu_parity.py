@@ -176,7 +176,7 @@ def test_select_semantics(api, orc, golden, box):
     assert ids.tolist() == golden["reference"]["scenes"]["0.5"]["select_fresh"]["10"]["ids"]
     ctx.close()
     # clean top-k
-    for k in (2, 10, 64):
+    for k in (2, 10, 64, 100, 256, 512):
         ctx = make_ctx(api, orc, box, 32, k=k, select_mode=api.SELECT_TOPK)
         for rad in [r] + [seeded_radiosity(P, s) for s in (0, 7)]:
             ctx.upload_state(rad, il)
