@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t key_id(unsigned long long k, uint32_t tag) {
 template <bool FROM_KEYS>
 __global__ void __launch_bounds__(256) process_kernel(RadDev D, int keep_items) {
 	const uint32_t slot = D.h0 + blockIdx.y;
-	if (FROM_KEYS && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.ctl->q_tris | D.ctl->q_small | D.ctl->n_pairs)) { D.ctl->pad = D.ctl->q_tris + D.ctl->q_small; D.ctl->q_tris = 0; D.ctl->q_entries = 0; D.ctl->q_small = 0; D.ctl->n_pairs = 0; }
+	if (FROM_KEYS && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.qc->q_tris | D.qc->q_small | D.qc->n_pairs)) { D.qc->parked = D.qc->q_tris + D.qc->q_small; D.qc->q_tris = 0; D.qc->q_entries = 0; D.qc->q_small = 0; D.qc->n_pairs = 0; }
 	if (!D.em[slot].valid) return;
 	const int lane = threadIdx.x & 31;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -117,12 +117,15 @@ void rad_launch_process(rad_ctx* c) {
 	c->launches++;
 }
 
-void rad_launch_process_group(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase, bool keep_items) {
-	RadDev D = c->d;
-	D.h0 = c->d.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
-	process_kernel<true><<<process_grid(D), 256, 0, c->stream>>>(D, keep_items ? 1 : 0);
+void rad_launch_process_view(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n, uint32_t kbase, bool keep_items) {
+	RadDev D = V;
+	D.h0 = V.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
+	process_kernel<true><<<process_grid(D), 256, 0, st>>>(D, keep_items ? 1 : 0);
 	c->launches++;
 	c->keys_dirty = false;
+}
+void rad_launch_process_group(rad_ctx* c, uint32_t s0, uint32_t n, uint32_t kbase, bool keep_items) {
+	rad_launch_process_view(c, c->d, c->stream, s0, n, kbase, keep_items);
 }
 
 void rad_launch_resolve_process(rad_ctx* c, bool keep_items) {

@@ -75,6 +75,9 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
 	c->launches = 0; c->epoch = 254; c->multi_graph = true;
 	if (const char* e = getenv("RAD_MULTI_GRAPH")) c->multi_graph = atoi(e) != 0;
+	c->lanes = 4;             // concurrent raster lanes of the fused path (tuning knob RAD_LANES, 1 .. 8)
+	if (const char* e = getenv("RAD_LANES")) { const int v = atoi(e); if (v >= 1 && v <= RAD_MAX_LANES) c->lanes = (uint32_t)v; }
+	c->ev_fork = nullptr; for (int l = 0; l < RAD_MAX_LANES; l++) { c->lane_stream[l] = nullptr; c->ev_lane[l] = nullptr; }
 	c->inline_area_forced = false; c->l2_group_mb = 1u << 20;   // default: the whole batch in one group (measured faster than L2-sized groups)
 	if (const char* e = getenv("RAD_L2_GROUP_MB")) { const int v = atoi(e); if (v >= 1) c->l2_group_mb = (uint32_t)v; }   // tuning knob
 	RadDev& D = c->d;
@@ -99,6 +102,8 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	#define A(expr) do { if (ok && (expr) != cudaSuccess) ok = false; } while (0)
 	A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	A(cudaEventCreate(&c->ev0)); A(cudaEventCreate(&c->ev1));
+	A(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	for (int l = 0; l < RAD_MAX_LANES; l++) { A(cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking)); A(cudaEventCreateWithFlags(&c->ev_lane[l], cudaEventDisableTiming)); }
 	A(dalloc(v0, Pm)); A(dalloc(v1, Pm)); A(dalloc(v2, Pm));
 	A(dalloc(color, 3 * Pm)); A(dalloc(D.rad, 3 * Pm)); A(dalloc(D.illum, 3 * Pm));
 	A(dalloc(ff, (size_t)D.RES));
@@ -113,6 +118,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 		delete c; return RAD_E_CUDA;
 	}
 	D.v0 = v0; D.v1 = v1; D.v2 = v2; D.color = color; D.ff = ff; D.proj = proj;
+	D.qc = &D.ctl->lane[0];
 	cudaMemcpyAsync(proj, cfg->projection, 64, cudaMemcpyHostToDevice, c->stream);
 	cudaMemsetAsync(D.keys, 0xFF, (size_t)D.k * D.RES * 8, c->stream);
 	cudaMemsetAsync(D.items, 0, (size_t)D.k * D.RES * 4, c->stream);
@@ -142,6 +148,8 @@ int rad_destroy(rad_ctx* c) {
 	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.pairs); cudaFree(D.nb); cudaFree(D.shade_e); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->saved) cudaFree(c->saved);
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	for (int l = 0; l < RAD_MAX_LANES; l++) { if (c->ev_lane[l]) cudaEventDestroy(c->ev_lane[l]); if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]); }
 	if (c->d_stage) cudaFree(c->d_stage);
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->stream);
@@ -428,7 +436,8 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 		out->last_energy_len = ctl.last_energy_len;
 		cudaEventElapsedTime(&out->gpu_ms, c->ev0, c->ev1);
 		out->kernel_launches = (uint32_t)launches;
-		out->big_triangles = ctl.pad;
+		out->big_triangles = 0;
+		for (int l = 0; l < RAD_MAX_LANES; l++) out->big_triangles += ctl.lane[l].parked;
 		out->queue_overflow = ctl.q_overflow;
 	}
 	if (ctl.q_overflow) { c->err = "rad_shoot: tile queue overflow"; return RAD_E_CUDA; }

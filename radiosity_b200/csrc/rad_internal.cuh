@@ -38,18 +38,24 @@ struct __align__(16) RadSmallQuad {
 	uint16_t pad0; uint32_t pad1[2];
 };
 
+#define RAD_MAX_LANES 8            // concurrent raster lanes (streams) a batch can be split into
+struct RadQueueCtl {              // work-list counters of one raster lane
+	uint32_t q_tris;              // chunk queue: triangles parked
+	uint32_t q_entries;           // chunk queue: (triangle, chunk) entries
+	uint32_t q_small;             // small-quad queue: records (one quarter warp each)
+	uint32_t n_pairs;             // (patch, face) pairs that survived the conservative culls
+	uint32_t parked;              // records parked by the lane's last batch (statistics)
+	uint32_t pad[3];
+};
 struct RadControl {               // small device-resident control block
 	unsigned long long selkey[2]; // k==1 selection: (E bits << 32 | id), ping-pong by batch parity
-	uint32_t q_tris;              // tile queue: triangles parked
-	uint32_t q_entries;           // tile queue: (triangle, tile) entries
 	uint32_t q_overflow;
-	uint32_t q_small;             // small-triangle queue: records (one quarter warp each)
 	uint32_t stopped;             // |lastEnergy| < 0.1 seen
 	float last_energy_len;
 	uint32_t batches_done;
 	uint32_t shots_done;
-	uint32_t pad;                 // triangles parked by the last batch (statistics)
-	uint32_t n_pairs;             // (patch, face) pairs that survived the conservative culls
+	uint32_t pad;
+	RadQueueCtl lane[RAD_MAX_LANES];
 	uint32_t ticket;              // blocks finished ("last block merges" pattern of the selection / update kernels)
 	uint32_t pad2;
 };
@@ -83,6 +89,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	float* mvp;                   // [k][5][16] column-major
 	RadEmitter* em;               // [k]
 	RadControl* ctl;
+	RadQueueCtl* qc;              // this launch's lane counters (= &ctl->lane[lane])
 	RadBigTri* q_tri; RadQueueEntry* q_ent;
 	uint32_t q_tri_cap, q_ent_cap;
 	uint32_t* pairs; uint32_t pairs_cap;  // compacted (patch | face << 23 | local slot << 26) work list of the exact set-up stage
@@ -99,6 +106,11 @@ struct rad_ctx {
 	RadDev d;
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1;
+	// raster lanes: a batch's hemicube slots are split into `lanes` groups that run cull -> set-up -> queues -> process
+	// concurrently on their own streams (forked from / joined to `stream`), each with its own counters and its own
+	// share of the work lists; cur = the stream the launchers enqueue on
+	uint32_t lanes; cudaStream_t lane_stream[RAD_MAX_LANES]; cudaEvent_t ev_fork, ev_lane[RAD_MAX_LANES];
+	cudaStream_t cur;
 	std::string err;
 	bool have_nb;
 	bool have_ff, have_scene, emitters_ready, rendered, processed, keys_dirty;
