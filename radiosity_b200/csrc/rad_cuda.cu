@@ -177,22 +177,8 @@ int rad_set_formfactors(rad_ctx* c, const float* ff, uint32_t n) {
 }
 
 // Host arrays travel in the reference's layouts (AoS float[P*3], float[P*12]); the conversion to / from the device
-// layouts (three planes, three float4 streams) runs on the GPU (layout.cu), so the host only does one straight copy
-// through the pinned staging buffer per array.
-static int h2d_aos3(rad_ctx* c, const float* src, float* dst_planes, size_t P) {
-	memcpy(c->h_stage, src, 3 * P * 4);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, c->h_stage, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
-	rad_launch_aos3_to_planes(c, c->d_stage, dst_planes, (uint32_t)P);
-	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));       // the staging buffers are reused by the next array
-	return RAD_OK;
-}
-static int d2h_aos3(rad_ctx* c, const float* src_planes, float* dst, size_t P) {
-	rad_launch_planes_to_aos3(c, src_planes, c->d_stage, (uint32_t)P);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_stage, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
-	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-	memcpy(dst, c->h_stage, 3 * P * 4);
-	return RAD_OK;
-}
+// layouts (three planes, three float4 streams) runs on the GPU (layout.cu).  Every call packs its arrays back to back
+// into the pinned staging buffer, moves them with ONE copy and synchronises ONCE.
 static int stage_dev(rad_ctx* c, size_t bytes) {
 	int r = stage(c, bytes); if (r) return r;
 	if (c->d_stage_bytes >= bytes) return RAD_OK;
@@ -202,18 +188,43 @@ static int stage_dev(rad_ctx* c, size_t bytes) {
 	c->d_stage_bytes = bytes;
 	return RAD_OK;
 }
+// single-array forms (multi-GPU dB exchange)
+static int h2d_aos3(rad_ctx* c, const float* src, float* dst_planes, size_t P) {
+	memcpy(c->h_stage, src, 3 * P * 4);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, c->h_stage, 3 * P * 4, cudaMemcpyHostToDevice, c->stream));
+	rad_launch_aos3_to_planes(c, c->d_stage, dst_planes, (uint32_t)P);
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));       // the staging buffers are reused by the next call
+	return RAD_OK;
+}
+static int d2h_aos3(rad_ctx* c, const float* src_planes, float* dst, size_t P) {
+	rad_launch_planes_to_aos3(c, src_planes, c->d_stage, (uint32_t)P);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_stage, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	memcpy(dst, c->h_stage, 3 * P * 4);
+	return RAD_OK;
+}
+
+// enqueue only (no synchronisation): B and I from staging floats [off, off + 6P)
+static int enqueue_state_upload(rad_ctx* c, const float* rad3, const float* illum3, size_t off_floats) {
+	const size_t P = c->d.P;
+	memcpy(c->h_stage + off_floats, rad3, 3 * P * 4);
+	memcpy(c->h_stage + off_floats + 3 * P, illum3, 3 * P * 4);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage + off_floats, c->h_stage + off_floats, 6 * P * 4, cudaMemcpyHostToDevice, c->stream));
+	rad_launch_aos3_to_planes(c, c->d_stage + off_floats, c->d.rad, (uint32_t)P);
+	rad_launch_aos3_to_planes(c, c->d_stage + off_floats + 3 * P, c->d.illum, (uint32_t)P);
+	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.ctl, 0, sizeof(RadControl), c->stream));
+	c->selkey_valid = false; c->emitters_ready = c->rendered = c->processed = false;
+	return RAD_OK;
+}
 
 int rad_upload_state(rad_ctx* c, const float* rad3, const float* illum3) {
 	if (!c || !rad3 || !illum3) return RAD_E_ARG;
 	if (!c->have_scene) { c->err = "rad_upload_state: no scene"; return RAD_E_STATE; }
 	cudaSetDevice(c->cfg.device);
 	const size_t P = c->d.P;
-	int r = stage_dev(c, 12 * P * 4); if (r) return r;
-	if ((r = h2d_aos3(c, rad3, c->d.rad, P))) return r;
-	if ((r = h2d_aos3(c, illum3, c->d.illum, P))) return r;
-	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.ctl, 0, sizeof(RadControl), c->stream));
+	int r = stage_dev(c, 21 * P * 4); if (r) return r;
+	if ((r = enqueue_state_upload(c, rad3, illum3, 0))) return r;
 	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-	c->selkey_valid = false; c->emitters_ready = c->rendered = c->processed = false;
 	return RAD_OK;
 }
 
@@ -221,19 +232,21 @@ int rad_upload_scene(rad_ctx* c, const float* verts12, const float* color3, cons
 	if (!c || !verts12 || !color3 || !rad3 || !illum3) return RAD_E_ARG;
 	if (P < 1 || P > c->cfg.max_patches) { c->err = "rad_upload_scene: P out of range (max_patches)"; return RAD_E_ARG; }
 	cudaSetDevice(c->cfg.device);
-	drop_graph(c);
-	int r = stage_dev(c, (size_t)P * 12 * 4); if (r) return r;
+	if (P != c->d.P) drop_graph(c);           // the captured launches carry P (nothing else of the scene)
+	int r = stage_dev(c, (size_t)P * 21 * 4); if (r) return r;
+	// staging layout (floats): [0, 12P) quads | [12P, 15P) colour | [15P, 21P) B, I
 	// 48-byte quad records -> three float4 streams (coalesced 16 B loads per lane in the rasteriser)
 	memcpy(c->h_stage, verts12, (size_t)P * 48);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, c->h_stage, (size_t)P * 48, cudaMemcpyHostToDevice, c->stream));
+	memcpy(c->h_stage + (size_t)P * 12, color3, (size_t)P * 12);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, c->h_stage, (size_t)P * 60, cudaMemcpyHostToDevice, c->stream));
 	rad_launch_split_quads(c, c->d_stage, P);
-	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-	if ((r = h2d_aos3(c, color3, (float*)c->d.color, P))) return r;
+	rad_launch_aos3_to_planes(c, c->d_stage + (size_t)P * 12, (float*)c->d.color, P);
 	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.F, 0, (size_t)c->d.k * P * 4, c->stream));
-	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
 	c->d.P = P;
 	c->have_scene = true;
-	return rad_upload_state(c, rad3, illum3);
+	if ((r = enqueue_state_upload(c, rad3, illum3, (size_t)P * 15))) return r;
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	return RAD_OK;
 }
 
 int rad_download_state(rad_ctx* c, float* rad3, float* illum3) {
@@ -241,9 +254,14 @@ int rad_download_state(rad_ctx* c, float* rad3, float* illum3) {
 	if (!c->have_scene) { c->err = "rad_download_state: no scene"; return RAD_E_STATE; }
 	cudaSetDevice(c->cfg.device);
 	const size_t P = c->d.P;
-	int r = stage_dev(c, 12 * P * 4); if (r) return r;
-	if ((r = d2h_aos3(c, c->d.rad, rad3, P))) return r;
-	return d2h_aos3(c, c->d.illum, illum3, P);
+	int r = stage_dev(c, 21 * P * 4); if (r) return r;
+	rad_launch_planes_to_aos3(c, c->d.rad, c->d_stage, (uint32_t)P);
+	rad_launch_planes_to_aos3(c, c->d.illum, c->d_stage + 3 * P, (uint32_t)P);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_stage, 6 * P * 4, cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+	memcpy(rad3, c->h_stage, 3 * P * 4);
+	memcpy(illum3, c->h_stage + 3 * P, 3 * P * 4);
+	return RAD_OK;
 }
 
 static int need_ready(rad_ctx* c, const char* who) {
