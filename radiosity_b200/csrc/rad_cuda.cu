@@ -75,7 +75,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
 	c->launches = 0; c->epoch = 254; c->multi_graph = true;
 	if (const char* e = getenv("RAD_MULTI_GRAPH")) c->multi_graph = atoi(e) != 0;
-	c->lanes = 4;             // concurrent raster lanes of the fused path (tuning knob RAD_LANES, 1 .. 8)
+	c->lanes = 8;             // concurrent raster lanes of the fused path (tuning knob RAD_LANES, 1 .. 8)
 	if (const char* e = getenv("RAD_LANES")) { const int v = atoi(e); if (v >= 1 && v <= RAD_MAX_LANES) c->lanes = (uint32_t)v; }
 	c->ev_fork = nullptr; for (int l = 0; l < RAD_MAX_LANES; l++) { c->lane_stream[l] = nullptr; c->ev_lane[l] = nullptr; }
 	c->inline_area_forced = false; c->l2_group_mb = 1u << 20;   // default: the whole batch in one group (measured faster than L2-sized groups)

@@ -769,7 +769,8 @@ static void launch_setup(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t 
 	raster_cull_kernel<<<dim3((D.P + 255) / 256, 1, n), 256, 0, st>>>(D);
 	// exact stage: persistent grid over the surviving pairs (their number is only known on the device)
 	uint64_t want = ((uint64_t)D.P * n * 2 + 127) / 128;      // typically ~1 of 5 (patch, face) pairs survives
-	const uint32_t blocks = (uint32_t)(want < 148 ? 148 : (want > 148 * 16 ? 148 * 16 : want));
+	static const int sctas = [] { const char* e = getenv("RAD_SETUP_CTAS"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 16 ? 16 : v); }();   // tuning knob: CTAs per SM of the set-up grid (3 = what fits; more only queue up behind the other lanes)
+	const uint32_t blocks = (uint32_t)(want < 148 ? 148 : (want > 148u * sctas ? 148u * sctas : want));
 	static const int minb = [] { const char* e = getenv("RAD_SETUP_MINB"); const int v = e ? atoi(e) : 3; return v < 3 ? 3 : (v > 5 ? 5 : v); }();   // tuning knob: resident CTAs per SM the set-up kernel is compiled for
 	if (minb == 3) raster_setup_kernel<3><<<blocks, 128, 0, st>>>(D);
 	else if (minb == 4) raster_setup_kernel<4><<<blocks, 128, 0, st>>>(D);
@@ -779,7 +780,8 @@ static void launch_setup(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t 
 static void launch_chunks(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t kbase) {
 	RadDev D = V;
 	D.kbase = kbase;
-	raster_queue_kernel<<<148 * 8, 128, 0, st>>>(D);
+	static const int ctas = [] { const char* e = getenv("RAD_QUEUE_CTAS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();   // tuning knob: persistent CTAs per SM
+	raster_queue_kernel<<<148 * ctas, 128, 0, st>>>(D);
 	c->launches++;
 }
 
