@@ -9,8 +9,11 @@ patches (`area 0.014`), hemicube 512 (atlas 1024 x 768), 1024 shots per step fro
 shot in batches of k = 64 (the reference batches too, `hemicubes`, default 10) with the clean top-k schedule.  One
 "step" = one rad_shoot() call of 16 batches.  `value` = whole-job shots/s with the scene resident in HBM (device time,
 CUDA events on the launching stream inside rad_shoot, max over ranks); `e2e` = the same through the C ABI with HOST
-buffers: scene upload + shoot + state download inside the timed region.  With N > 1 the k emitters of every batch
-are sharded over the ranks and dB is combined by one NCCL all-reduce per batch (fixed total work: strong scaling).
+buffers: scene upload + shoot + state download inside the timed region.  With N > 1 the emitters of every batch
+are sharded over the ranks and dB is combined by one NCCL all-reduce per batch.  Default `--scaling weak`: every rank
+keeps k = 64 emitters per batch, i.e. the batch is the top-(64 N) list (per-GPU work fixed); `--scaling strong` keeps
+the batch at k = 64 and gives every rank 64 / N of it.  Shots are counted from the library's own counter (a batch
+whose list is not full — the first one of a fresh scene with 99 light patches — counts what it shot).
 
 `--impl reference` times the reference's own algorithm on the host cores (the CPU oracle port — GL/CL cannot run in
 this image) on a bounded sample of the same workload, all host threads.
@@ -185,6 +188,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: dB combined by the fused peer-memory kernel (default) or by ncclAllReduce")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1: emitters per batch grow with N (weak) or stay at k (strong)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -204,6 +209,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     area, N, k, batches, desc = wl
+    k_rank = k                                   # emitters per batch and rank
+    scaling = "strong" if (world == 1 or k == 1) else args.scaling
+    if world > 1 and scaling == "weak":
+        k = k * world                            # the batch is the top-(k N) list, every rank renders k of it
+        import re
+        desc = re.sub(r"(\d+) shots \(k=64 x (\d+) batch", lambda m: f"up to {k * int(m.group(2))} shots (k={k} = 64 per rank x {m.group(2)} batch", desc)
+    elif world > 1:
+        k_rank = k // world
     scene = api.Scene(area)
     v, _, c, r, il = scene.arrays()
     P = scene.P
@@ -212,7 +225,10 @@ def main():
     ctx.set_formfactors(api.formfactors(N))
     ctx.upload_scene(v, c, r, il)
     if world > 1:
-        multi.init_nccl(ctx, dist)
+        if args.exchange == "peer":
+            multi.init_peer(ctx, dist)
+        else:
+            multi.init_nccl(ctx, dist)
     ctx.save_state()
     shots_per_step = batches * k
     RES = 3 * N * N
@@ -230,6 +246,7 @@ def main():
         return ctx.shoot(batches)
 
     launches = 0
+    shots_timed = 0
     gpu_ms = []
     with ClockSampler(local, enabled=(rank == 0)) as clk:
         time.sleep(0.5)                                                   # let nvidia-smi finish starting before anything is timed
@@ -241,20 +258,22 @@ def main():
         for _ in range(args.steps):
             st = step_device()
             assert st.batches_done == batches and st.queue_overflow == 0
-            gpu_ms.append(st.gpu_ms); launches += st.kernel_launches
+            gpu_ms.append(st.gpu_ms); launches += st.kernel_launches; shots_timed += st.shots_done
         barrier()
         wall = time.perf_counter() - t0
 
         # e2e: host buffers in, host buffers out, through the C ABI
-        e2e_t = []
+        e2e_t = []; e2e_shots = 0
         for i in range(2 + min(args.steps, 10)):
             flush.fill_(1); torch.cuda.synchronize()
             barrier()
             t1 = time.perf_counter()
             ctx.upload_scene(v, c, r, il)
-            ctx.shoot(batches)
+            st = ctx.shoot(batches)
             rad, illum = ctx.download_state()
             e2e_t.append(time.perf_counter() - t1)
+            if i >= 2:
+                e2e_shots += st.shots_done
         e2e_t = e2e_t[2:]
 
         # per-kernel shares: the same batches un-graphed with CUDA events between the launches
@@ -282,13 +301,14 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = float(t[0]), float(t[1])
-    value = shots_per_step * args.steps / (total_ms * 1e-3)
-    e2e_value = shots_per_step * len(e2e_t) / e2e_s
+    value = shots_timed / (total_ms * 1e-3)
+    e2e_value = e2e_shots / e2e_s
+    shots_per_step = shots_timed // args.steps
 
     if rank == 0:
         peak, peak_src = measured_peak()
         h = ctx.lib  # noqa: F841
-        nslots = k // world if world > 1 else k
+        nslots = k_rank
         # stage times of one batch: [0] select+camera, [1] raster set-up, [2] raster queues, [4] fused ProcessHemicube, [5] apply
         # algorithmic bytes per launch: K3 12 B/patch; K1 48 B/patch/hemicube + 4 B/pixel (set-up + queue kernels together);
         # K2 8 B/pixel + 4 B/patch/hemicube (F); K4 36 B/patch + 4 B/patch/hemicube
@@ -322,16 +342,19 @@ def main():
                     "peak_source": peak_src,
                     "note": "the dominant kernel (K1 raster) is bound by set-up arithmetic, instruction issue and L2 atomics, not by HBM: its algorithmic bytes are tiny; "
                             "the HBM-bound kernel of the path is K2 (ProcessHemicube), reported in process_hemicube against the same peak"}
-        k2_bytes = k * 8.0 * RES + k * 4.0 * P
-        k2 = {"gpix_per_s": k * RES / (k2_ms * 1e-3) / 1e9, "ms_per_launch": k2_ms, "pixels_per_launch": k * RES,
+        kk = k_rank                                      # item buffers one launch of this rank covers
+        k2_bytes = kk * 8.0 * RES + kk * 4.0 * P
+        k2 = {"gpix_per_s": kk * RES / (k2_ms * 1e-3) / 1e9, "ms_per_launch": k2_ms, "pixels_per_launch": kk * RES,
               "achieved_gbs": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak_gbs": peak, "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak,
-              "algorithmic_bytes_per_pixel": 8, "itembuffer_bytes": k * RES * 4,
-              "note": "rad_bench_process: k item buffers of a real batch (%.0f MB, %s L2), uint32 ids + shared dFF table" % (k * RES * 4 / 1e6, "larger than" if k * RES * 4 > 126e6 else "fits in")}
+              "algorithmic_bytes_per_pixel": 8, "itembuffer_bytes": kk * RES * 4,
+              "note": "rad_bench_process: k item buffers of a real batch (%.0f MB, %s L2), uint32 ids + shared dFF table" % (kk * RES * 4 / 1e6, "larger than" if kk * RES * 4 > 126e6 else "fits in")}
         line = {"metric": "hemicubes_per_sec", "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": desc, "patches": P, "hemicube": N, "atlas": [2 * N, N + N // 2], "k": k, "batches_per_step": batches,
-                           "shots_per_step": shots_per_step, "schedule": "topk" if k > 1 else "reference", "parallelism": f"shooters/{world}" if world > 1 else "1gpu",
+                           "shots_per_step": shots_per_step, "schedule": "topk" if k > 1 else "reference",
+                           "parallelism": (f"{k_rank} of the batch's {k} shooters per rank, dB combined once per batch by " +
+                                           ("the fused peer-memory update kernel (NVLink, CUDA IPC)" if args.exchange == "peer" else "ncclAllReduce") if world > 1 else "1gpu"),
                            "l2": "256 MB write between timed iterations (flush)", "timing": "CUDA events on the launching stream inside rad_shoot, max over ranks",
                            "wall_s_incl_flush": wall},
                 "clocks": clocks,
@@ -344,6 +367,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()                           # nobody unmaps its exchange buffer while a peer may still read it
     ctx.close()
     if dist is not None:
         dist.barrier()

@@ -155,6 +155,13 @@ int rad_profile_batch(rad_ctx* ctx, float* ms6);
  * ONE ncclAllReduce(sum) per batch over NVLink; every rank applies the identical update. */
 int rad_nccl_unique_id(void* id_out128 /* 128 bytes */);
 int rad_comm_init(rad_ctx* ctx, int rank, int world, const void* id128);
+/* Fused exchange over peer memory (default of bench.py): every rank exposes ONE exchange buffer through CUDA IPC
+ * (rad_peer_handle -> 64 opaque bytes, all-gathered by the caller, e.g. torch.distributed), rad_peer_init maps the
+ * peers' buffers over NVLink.  The batch then needs no collective call: the local-dB kernel publishes its planes with
+ * a release flag on every peer, the update kernel waits for all flags and sums the ranks' planes in rank order while
+ * it applies them.  All ranks must have finished shooting before any of them calls rad_destroy. */
+int rad_peer_handle(rad_ctx* ctx, void* handle64_out /* 64 bytes */);
+int rad_peer_init(rad_ctx* ctx, int rank, int world, const void* handles /* world x 64 bytes, rank order */);
 /* partition-only mode (no NCCL): shard like `world` ranks and expose the partial dB so that a
  * host-side collective (e.g. torch.distributed gloo in CPU tests) can combine it */
 int rad_set_partition(rad_ctx* ctx, int rank, int world);

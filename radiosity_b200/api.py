@@ -63,6 +63,8 @@ CUDA_SIGNATURES = {
     "rad_nccl_unique_id": (ctypes.c_int, [_vp]),
     "rad_comm_init": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "rad_set_partition": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    "rad_peer_handle": (ctypes.c_int, [_vp, _vp]),
+    "rad_peer_init": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "rad_batch_partial": (ctypes.c_int, [_vp]),
     "rad_read_delta": (ctypes.c_int, [_vp, _vp]),
     "rad_write_delta": (ctypes.c_int, [_vp, _vp]),
@@ -367,6 +369,17 @@ class Context:
 
     def comm_init(self, rank, world, uid):
         self._ck(self.lib.rad_comm_init(self.h, rank, world, ctypes.c_char_p(uid)), "rad_comm_init")
+
+    def peer_handle(self):
+        """64-byte CUDA IPC handle of this rank's exchange buffer (fused dB exchange over peer memory)"""
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self.lib.rad_peer_handle(self.h, buf), "rad_peer_handle")
+        return buf.raw
+
+    def peer_init(self, rank, world, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._ck(self.lib.rad_peer_init(self.h, rank, world, ctypes.c_char_p(blob)), "rad_peer_init")
 
     def set_partition(self, rank, world):
         self._ck(self.lib.rad_set_partition(self.h, rank, world), "rad_set_partition")

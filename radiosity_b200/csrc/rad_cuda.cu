@@ -73,6 +73,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->graph_exec = nullptr; c->graph_batches = 0; c->graph_keep_items = false;
 	c->h_stage = nullptr; c->h_stage_bytes = 0; c->d_stage = nullptr; c->d_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
+	c->peer_mode = false; c->xbuf = nullptr; c->xbuf_bytes = 0; for (int r = 0; r < RAD_MAX_PEERS; r++) c->peer_ptr[r] = nullptr;
 	c->launches = 0; c->epoch = 254; c->multi_graph = true;
 	if (const char* e = getenv("RAD_MULTI_GRAPH")) c->multi_graph = atoi(e) != 0;
 	c->lanes = 8;             // concurrent raster lanes of the fused path (tuning knob RAD_LANES, 1 .. 8)
@@ -141,6 +142,8 @@ int rad_destroy(rad_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	drop_graph(c);
 	if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+	for (int r = 0; r < RAD_MAX_PEERS; r++) if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]);
+	if (c->xbuf) cudaFree(c->xbuf);
 	RadDev& D = c->d;
 	cudaFree((void*)D.v0); cudaFree((void*)D.v1); cudaFree((void*)D.v2); cudaFree((void*)D.color);
 	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
@@ -356,7 +359,7 @@ static int enqueue_batch_multi(rad_ctx* c, bool keep_items) {
 	rad_launch_select(c);
 	rad_launch_raster_process(c, keep_items);
 	rad_launch_delta(c);
-	if (c->nccl_comm) {
+	if (c->nccl_comm && !c->peer_mode) {
 		int rc = g_nccl.AllReduce(c->d.dB, c->d.dB, (size_t)3 * c->d.P, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream);
 		if (rc != 0) { c->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return RAD_E_NCCL; }
 	}
@@ -378,7 +381,7 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 		// sharded batches: the same CUDA-graph replay as on one GPU, the ncclAllReduce of every batch captured inside it
 		// (RAD_MULTI_GRAPH=0 falls back to direct launches)
 		const uint32_t GB = 8;
-		if (c->multi_graph && c->nccl_comm && n_batches >= GB) {
+		if (c->multi_graph && (c->nccl_comm || c->peer_mode) && n_batches >= GB) {
 			if (!c->graph_exec || c->graph_batches != GB || c->graph_keep_items != keep) {
 				drop_graph(c);
 				cudaGraph_t g = nullptr;
@@ -636,6 +639,40 @@ int rad_comm_init(rad_ctx* c, int rank, int world, const void* id128) {
 	NcclId id; memcpy(&id, id128, 128);
 	int rc = g_nccl.CommInitRank(&c->nccl_comm, world, id, rank);
 	if (rc != 0) { c->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); c->nccl_comm = nullptr; return RAD_E_NCCL; }
+	int r = rad_set_partition(c, rank, world);
+	c->partition_only = false;
+	return r;
+}
+
+// ---- fused exchange over peer memory (NVLink, CUDA IPC): no collective call, the update kernel reads every rank's dB ----
+int rad_peer_handle(rad_ctx* c, void* handle64_out) {
+	if (!c || !handle64_out) return RAD_E_ARG;
+	cudaSetDevice(c->cfg.device);
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	if (!c->xbuf) {
+		c->xbuf_bytes = (size_t)RAD_XB_DATA + 2ull * 3ull * c->cfg.max_patches * 4ull;
+		RAD_CUDA_TRY(c, cudaMalloc((void**)&c->xbuf, c->xbuf_bytes));
+		RAD_CUDA_TRY(c, cudaMemset(c->xbuf, 0, c->xbuf_bytes));
+	}
+	cudaIpcMemHandle_t h;
+	RAD_CUDA_TRY(c, cudaIpcGetMemHandle(&h, c->xbuf));
+	memcpy(handle64_out, &h, 64);
+	return RAD_OK;
+}
+int rad_peer_init(rad_ctx* c, int rank, int world, const void* handles /* world x 64 bytes, rank order */) {
+	if (!c || !handles || world < 1 || world > RAD_MAX_PEERS || rank < 0 || rank >= world) return RAD_E_ARG;
+	if (!c->xbuf) { c->err = "rad_peer_init: call rad_peer_handle first"; return RAD_E_STATE; }
+	cudaSetDevice(c->cfg.device);
+	drop_graph(c);
+	for (int r = 0; r < world; r++) {
+		if (r == rank) { c->d.xb[r] = c->xbuf; continue; }
+		cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + 64 * (size_t)r, 64);
+		void* p = nullptr;
+		RAD_CUDA_TRY(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		c->peer_ptr[r] = p; c->d.xb[r] = (char*)p;
+	}
+	c->d.xrank = (uint32_t)rank; c->d.xworld = (uint32_t)world; c->d.xPmax = c->cfg.max_patches;
+	c->peer_mode = true;
 	int r = rad_set_partition(c, rank, world);
 	c->partition_only = false;
 	return r;

@@ -38,6 +38,8 @@ struct __align__(16) RadSmallQuad {
 	uint16_t pad0; uint32_t pad1[2];
 };
 
+#define RAD_MAX_PEERS 8
+#define RAD_XB_DATA 2048           // byte offset of the dB planes inside an exchange buffer
 #define RAD_MAX_LANES 8            // concurrent raster lanes (streams) a batch can be split into
 struct RadQueueCtl {              // work-list counters of one raster lane
 	uint32_t q_tris;              // chunk queue: triangles parked
@@ -85,7 +87,12 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	unsigned long long* keys;     // [k][RES] (epoch tag << 56 | depth24 << 32 | id+1); empty = any other top byte
 	uint32_t* items;              // [k][RES] id+1
 	float* F;                     // [k][P]
-	float* dB;                    // [3][P] partial received energy (multi-GPU)
+	float* dB;                    // [3][P] partial received energy (multi-GPU: NCCL / host-mediated exchange)
+	// fused peer-memory exchange (multi-GPU, rad_peer_init): every rank owns one exchange buffer, mapped into all its
+	// peers over NVLink (CUDA IPC):  [0] uint32 seq | [128 + 128 r] uint32 flag of rank r | [RAD_XB_DATA] float dB[2][3][Pmax]
+	// xb[r] = rank r's buffer as seen from this GPU (xb[xrank] is the local one); xworld == 0: not in use
+	char* xb[RAD_MAX_PEERS];
+	uint32_t xrank, xworld, xPmax;
 	float* mvp;                   // [k][5][16] column-major
 	RadEmitter* em;               // [k]
 	RadControl* ctl;
@@ -124,6 +131,7 @@ struct rad_ctx {
 	float* d_stage; size_t d_stage_bytes;      // device mirror of the staging buffer
 	// multi-GPU
 	int rank, world; void* nccl_comm; bool partition_only; bool multi_graph;
+	bool peer_mode; char* xbuf; size_t xbuf_bytes; void* peer_ptr[RAD_MAX_PEERS];   // fused exchange over peer memory
 	uint32_t launches;            // kernels launched since last reset
 	uint32_t graph_epoch_after;   // epoch value after one replay of the captured graph
 	uint32_t epoch;               // next key epoch tag (254 .. 1, decreasing; 0 = clear the key buffers first)

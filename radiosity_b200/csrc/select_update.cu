@@ -23,6 +23,12 @@ namespace {
 // acquire/release fence at GPU scope.  NOT __threadfence(): that is a sequentially consistent fence here (MEMBAR.SC.GPU +
 // L1 invalidate), and SC fences of different blocks serialise — 258 of them cost 70 us in the update kernel.
 __device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// system scope (peer GPUs over NVLink): flags of the fused dB exchange
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ float* xb_planes(const RadDev& D, uint32_t r, uint32_t parity) {
+	return reinterpret_cast<float*>(D.xb[r] + RAD_XB_DATA) + (size_t)parity * 3 * D.xPmax;
+}
 
 __device__ __forceinline__ float len2(float x, float y, float z) { return x * x + y * y + z * z; }   // Vector.h:356-359
 
@@ -288,6 +294,24 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	__syncthreads();
 	const float rho = D.reflectivity;
 	unsigned long long best = 0;
+	// fused exchange: the batch's sequence number lives in this rank's exchange buffer (device side, so that CUDA-graph
+	// replays advance it); MODE 1 writes plane set (seq + 1) & 1 and its last block publishes seq + 1 to every peer,
+	// MODE 2 waits until every rank has published the current seq and then sums the ranks' planes in rank order —
+	// the same order on every GPU, so the replicas stay bit-identical.
+	const bool fused = (MODE != 0) && D.xworld > 0;
+	uint32_t xseq = 0;
+	float* dB_out = D.dB;
+	if (fused) {
+		xseq = *reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]);
+		if (MODE == 1) dB_out = xb_planes(D, D.xrank, (xseq + 1) & 1u);
+		if (MODE == 2) {
+			if (threadIdx.x < D.xworld) {
+				const uint32_t* flag = reinterpret_cast<const uint32_t*>(D.xb[D.xrank] + 128 + 128 * threadIdx.x);
+				while ((int32_t)(ld_acquire_sys(flag) - xseq) < 0) { }
+			}
+			__syncthreads();
+		}
+	}
 	for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < P; i0 += gridDim.x * blockDim.x) {
 		const uint32_t i = i0 + threadIdx.x;
 		if (MODE != 1) {
@@ -302,12 +326,21 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 		if (MODE == 1) {
 			float dx = 0.0f, dy = 0.0f, dz = 0.0f;
 			gather_transfer(D, s_em, D.h0, D.h1, P, i, rho, dx, dy, dz);
-			D.dB[i] = dx; D.dB[P + i] = dy; D.dB[2 * (size_t)P + i] = dz;
+			const size_t pl = fused ? D.xPmax : P;
+			dB_out[i] = dx; dB_out[pl + i] = dy; dB_out[2 * pl + i] = dz;
 			continue;
 		}
 		float bx = D.rad[i], by = D.rad[P + i], bz = D.rad[2 * (size_t)P + i];
 		if (MODE == 0) gather_transfer(D, s_em, 0, k, P, i, rho, bx, by, bz);
-		else { bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i]; }
+		else if (!fused) { bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i]; }
+		else {
+			float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+			for (uint32_t r = 0; r < D.xworld; r++) {         // peer loads over NVLink, L1 bypassed
+				const float* pl = xb_planes(D, r, xseq & 1u);
+				sx += __ldcg(pl + i); sy += __ldcg(pl + D.xPmax + i); sz += __ldcg(pl + 2 * (size_t)D.xPmax + i);
+			}
+			bx += sx; by += sy; bz += sz;
+		}
 		const int h = s_slot[threadIdx.x];
 		if (h != 0x7FFFFFFF) {
 			emitter_update(D, s_em[h], h == s_last_h, P, bx, by, bz);
@@ -320,7 +353,19 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 		D.rad[i] = bx; D.rad[P + i] = by; D.rad[2 * (size_t)P + i] = bz;
 		if (fuse_select) best = max(best, energy_key_last(len2(bx, by, bz), i));
 	}
-	if (MODE == 1) return;
+	if (MODE == 1) {
+		if (!fused) return;
+		// the last block to finish publishes the planes: seq + 1 into this rank's flag slot on every peer
+		__shared__ bool s_lastblk;
+		__syncthreads();
+		if (threadIdx.x == 0) { __threadfence_system(); const uint32_t done = atomicAdd(&D.ctl->ticket, 1u); s_lastblk = done == gridDim.x - 1; if (s_lastblk) D.ctl->ticket = 0; }
+		__syncthreads();
+		if (!s_lastblk) return;
+		if (threadIdx.x == 0) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(D.xb[D.xrank]) = xseq + 1; }
+		__syncthreads();
+		if (threadIdx.x < D.xworld) st_release_sys(reinterpret_cast<uint32_t*>(D.xb[threadIdx.x] + 128 + 128 * D.xrank), xseq + 1);
+		return;
+	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) { D.ctl->batches_done += 1; D.ctl->shots_done += s_nvalid; }
 	if (fuse_select) {
 		best = block_max(best);

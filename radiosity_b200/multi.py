@@ -4,7 +4,10 @@ The path shards at the shooter level: scene and state are repli
 deterministic selection, rank r renders and processes emitters [r*k/G, (r+1)*k/G) of the batch, the received energy
 dB[P][3] is summed over ranks, and every rank applies the identical update.
 
-Two ways to combine dB:
+Three ways to combine dB:
+  * fused over peer memory (Context.peer_init + Context.shoot): the ranks' exchange buffers are mapped into each other
+    over NVLink (CUDA IPC); the update kernel waits for the peers' release flags and sums their dB planes itself —
+    no collective call at all (the default of bench.py);
   * in-library NCCL (Context.comm_init + Context.shoot): one ncclAllReduce per batch on the context's stream —
     the production path, no host round trip;
   * host-mediated (shoot_batches_hosted below): read dB, all_reduce through any torch.distributed backend, write it
@@ -25,6 +28,15 @@ def init_nccl(ctx, dist):
     uid = [ctx.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(rank, world, uid[0])
+    return rank, world
+
+
+def init_peer(ctx, dist):
+    """Fused exchange over peer memory: all-gather the ranks' CUDA IPC handles, map the peers' exchange buffers."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.peer_handle())
+    ctx.peer_init(rank, world, handles)
     return rank, world
 
 

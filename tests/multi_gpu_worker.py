@@ -31,6 +31,25 @@ lst = [torch.zeros_like(t) for _ in range(world)]
 dist.all_gather(lst, t)
 assert all(torch.equal(lst[0], x) for x in lst), "ranks diverged"
 
+# fused exchange over peer memory (CUDA IPC over NVLink, no collective call): same batches, replicas bit-identical,
+# graph path (>= 8 batches) and direct path, and a second run after a state restore (sequence numbers keep counting)
+ctx3 = api.context_for_scene(scene, N, k, device=local, select_mode=api.SELECT_TOPK)
+multi.init_peer(ctx3, dist)
+ctx3.save_state()
+for nb in (batches, 2 * 8 + 3, batches):
+    ctx3.restore_state()
+    st3 = ctx3.shoot(nb)
+    assert st3.batches_done == nb and st3.queue_overflow == 0
+    rad3, illum3 = ctx3.download_state()
+    t3 = torch.from_numpy(np.concatenate([rad3, illum3]).copy()).cuda()
+    lst3 = [torch.zeros_like(t3) for _ in range(world)]
+    dist.all_gather(lst3, t3)
+    assert all(torch.equal(lst3[0], x) for x in lst3), "ranks diverged (peer exchange)"
+    if nb == batches:
+        assert rel_l2(rad3, rad) < 1e-6 and rel_l2(illum3, illum) < 1e-6, (rel_l2(rad3, rad), rel_l2(illum3, illum))
+dist.barrier()                                  # nobody unmaps while a peer may still be reading
+ctx3.close()
+
 # host-mediated variant of the same batches (dB through torch.distributed instead of the in-library NCCL call)
 ctx2 = api.context_for_scene(scene, N, k, device=local, select_mode=api.SELECT_TOPK)
 ctx2.set_partition(rank, world)
