@@ -1,0 +1,112 @@
+// Shooter camera: radiosity snapshot, emitter record and the five face MVPs (replaces the per-emitter CPU work of OnIdle,
+// Main.cpp:1161,1172-1183 -> Camera.cpp:19-52,97-103, Transform.cpp:26-46,70-80,127-156).  Shared by camera_kernel
+// (raster.cu) and by the tail of the fused k == 1 update kernel (select_update.cu), which prepares the next shot's camera
+// as soon as its argmax is known.
+#pragma once
+#include "rad_internal.cuh"
+
+namespace {
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 vneg(V3 a) { return mk(-a.x, -a.y, -a.z); }
+// the reference's v_Cross: a.v_Cross(b) == b x a   (Vector.h:534-537)
+__device__ __forceinline__ V3 rcross(V3 a, V3 b) {
+	return mk(b.y * a.z - b.z * a.y, b.z * a.x - b.x * a.z, b.x * a.y - b.y * a.x);
+}
+__device__ __forceinline__ V3 vnormalize(V3 a) {   // Vector.h:390-400: t = 1/len, then scale
+	float t = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+	if (t != 0) { t = 1 / t; a.x *= t; a.y *= t; a.z *= t; }
+	return a;
+}
+
+// out = a * b, column-major m[c*4+r], term order of Matrix4f::ProductOf (Vector.cpp:445-458)
+__device__ __forceinline__ void mat_product(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b) {
+	for (int c = 0; c < 4; c++)
+		for (int r = 0; r < 4; r++)
+			out[c * 4 + r] = a[r] * b[c * 4] + a[4 + r] * b[c * 4 + 1] + a[8 + r] * b[c * 4 + 2] + a[12 + r] * b[c * 4 + 3];
+}
+
+struct Quad { V3 a, b, c, d; };
+__device__ __forceinline__ Quad load_quad(const float4* __restrict__ v0, const float4* __restrict__ v1, const float4* __restrict__ v2, uint32_t p) {
+	float4 q0 = __ldg(v0 + p), q1 = __ldg(v1 + p), q2 = __ldg(v2 + p);
+	Quad q;
+	q.a = mk(q0.x, q0.y, q0.z); q.b = mk(q0.w, q1.x, q1.y); q.c = mk(q1.z, q1.w, q2.x); q.d = mk(q2.y, q2.z, q2.w);
+	return q;
+}
+__device__ __forceinline__ Quad load_quad(const RadDev& D, uint32_t p) { return load_quad(D.v0, D.v1, D.v2, p); }
+
+// face order in the atlas = p_patchlook_perm (Main.h:210-211): UP, DOWN, LEFT, RIGHT, FRONT
+// MVP = Perspective * LookAt(eye, target + eye, up), column-major m[c*4+r]
+__device__ void build_mvp(const Quad& q, int face, const float* __restrict__ proj, float* __restrict__ out) {
+	V3 eye = mk((q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f, (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f, (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f);
+	V3 normal = rcross(vsub(q.b, q.a), vsub(q.d, q.a));   // Patch::getNormal, Patch.cpp:272-276
+	V3 pup = vsub(q.d, q.a);                              // Patch::getUp, Patch.cpp:253-255
+	V3 target, up;
+	switch (face) {                                       // Camera::lookFromPatch, Camera.cpp:19-52
+	case 0: target = pup; up = vneg(normal); break;                       // UP
+	case 1: target = vneg(pup); up = normal; break;                       // DOWN
+	case 2: target = vneg(rcross(normal, pup)); up = pup; break;          // LEFT
+	case 3: target = rcross(normal, pup); up = pup; break;                // RIGHT
+	default: target = normal; up = pup; break;                            // FRONT
+	}
+	// CGLTransform::LookAt(eye, target + eye, up)
+	V3 dir = vnormalize(vsub(vadd(target, eye), eye));
+	V3 right = vnormalize(rcross(dir, up));
+	up = rcross(right, dir);
+	float la[16], tr[16], mv[16];
+	la[0] = right.x; la[4] = right.y; la[8] = right.z;
+	la[1] = up.x; la[5] = up.y; la[9] = up.z;
+	la[2] = -dir.x; la[6] = -dir.y; la[10] = -dir.z;
+	la[3] = 0; la[7] = 0; la[11] = 0; la[12] = 0; la[13] = 0; la[14] = 0; la[15] = 1;
+	// Translate(-eye): (*this) *= Translation  (Vector.cpp:325-330,478-527) — full products so that signed
+	// zeros come out exactly as in the reference
+	for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) tr[c * 4 + r] = (c < 3) ? (float)(c == r) : 0.0f;
+	tr[12] = -eye.x; tr[13] = -eye.y; tr[14] = -eye.z; tr[15] = 1;
+	mat_product(mv, la, tr);
+	mat_product(out, proj, mv);     // t_projection * t_modelview (Main.cpp:1183)
+}
+
+// thread 0 of a block: emitter record of slot h.  sel_parity >= 0 (k == 1 only): the emitter is first decoded from the
+// fused argmax key selkey[sel_parity] (all-zero energies leave key 0 == patch 0, the reference's seeded entry) and the
+// other key is recycled.  Loads bypass L1: in the update kernel's tail the state was just written by other blocks.
+__device__ __forceinline__ RadEmitter camera_emitter(const RadDev& D, uint32_t h, int sel_parity) {
+	RadEmitter e = D.em[h];
+	if (sel_parity >= 0) {
+		const unsigned long long key = __ldcg(&D.ctl->selkey[sel_parity]);
+		e.id = (uint32_t)(key & 0xFFFFFFFFull); e.valid = 1;
+		D.ctl->selkey[sel_parity ^ 1] = 0ull;
+	}
+	if (e.valid && e.id < D.P) {
+		for (int c = 0; c < 3; c++) {
+			e.S[c] = __ldcg(D.rad + (size_t)c * D.P + e.id);            // p_tmp_radiosities[hi] (Main.cpp:1161)
+			e.color[c] = D.color[(size_t)c * D.P + e.id];
+		}
+		const Quad q = load_quad(D, e.id);
+		e.eye[0] = (q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f; e.eye[1] = (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f; e.eye[2] = (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f;
+		const V3 n = rcross(vsub(q.b, q.a), vsub(q.d, q.a));
+		e.nrm[0] = n.x; e.nrm[1] = n.y; e.nrm[2] = n.z;
+		// orthonormal shooter frame for the conservative culls: s = n x u, t = u, f = n (u = v4 - v1 lies in the patch plane)
+		const V3 u = vsub(q.d, q.a);
+		const V3 sx = rcross(u, n);               // rcross(a, b) = b x a  ->  n x u
+		const float ls = rsqrtf(fmaxf(sx.x * sx.x + sx.y * sx.y + sx.z * sx.z, 1e-30f)), lt = rsqrtf(fmaxf(u.x * u.x + u.y * u.y + u.z * u.z, 1e-30f)), lf = rsqrtf(fmaxf(n.x * n.x + n.y * n.y + n.z * n.z, 1e-30f));
+		e.ax[0] = sx.x * ls; e.ax[1] = sx.y * ls; e.ax[2] = sx.z * ls;
+		e.ax[3] = u.x * lt; e.ax[4] = u.y * lt; e.ax[5] = u.z * lt;
+		e.ax[6] = n.x * lf; e.ax[7] = n.y * lf; e.ax[8] = n.z * lf;
+	} else e.valid = 0;
+	D.em[h] = e;
+	return e;
+}
+// whole block: slot h's emitter record (thread 0) and its five MVPs (threads 0..4)
+__device__ __forceinline__ void camera_block(const RadDev& D, uint32_t h, int sel_parity, RadEmitter* s_e) {
+	if (threadIdx.x == 0) *s_e = camera_emitter(D, h, sel_parity);
+	__syncthreads();
+	if (s_e->valid && threadIdx.x < RAD_NFACES) {
+		const Quad q = load_quad(D, s_e->id);
+		build_mvp(q, threadIdx.x, D.proj, D.mvp + ((size_t)h * RAD_NFACES + threadIdx.x) * 16);
+	}
+}
+
+} // namespace

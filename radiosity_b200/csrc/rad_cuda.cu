@@ -69,7 +69,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	rad_ctx* c = new rad_ctx();
 	c->cfg = *cfg;
 	c->have_ff = c->have_scene = c->emitters_ready = c->rendered = c->processed = c->keys_dirty = false;
-	c->parity = 0; c->selkey_valid = false; c->have_nb = false;
+	c->parity = 0; c->selkey_valid = false; c->cam_valid = false; c->have_nb = false;
 	c->graph_exec = nullptr; c->graph_batches = 0; c->graph_keep_items = false;
 	c->h_stage = nullptr; c->h_stage_bytes = 0; c->d_stage = nullptr; c->d_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
@@ -96,6 +96,9 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 		D.pairs_cap = (uint32_t)(wantp < (1u << 20) ? (1u << 20) : (wantp > (1u << 26) ? (1u << 26) : wantp));
 	}
 	D.kbase = 0; D.inline_area = 64;
+	D.small_steps = D.k == 1 ? 16 : RAD_SMALL_STEPS; D.tile = D.k == 1 ? 16 : RAD_TILE;
+	if (const char* e = getenv("RAD_SMALL_STEPS")) { const int v = atoi(e); if (v >= 1 && v <= 64) D.small_steps = (uint32_t)v; }   // tuning knobs
+	if (const char* e = getenv("RAD_TILE")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32 || v == 64) D.tile = (uint32_t)v; }
 	if (const char* e = getenv("RAD_INLINE_AREA")) { const int v = atoi(e); if (v >= 1 && v <= 4096) { D.inline_area = (uint32_t)v; c->inline_area_forced = true; } }   // tuning knob
 	const size_t Pm = cfg->max_patches;
 	float4 *v0, *v1, *v2; float *color, *ff, *proj;
@@ -352,7 +355,7 @@ static void enqueue_batch(rad_ctx* c, bool keep_items) {
 	rad_launch_raster_process(c, keep_items);
 	const bool fuse = c->d.k == 1;
 	rad_launch_apply(c, fuse);
-	if (fuse) { c->parity ^= 1; c->selkey_valid = true; }
+	if (fuse) { c->parity ^= 1; c->selkey_valid = true; c->cam_valid = true; }
 }
 
 static int enqueue_batch_multi(rad_ctx* c, bool keep_items) {
@@ -418,7 +421,8 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 			if (!c->graph_exec || c->graph_batches != GB || c->graph_keep_items != keep || c->graph_parity0 != c->parity) {
 				drop_graph(c);
 				cudaGraph_t g = nullptr;
-				const uint32_t parity0 = c->parity; const bool sk0 = c->selkey_valid; const uint32_t l0 = c->launches;
+				const uint32_t parity0 = c->parity; const bool sk0 = c->selkey_valid, cam0 = c->cam_valid; const uint32_t l0 = c->launches;
+				c->cam_valid = false;              // a replay starts with the camera kernel (it cannot know what ran before it)
 				RAD_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
 				rad_launch_clear_keys(c);          // a replay re-uses the captured epoch tags: start every replay from cleared keys
 				for (uint32_t b = 0; b < GB; b++) enqueue_batch(c, keep);
@@ -428,7 +432,7 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 				cudaGraphDestroy(g);
 				c->graph_batches = GB; c->graph_keep_items = keep;
 				c->graph_launches = c->launches - l0;
-				c->parity = parity0; c->selkey_valid = sk0; c->launches = l0;   // capture did not execute anything
+				c->parity = parity0; c->selkey_valid = sk0; c->cam_valid = cam0; c->launches = l0;   // capture did not execute anything
 				c->graph_parity0 = parity0;
 			}
 			while (n_batches - done >= GB && !stopped && c->parity == c->graph_parity0) {
@@ -436,7 +440,7 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 				launches += c->graph_launches;
 				done += GB;
 				c->epoch = c->graph_epoch_after;
-				if (c->d.k == 1) c->selkey_valid = true;
+				if (c->d.k == 1) { c->selkey_valid = true; c->cam_valid = true; }
 				if (stop_test) { RadControl t; if ((r = read_ctl(c, &t))) return r; stopped = t.stopped != 0; }
 			}
 		}
@@ -551,7 +555,7 @@ int rad_profile_batch(rad_ctx* c, float* ms6) {
 	rad_launch_raster_process_marked(c, keep, [&](int st) { mark(st); });
 	const bool fuse = c->d.k == 1;
 	rad_launch_apply(c, fuse); mark(5);
-	if (fuse) { c->parity ^= 1; c->selkey_valid = true; }
+	if (fuse) { c->parity ^= 1; c->selkey_valid = true; c->cam_valid = true; }
 	r = sync_check(c);
 	for (int i = 0; i < 6; i++) ms6[i] = 0.0f;
 	for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); ms6[stage[i]] += ms; }

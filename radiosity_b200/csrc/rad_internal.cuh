@@ -11,8 +11,8 @@
 
 #define RAD_NFACES 5
 #define RAD_CLEAR_KEY 0xFFFFFFFFFFFFFFFFull
-#define RAD_TILE 32               // chunk edge in pixels (chunks are bbox-relative)
-#define RAD_SMALL_STEPS 64         // quarter-warp walk: ceil(bbox pixels / 8) steps at most
+#define RAD_TILE 32               // chunk edge in pixels (chunks are bbox-relative) — batched default; see RadDev::tile
+#define RAD_SMALL_STEPS 64         // quarter-warp walk: ceil(bbox pixels / 8) steps at most — batched default; see RadDev::small_steps
 
 struct RadBigTri {                // one screen-space triangle parked for tile processing (64 B)
 	int X0, Y0, X1, Y1, X2, Y2;   // snapped window coordinates, 8 sub-pixel bits
@@ -34,7 +34,7 @@ struct __align__(16) RadSmallQuad {
 	uint16_t slot;                          // hemicube slot (atlas index)
 	uint16_t rcpw;                          // ceil(32768 / w): (l * rcpw) >> 15 == l / w exactly for l <= 8, w <= 255
 	uint16_t px0, py0;                      // bbox origin (already clipped to the face scissor)
-	uint8_t w, h;                           // bbox size in pixels (w * h <= 8 * RAD_SMALL_STEPS)
+	uint8_t w, h;                           // bbox size in pixels (w * h <= 8 * small_steps)
 	uint16_t pad0; uint32_t pad1[2];
 };
 
@@ -78,6 +78,9 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	uint32_t kbase;               // slot whose keys live in key buffer 0 (fused path recycles L2-resident key buffers per group)
 	uint32_t tag;                 // epoch tag (top byte of every key written / accepted by this launch)
 	uint32_t inline_area;         // bbox area (px) up to which the owning lane rasterises alone; larger -> chunk queue
+	uint32_t small_steps;         // longest quarter-warp walk (8 px per step) accepted by the small-quad queue
+	uint32_t tile;                // chunk edge (px) of the chunk queue.  k == 1 is latency-bound (one hemicube cannot fill the
+	                              // GPU): shorter walks and smaller chunks there, longer ones for batches
 	float reflectivity;
 	const float4* v0; const float4* v1; const float4* v2;   // verts: (v1.xyz,v2.x) (v2.yz,v3.xy) (v3.z,v4.xyz)
 	const float* color;           // [3][P] planes
@@ -100,7 +103,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	RadBigTri* q_tri; RadQueueEntry* q_ent;
 	uint32_t q_tri_cap, q_ent_cap;
 	uint32_t* pairs; uint32_t pairs_cap;  // compacted (patch | face << 23 | local slot << 26) work list of the exact set-up stage
-	RadSmallQuad* q_sm; uint32_t q_sm_cap;   // small-quad queue (bbox steps <= RAD_SMALL_STEPS, int32 walk)
+	RadSmallQuad* q_sm; uint32_t q_sm_cap;   // small-quad queue (bbox steps <= small_steps, int32 walk)
 	uint32_t* ework;              // [max(P,64)] scratch (emitter id staging)
 	unsigned long long* cand0; unsigned long long* cand1;   // top-k tournament candidates, ceil(P/2048) * keep keys each
 	const float* proj;            // [16]
@@ -123,6 +126,7 @@ struct rad_ctx {
 	bool have_ff, have_scene, emitters_ready, rendered, processed, keys_dirty;
 	uint32_t parity;              // selkey ping-pong for k==1
 	bool selkey_valid;            // selkey[parity] holds the argmax of the current B
+	bool cam_valid;               // ... and the fused update's tail has already prepared that shooter's camera (k == 1)
 	// CUDA graph of the steady-state loop
 	cudaGraphExec_t graph_exec; uint32_t graph_batches; bool graph_keep_items; uint32_t graph_launches, graph_parity0;
 	float* saved;                 // device snapshot of (B, I) for rad_save_state / rad_restore_state

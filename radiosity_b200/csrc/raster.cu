@@ -24,109 +24,14 @@
 // GL_CULL_FACE back); pixel centres, exact int64 edge functions, top-left tie rule; depth =
 // barycentric interpolation of (z*iw)*0.5+0.5, RNE-quantised to 24 bit, d >= 0xFFFFFF fails (LESS vs 1.0).
 #include "rad_internal.cuh"
+#include "camera.cuh"
 
 namespace {
 
-struct V3 { float x, y, z; };
-__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ V3 vneg(V3 a) { return mk(-a.x, -a.y, -a.z); }
-// the reference's v_Cross: a.v_Cross(b) == b x a   (Vector.h:534-537)
-__device__ __forceinline__ V3 rcross(V3 a, V3 b) {
-	return mk(b.y * a.z - b.z * a.y, b.z * a.x - b.x * a.z, b.x * a.y - b.y * a.x);
-}
-__device__ __forceinline__ V3 vnormalize(V3 a) {   // Vector.h:390-400: t = 1/len, then scale
-	float t = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
-	if (t != 0) { t = 1 / t; a.x *= t; a.y *= t; a.z *= t; }
-	return a;
-}
-
-// out = a * b, column-major m[c*4+r], term order of Matrix4f::ProductOf (Vector.cpp:445-458)
-__device__ __forceinline__ void mat_product(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b) {
-	for (int c = 0; c < 4; c++)
-		for (int r = 0; r < 4; r++)
-			out[c * 4 + r] = a[r] * b[c * 4] + a[4 + r] * b[c * 4 + 1] + a[8 + r] * b[c * 4 + 2] + a[12 + r] * b[c * 4 + 3];
-}
-
-struct Quad { V3 a, b, c, d; };
-__device__ __forceinline__ Quad load_quad(const float4* __restrict__ v0, const float4* __restrict__ v1, const float4* __restrict__ v2, uint32_t p) {
-	float4 q0 = __ldg(v0 + p), q1 = __ldg(v1 + p), q2 = __ldg(v2 + p);
-	Quad q;
-	q.a = mk(q0.x, q0.y, q0.z); q.b = mk(q0.w, q1.x, q1.y); q.c = mk(q1.z, q1.w, q2.x); q.d = mk(q2.y, q2.z, q2.w);
-	return q;
-}
-__device__ __forceinline__ Quad load_quad(const RadDev& D, uint32_t p) { return load_quad(D.v0, D.v1, D.v2, p); }
-
-// face order in the atlas = p_patchlook_perm (Main.h:210-211): UP, DOWN, LEFT, RIGHT, FRONT
-// MVP = Perspective * LookAt(eye, target + eye, up), column-major m[c*4+r]
-__device__ void build_mvp(const Quad& q, int face, const float* __restrict__ proj, float* __restrict__ out) {
-	V3 eye = mk((q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f, (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f, (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f);
-	V3 normal = rcross(vsub(q.b, q.a), vsub(q.d, q.a));   // Patch::getNormal, Patch.cpp:272-276
-	V3 pup = vsub(q.d, q.a);                              // Patch::getUp, Patch.cpp:253-255
-	V3 target, up;
-	switch (face) {                                       // Camera::lookFromPatch, Camera.cpp:19-52
-	case 0: target = pup; up = vneg(normal); break;                       // UP
-	case 1: target = vneg(pup); up = normal; break;                       // DOWN
-	case 2: target = vneg(rcross(normal, pup)); up = pup; break;          // LEFT
-	case 3: target = rcross(normal, pup); up = pup; break;                // RIGHT
-	default: target = normal; up = pup; break;                            // FRONT
-	}
-	// CGLTransform::LookAt(eye, target + eye, up)
-	V3 dir = vnormalize(vsub(vadd(target, eye), eye));
-	V3 right = vnormalize(rcross(dir, up));
-	up = rcross(right, dir);
-	float la[16], tr[16], mv[16];
-	la[0] = right.x; la[4] = right.y; la[8] = right.z;
-	la[1] = up.x; la[5] = up.y; la[9] = up.z;
-	la[2] = -dir.x; la[6] = -dir.y; la[10] = -dir.z;
-	la[3] = 0; la[7] = 0; la[11] = 0; la[12] = 0; la[13] = 0; la[14] = 0; la[15] = 1;
-	// Translate(-eye): (*this) *= Translation  (Vector.cpp:325-330,478-527) — full products so that signed
-	// zeros come out exactly as in the reference
-	for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) tr[c * 4 + r] = (c < 3) ? (float)(c == r) : 0.0f;
-	tr[12] = -eye.x; tr[13] = -eye.y; tr[14] = -eye.z; tr[15] = 1;
-	mat_product(mv, la, tr);
-	mat_product(out, proj, mv);     // t_projection * t_modelview (Main.cpp:1183)
-}
-
-// one block per hemicube slot: lanes 0..4 build the face matrices, lane 0 takes the snapshot.
-// sel_parity >= 0 (k == 1 only): the emitter is first decoded from the fused argmax key selkey[sel_parity]
-// (all-zero energies leave key 0 == patch 0, the reference's seeded entry) and the other key is recycled.
+// one block per hemicube slot: lanes 0..4 build the face matrices, lane 0 takes the snapshot (camera.cuh)
 __global__ void camera_kernel(RadDev D, int sel_parity) {
 	__shared__ RadEmitter s_e;
-	const uint32_t h = blockIdx.x;
-	if (threadIdx.x == 0) {
-		RadEmitter e = D.em[h];
-		if (sel_parity >= 0) {
-			const unsigned long long key = D.ctl->selkey[sel_parity];
-			e.id = (uint32_t)(key & 0xFFFFFFFFull); e.valid = 1;
-			D.ctl->selkey[sel_parity ^ 1] = 0ull;
-		}
-		if (e.valid && e.id < D.P) {
-			for (int c = 0; c < 3; c++) {
-				e.S[c] = D.rad[(size_t)c * D.P + e.id];            // p_tmp_radiosities[hi] (Main.cpp:1161)
-				e.color[c] = D.color[(size_t)c * D.P + e.id];
-			}
-			const Quad q = load_quad(D, e.id);
-			e.eye[0] = (q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f; e.eye[1] = (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f; e.eye[2] = (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f;
-			const V3 n = rcross(vsub(q.b, q.a), vsub(q.d, q.a));
-			e.nrm[0] = n.x; e.nrm[1] = n.y; e.nrm[2] = n.z;
-			// orthonormal shooter frame for the conservative culls: s = n x u, t = u, f = n (u = v4 - v1 lies in the patch plane)
-			const V3 u = vsub(q.d, q.a);
-			const V3 sx = rcross(u, n);               // rcross(a, b) = b x a  ->  n x u
-			const float ls = rsqrtf(fmaxf(sx.x * sx.x + sx.y * sx.y + sx.z * sx.z, 1e-30f)), lt = rsqrtf(fmaxf(u.x * u.x + u.y * u.y + u.z * u.z, 1e-30f)), lf = rsqrtf(fmaxf(n.x * n.x + n.y * n.y + n.z * n.z, 1e-30f));
-			e.ax[0] = sx.x * ls; e.ax[1] = sx.y * ls; e.ax[2] = sx.z * ls;
-			e.ax[3] = u.x * lt; e.ax[4] = u.y * lt; e.ax[5] = u.z * lt;
-			e.ax[6] = n.x * lf; e.ax[7] = n.y * lf; e.ax[8] = n.z * lf;
-		} else e.valid = 0;
-		D.em[h] = e;
-		s_e = e;
-	}
-	__syncthreads();
-	if (s_e.valid && threadIdx.x < RAD_NFACES) {
-		Quad q = load_quad(D, s_e.id);
-		build_mvp(q, threadIdx.x, D.proj, D.mvp + ((size_t)h * RAD_NFACES + threadIdx.x) * 16);
-	}
+	camera_block(D, blockIdx.x, sel_parity, &s_e);
 }
 
 struct CV { float x, y, z, w; };
@@ -297,7 +202,7 @@ __device__ __forceinline__ bool emit_quad(const RadDev& D, const Tri& ta, const 
 	if (areaA > 0 && areaB > 0) {
 		px0 = min(ta.bx & 0xFFFF, tb.bx & 0xFFFF); py0 = min(ta.by & 0xFFFF, tb.by & 0xFFFF);
 		bw = max(ta.bx >> 16, tb.bx >> 16) - px0 + 1; bh = max(ta.by >> 16, tb.by >> 16) - py0 + 1;
-		if (bw * bh > (int)D.inline_area && bw * bh <= 8 * RAD_SMALL_STEPS && bw <= 255 && bh <= 255) {   // w, h are bytes in the record
+		if (bw * bh > (int)D.inline_area && bw * bh <= 8 * (int)D.small_steps && bw <= 255 && bh <= 255) {   // w, h are bytes in the record
 			const int cx = px0 * 256 + 128, cy = py0 * 256 + 128;
 			const int r = max(max(radius_about(cx, cy, ta.X0, ta.Y0), radius_about(cx, cy, ta.X1, ta.Y1)), max(radius_about(cx, cy, ta.X2, ta.Y2), radius_about(cx, cy, X3, Y3)));
 			take = (long long)r * (long long)(r + (max(bw, bh) + 8) * 256) < (1ll << 29);
@@ -312,7 +217,7 @@ __device__ __forceinline__ bool emit_quad(const RadDev& D, const Tri& ta, const 
 
 // One triangle per lane (area == 0: none).  Small bboxes are walked by the owning lane; everything else is parked:
 // short int32-safe walks in the small-quad queue (as a quad whose second triangle is degenerate), the rest in the chunk
-// queue — bbox-relative chunks of RAD_TILE x RAD_TILE pixels, one warp each in raster_queue_kernel — so that no warp of
+// queue — bbox-relative chunks of tile x tile pixels (RadDev::tile), one warp each in raster_queue_kernel — so that no warp of
 // the set-up kernel ever carries a long pixel loop (load balance).  Queue slots are claimed with one atomic per warp.
 __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
                                          unsigned long long* __restrict__ keys) {
@@ -332,7 +237,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 		}
 	}
 	const bool parked = area > 0 && !tiny;
-	const bool small = parked && bw * bh <= 8 * RAD_SMALL_STEPS && bw <= 255 && bh <= 255 && fits32(tr, tr.bx & 0xFFFF, tr.by & 0xFFFF, max(bw, bh) + 8);   // +8: lanes start up to 7 px right of the origin
+	const bool small = parked && bw * bh <= 8 * (int)D.small_steps && bw <= 255 && bh <= 255 && fits32(tr, tr.bx & 0xFFFF, tr.by & 0xFFFF, max(bw, bh) + 8);   // +8: lanes start up to 7 px right of the origin
 	const bool big = parked && !small;
 	const unsigned ms = __ballot_sync(FULL, small), mb = __ballot_sync(FULL, big);
 	if ((ms | mb) == 0) return;
@@ -351,7 +256,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 		r.px0 = tr.bx & 0xFFFF; r.px1 = tr.bx >> 16; r.py0 = tr.by & 0xFFFF; r.py1 = tr.by >> 16;
 	}
 	int ncx = 0, ncy = 0, nent = 0;
-	if (big) { ncx = (bw - 1) / RAD_TILE + 1; ncy = (bh - 1) / RAD_TILE + 1; nent = ncx * ncy; }
+	if (big) { ncx = (bw - 1) / (int)D.tile + 1; ncy = (bh - 1) / (int)D.tile + 1; nent = ncx * ncy; }
 	int pre = nent;                               // inclusive warp scan of the entry counts
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += o; }
@@ -567,7 +472,7 @@ __device__ __forceinline__ void edge_origin(int ax, int ay, int bx, int by, int&
 //     A pixel belongs to A or to B (never both: they lie on opposite sides of the diagonal and the top-left rule gives
 //     the diagonal itself to exactly one) and takes its depth from that triangle's plane — the same integers and the
 //     same float operations as two separate triangle walks, in about half the pixel visits;
-//  2. chunk queue: one warp per (triangle, chunk) of at most RAD_TILE x RAD_TILE pixels, 8x4 pixels per step.
+//  2. chunk queue: one warp per (triangle, chunk) of at most tile x tile pixels, 8x4 pixels per step.
 __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
 	const uint32_t tagsh = D.tag << 24;
@@ -641,12 +546,13 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 		Tri w;
 		w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
 		w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
-		const int px0 = r.px0 + (int)e.tx * RAD_TILE, px1 = min(r.px1, px0 + RAD_TILE - 1);
-		const int py0 = r.py0 + (int)e.ty * RAD_TILE, py1 = min(r.py1, py0 + RAD_TILE - 1);
+		const int T = (int)D.tile;
+		const int px0 = r.px0 + (int)e.tx * T, px1 = min(r.px1, px0 + T - 1);
+		const int py0 = r.py0 + (int)e.ty * T, py1 = min(r.py1, py0 + T - 1);
 		unsigned long long* __restrict__ keys = D.keys + (size_t)(r.slot - D.kbase) * D.RES;
 		// this lane's first pixel; steps of 8 pixels in x and 4 in y
 		const int lx = px0 + (lane & 7), ly = py0 + (lane >> 3);
-		if (fits32(w, px0, py0, RAD_TILE)) {          // warp-uniform: small triangle around this chunk -> int32 walk
+		if (fits32(w, px0, py0, T)) {          // warp-uniform: small triangle around this chunk -> int32 walk
 			EdgeSet32 E; edges_at32(w, lx, ly, E);
 			for (int py = ly; py <= py1; py += 4, E.e0 += 4 * E.sy0, E.e1 += 4 * E.sy1, E.e2 += 4 * E.sy2) {
 				int e0 = E.e0, e1 = E.e1, e2 = E.e2;
@@ -658,7 +564,7 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 		}
 		EdgeSet E; edges_at(w, lx, ly, E);
 		// a triangle spread over several chunks: skip the chunk when one edge has all four corner pixels outside
-		if (r.px1 - r.px0 >= RAD_TILE || r.py1 - r.py0 >= RAD_TILE) {
+		if (r.px1 - r.px0 >= T || r.py1 - r.py0 >= T) {
 			// corner values from lane 0's origin value: e(px0,py0) + dx*sx + dy*sy
 			const long long dx = px1 - px0, dy = py1 - py0;
 			const long long c0 = __shfl_sync(FULL, E.e0, 0), c1 = __shfl_sync(FULL, E.e1, 0), c2 = __shfl_sync(FULL, E.e2, 0);
@@ -765,7 +671,9 @@ static void launch_setup(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t 
 	RadDev D = V;
 	D.h0 = V.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
 	// only bboxes of a few pixels are walked by the set-up lane itself; everything else goes through the balanced queues
-	if (!c->inline_area_forced) D.inline_area = D.P >= 65536u ? 64u : 8u;   // micro-triangle scenes: the queues' per-triangle overhead is not worth it
+	// measured: with a few pixels per patch (1 M patches at hemicube 1024) the queues' per-record overhead is not worth it
+	// and the owning lane walks bboxes up to 64 px itself; from ~8 pixels per patch on, everything above 2 px is parked
+	if (!c->inline_area_forced) D.inline_area = D.RES / (D.P ? D.P : 1u) >= 8u ? 2u : 64u;
 	raster_cull_kernel<<<dim3((D.P + 255) / 256, 1, n), 256, 0, st>>>(D);
 	// exact stage: persistent grid over the surviving pairs (their number is only known on the device)
 	uint64_t want = ((uint64_t)D.P * n * 2 + 127) / 128;      // typically ~1 of 5 (patch, face) pairs survives

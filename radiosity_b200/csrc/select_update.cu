@@ -15,6 +15,7 @@
 // reject-below-minimum while not full, tie groups reversed by every insertion); RAD_SELECT_TOPK runs a
 // tournament of block-wide bitonic sorts over keys (bits << 32 | ~id): energy desc, id asc.
 #include "rad_internal.cuh"
+#include "camera.cuh"
 
 namespace {
 
@@ -370,6 +371,13 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	if (fuse_select) {
 		best = block_max(best);
 		if (threadIdx.x == 0 && best) atomicMax(&D.ctl->selkey[parity ^ 1], best);
+		// k == 1: the block that finishes last knows the next shooter — it takes the snapshot and builds the five face
+		// matrices right here, so the next shot starts with its raster kernels (one launch less per shot)
+		__shared__ bool s_lastblk; __shared__ RadEmitter s_e;
+		__syncthreads();
+		if (threadIdx.x == 0) { fence_acq_rel(); const uint32_t done = atomicAdd(&D.ctl->ticket, 1u); s_lastblk = done == gridDim.x - 1; if (s_lastblk) { D.ctl->ticket = 0; fence_acq_rel(); } }
+		__syncthreads();
+		if (s_lastblk) camera_block(D, 0, parity ^ 1, &s_e);
 	}
 }
 
@@ -385,15 +393,15 @@ void rad_launch_argmax(rad_ctx* c) {
 	cudaMemsetAsync(&c->d.ctl->selkey[c->parity], 0, sizeof(unsigned long long), c->stream);
 	argmax_kernel<<<patch_grid(c->d.P, 256), 256, 0, c->stream>>>(c->d, (int)c->parity);
 	c->launches++;
-	c->selkey_valid = true;
+	c->selkey_valid = true; c->cam_valid = false;
 }
 
 void rad_launch_select(rad_ctx* c) {
 	const RadDev& D = c->d;
 	if (D.k == 1) {
-		if (!c->selkey_valid) rad_launch_argmax(c);
-		rad_launch_camera(c, (int)c->parity);      // decodes the fused argmax key, then snapshot + MVPs
-		return;
+		if (!c->selkey_valid) { rad_launch_argmax(c); c->cam_valid = false; }
+		if (!c->cam_valid) rad_launch_camera(c, (int)c->parity);      // decodes the fused argmax key, then snapshot + MVPs
+		return;                                                       // (otherwise the previous update's tail already did)
 	} else if (c->cfg.select_mode == RAD_SELECT_REFERENCE) {
 		select_reference_kernel<<<1, 1024, 0, c->stream>>>(D);
 		c->launches++;
