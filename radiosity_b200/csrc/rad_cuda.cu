@@ -632,6 +632,7 @@ int rad_set_partition(rad_ctx* c, int rank, int world) {
 	c->rank = rank; c->world = world;
 	c->d.h0 = (uint32_t)((uint64_t)c->d.k * rank / world);
 	c->d.h1 = (uint32_t)((uint64_t)c->d.k * (rank + 1) / world);
+	c->d.deal = (world > 1 && c->d.k % (uint32_t)world == 0) ? (uint32_t)world : 0u;   // top-k lists are dealt out to the ranks (load balance)
 	c->partition_only = c->nccl_comm == nullptr;
 	return RAD_OK;
 }

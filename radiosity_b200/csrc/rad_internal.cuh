@@ -70,11 +70,15 @@ struct RadEmitter {               // per hemicube slot
 	float eye[3];                 // patch centre (hemicube eye) and un-normalised patch normal: conservative culling only
 	float nrm[3];
 	float ax[9];                  // orthonormal shooter frame s, t, f (rows) for the conservative culls
+	uint32_t order;               // position in the selection list (== slot unless the list is dealt out to ranks, see RadDev::deal)
 };
 
 struct RadDev {                   // device pointers + sizes, passed by value to kernels
 	uint32_t P, N, W, H, RES, k;
 	uint32_t h0, h1;              // hemicube slots this rank renders/processes (kernels: slots of this launch)
+	uint32_t deal;                // G > 1: the top-k list is dealt out to the G ranks like cards (entry j -> rank j % G), so that every
+	                              // rank gets the same mix of strong and weak shooters and the same number of non-NULL ones:
+	                              // slot(j) = (j % G) * (k / G) + j / G.  0 / 1: slot(j) = j
 	uint32_t kbase;               // slot whose keys live in key buffer 0 (fused path recycles L2-resident key buffers per group)
 	uint32_t tag;                 // epoch tag (top byte of every key written / accepted by this launch)
 	uint32_t inline_area;         // bbox area (px) up to which the owning lane rasterises alone; larger -> chunk queue

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
 		const bool ok = (int)threadIdx.x < s_n;
 		D.em[threadIdx.x].id = ok ? l_id[threadIdx.x] : 0u;
 		D.em[threadIdx.x].valid = ok ? 1u : 0u;
+		D.em[threadIdx.x].order = threadIdx.x;
 	}
 }
 
@@ -213,13 +214,15 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 		block_topk(a[0], a[1], s, t, keep, true);
 	}
 	if ((uint32_t)t < D.k) {
-		D.em[t].id = a[0] ? 0xFFFFFFFFu - (uint32_t)(a[0] & 0xFFFFFFFFull) : 0u;
-		D.em[t].valid = a[0] ? 1u : 0u;
+		const uint32_t G = D.deal, slot = G > 1 ? ((uint32_t)t % G) * (D.k / G) + (uint32_t)t / G : (uint32_t)t;
+		D.em[slot].id = a[0] ? 0xFFFFFFFFu - (uint32_t)(a[0] & 0xFFFFFFFFull) : 0u;
+		D.em[slot].valid = a[0] ? 1u : 0u;
+		D.em[slot].order = (uint32_t)t;
 	}
 }
 
 __global__ void set_emitters_kernel(RadDev D, const uint32_t* __restrict__ ids, uint32_t n) {
-	for (uint32_t h = threadIdx.x; h < D.k; h += blockDim.x) { D.em[h].id = h < n ? ids[h] : 0u; D.em[h].valid = (h < n && ids[h] < D.P) ? 1u : 0u; }
+	for (uint32_t h = threadIdx.x; h < D.k; h += blockDim.x) { D.em[h].id = h < n ? ids[h] : 0u; D.em[h].valid = (h < n && ids[h] < D.P) ? 1u : 0u; D.em[h].order = h; }
 }
 
 // ---- K4: energy transfer + emitter update (+ fused argmax) -----------------------------------
@@ -290,9 +293,10 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 		const RadEmitter e = D.em[h];
 		EmLite l; l.S0 = e.S[0]; l.S1 = e.S[1]; l.S2 = e.S[2]; l.valid = (e.valid && e.id < P) ? 1u : 0u; l.c0 = e.color[0]; l.c1 = e.color[1]; l.c2 = e.color[2]; l.id = e.id;
 		s_em[h] = l;
-		if (MODE != 1 && l.valid) { atomicMax(&s_last_h, (int)h); atomicAdd(&s_nvalid, 1u); }
+		if (MODE != 1 && l.valid) { atomicMax(&s_last_h, (int)((e.order << 10) | h)); atomicAdd(&s_nvalid, 1u); }   // "last" = end of the list
 	}
 	__syncthreads();
+	const int last_h = s_last_h < 0 ? -1 : (s_last_h & 1023);
 	const float rho = D.reflectivity;
 	unsigned long long best = 0;
 	// fused exchange: the batch's sequence number lives in this rank's exchange buffer (device side, so that CUDA-graph
@@ -344,11 +348,11 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 		}
 		const int h = s_slot[threadIdx.x];
 		if (h != 0x7FFFFFFF) {
-			emitter_update(D, s_em[h], h == s_last_h, P, bx, by, bz);
+			emitter_update(D, s_em[h], h == last_h, P, bx, by, bz);
 			if (s_dups)                     // a patch listed twice (only rad_set_emitters can do that): all of them, in slot order
 				for (uint32_t g = (uint32_t)h + 1; g < k; g++) {
 					const EmLite o = s_em[g];
-					if (o.valid && o.id == i) emitter_update(D, o, (int)g == s_last_h, P, bx, by, bz);
+					if (o.valid && o.id == i) emitter_update(D, o, (int)g == last_h, P, bx, by, bz);
 				}
 		}
 		D.rad[i] = bx; D.rad[P + i] = by; D.rad[2 * (size_t)P + i] = bz;
