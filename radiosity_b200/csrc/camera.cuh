@@ -97,6 +97,8 @@ __device__ __forceinline__ RadEmitter camera_emitter(const RadDev& D, uint32_t h
 		e.ax[6] = n.x * lf; e.ax[7] = n.y * lf; e.ax[8] = n.z * lf;
 	} else e.valid = 0;
 	D.em[h] = e;
+	D.emlite[2 * h] = make_float4(e.S[0], e.S[1], e.S[2], __uint_as_float(e.valid ? (1u | (e.order << 1)) : 0u));
+	D.emlite[2 * h + 1] = make_float4(e.color[0], e.color[1], e.color[2], __uint_as_float(e.id));
 	return e;
 }
 // whole block: slot h's emitter record (thread 0) and its five MVPs (threads 0..4)

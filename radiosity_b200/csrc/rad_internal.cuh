@@ -102,6 +102,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	uint32_t xrank, xworld, xPmax;
 	float* mvp;                   // [k][5][16] column-major
 	RadEmitter* em;               // [k]
+	float4* emlite;               // [k][2] what the update kernel needs of an emitter: (S, valid | order << 1), (colour, id)
 	RadControl* ctl;
 	RadQueueCtl* qc;              // this launch's lane counters (= &ctl->lane[lane])
 	RadBigTri* q_tri; RadQueueEntry* q_ent;

@@ -290,10 +290,11 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	if (threadIdx.x == 0) { s_last_h = -1; s_dups = 0; s_nvalid = 0; }
 	__syncthreads();
 	for (uint32_t h = threadIdx.x; h < k; h += blockDim.x) {
-		const RadEmitter e = D.em[h];
-		EmLite l; l.S0 = e.S[0]; l.S1 = e.S[1]; l.S2 = e.S[2]; l.valid = (e.valid && e.id < P) ? 1u : 0u; l.c0 = e.color[0]; l.c1 = e.color[1]; l.c2 = e.color[2]; l.id = e.id;
+		const float4 a = D.emlite[2 * h], b = D.emlite[2 * h + 1];        // packed by the camera kernel
+		const uint32_t vo = __float_as_uint(a.w), id = __float_as_uint(b.w);
+		EmLite l; l.S0 = a.x; l.S1 = a.y; l.S2 = a.z; l.valid = (vo && id < P) ? 1u : 0u; l.c0 = b.x; l.c1 = b.y; l.c2 = b.z; l.id = id;
 		s_em[h] = l;
-		if (MODE != 1 && l.valid) { atomicMax(&s_last_h, (int)((e.order << 10) | h)); atomicAdd(&s_nvalid, 1u); }   // "last" = end of the list
+		if (MODE != 1 && l.valid) { atomicMax(&s_last_h, (int)(((vo >> 1) << 10) | h)); atomicAdd(&s_nvalid, 1u); }   // "last" = end of the list
 	}
 	__syncthreads();
 	const int last_h = s_last_h < 0 ? -1 : (s_last_h & 1023);
