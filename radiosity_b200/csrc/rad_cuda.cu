@@ -363,6 +363,7 @@ static int enqueue_batch_multi(rad_ctx* c, bool keep_items) {
 	rad_launch_select(c);
 	rad_launch_raster_process(c, keep_items);
 	rad_launch_delta(c);
+	if (c->peer_mode && c->d.xtwo) rad_launch_xreduce(c);
 	if (c->nccl_comm && !c->peer_mode) {
 		int rc = g_nccl.AllReduce(c->d.dB, c->d.dB, (size_t)3 * c->d.P, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream);
 		if (rc != 0) { c->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return RAD_E_NCCL; }
@@ -656,7 +657,7 @@ int rad_peer_handle(rad_ctx* c, void* handle64_out) {
 	cudaSetDevice(c->cfg.device);
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
 	if (!c->xbuf) {
-		c->xbuf_bytes = (size_t)RAD_XB_DATA + 2ull * 3ull * c->cfg.max_patches * 4ull;
+		c->xbuf_bytes = (size_t)RAD_XB_DATA + 3ull * 3ull * c->cfg.max_patches * 4ull;
 		RAD_CUDA_TRY(c, cudaMalloc((void**)&c->xbuf, c->xbuf_bytes));
 		RAD_CUDA_TRY(c, cudaMemset(c->xbuf, 0, c->xbuf_bytes));
 	}
@@ -678,6 +679,9 @@ int rad_peer_init(rad_ctx* c, int rank, int world, const void* handles /* world 
 		c->peer_ptr[r] = p; c->d.xb[r] = (char*)p;
 	}
 	c->d.xrank = (uint32_t)rank; c->d.xworld = (uint32_t)world; c->d.xPmax = c->cfg.max_patches;
+	// one shot (every rank reads all peers' planes) while that is a few MB, two shots (reduce-scatter + all-gather) beyond
+	c->d.xtwo = (world > 2 && (uint64_t)c->cfg.max_patches * 12ull * (uint64_t)(world - 1) > (4ull << 20)) ? 1u : 0u;
+	if (const char* e = getenv("RAD_XTWO")) c->d.xtwo = atoi(e) != 0 ? 1u : 0u;   // tuning knob
 	c->peer_mode = true;
 	int r = rad_set_partition(c, rank, world);
 	c->partition_only = false;

@@ -39,7 +39,8 @@ struct __align__(16) RadSmallQuad {
 };
 
 #define RAD_MAX_PEERS 8
-#define RAD_XB_DATA 2048           // byte offset of the dB planes inside an exchange buffer
+#define RAD_XB_DATA 4096           // byte offset of the dB planes inside an exchange buffer
+#define RAD_XB_FLAG2 2048          // byte offset of the second flag row (two-shot exchange: reduced slices ready)
 #define RAD_MAX_LANES 8            // concurrent raster lanes (streams) a batch can be split into
 struct RadQueueCtl {              // work-list counters of one raster lane
 	uint32_t q_tris;              // chunk queue: triangles parked
@@ -96,10 +97,12 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	float* F;                     // [k][P]
 	float* dB;                    // [3][P] partial received energy (multi-GPU: NCCL / host-mediated exchange)
 	// fused peer-memory exchange (multi-GPU, rad_peer_init): every rank owns one exchange buffer, mapped into all its
-	// peers over NVLink (CUDA IPC):  [0] uint32 seq | [128 + 128 r] uint32 flag of rank r | [RAD_XB_DATA] float dB[2][3][Pmax]
+	// peers over NVLink (CUDA IPC):  [0] uint32 seq | [128 + 128 r] uint32 flag of rank r | [RAD_XB_FLAG2 + 128 r] second flag
+	// row | [RAD_XB_DATA] float dB[2][3][Pmax] | float red[3][Pmax] (two-shot: this rank's reduced slice of the patches)
 	// xb[r] = rank r's buffer as seen from this GPU (xb[xrank] is the local one); xworld == 0: not in use
 	char* xb[RAD_MAX_PEERS];
 	uint32_t xrank, xworld, xPmax;
+	uint32_t xtwo;                // two-shot exchange (reduce-scatter kernel + all-gather in the update kernel) for large P
 	float* mvp;                   // [k][5][16] column-major
 	RadEmitter* em;               // [k]
 	float4* emlite;               // [k][2] what the update kernel needs of an emitter: (S, valid | order << 1), (colour, id)
@@ -164,6 +167,7 @@ void rad_launch_raster_process(rad_ctx* c, bool keep_items);    // steady state:
 void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::function<void(int)>& mark);   // same, mark(stage) after each launch (1 set-up, 2 chunks, 4 process)
 void rad_launch_apply(rad_ctx* c, bool fuse_select); // S4..S6 (+ argmax of the new B for k==1)
 void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB
+void rad_launch_xreduce(rad_ctx* c);                // multi-GPU, fused two-shot exchange: this rank's slice of the summed dB
 void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update
 void rad_launch_argmax(rad_ctx* c);                 // k==1: prime selkey[parity] from the current B
 void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out);

@@ -30,6 +30,27 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm vo
 __device__ __forceinline__ float* xb_planes(const RadDev& D, uint32_t r, uint32_t parity) {
 	return reinterpret_cast<float*>(D.xb[r] + RAD_XB_DATA) + (size_t)parity * 3 * D.xPmax;
 }
+__device__ __forceinline__ float* xb_reduced(const RadDev& D, uint32_t r) { return reinterpret_cast<float*>(D.xb[r] + RAD_XB_DATA) + (size_t)6 * D.xPmax; }
+// spin until every rank's flag in row `row_off` of this rank's exchange buffer has reached seq (threads 0 .. world-1)
+__device__ __forceinline__ void xb_wait(const RadDev& D, uint32_t row_off, uint32_t seq) {
+	if (threadIdx.x < D.xworld) {
+		const uint32_t* flag = reinterpret_cast<const uint32_t*>(D.xb[D.xrank] + row_off + 128 * threadIdx.x);
+		while ((int32_t)(ld_acquire_sys(flag) - seq) < 0) { }
+	}
+	__syncthreads();
+}
+// the block that finishes last publishes `seq` into this rank's slot of flag row `row_off` on every peer
+__device__ __forceinline__ void xb_publish_last(const RadDev& D, uint32_t row_off, uint32_t seq, bool bump_seq) {
+	__shared__ bool s_lastblk;
+	__syncthreads();
+	if (threadIdx.x == 0) { __threadfence_system(); const uint32_t done = atomicAdd(&D.ctl->ticket, 1u); s_lastblk = done == gridDim.x - 1; if (s_lastblk) D.ctl->ticket = 0; }
+	__syncthreads();
+	if (!s_lastblk) return;
+	if (threadIdx.x == 0) { __threadfence_system(); if (bump_seq) *reinterpret_cast<volatile uint32_t*>(D.xb[D.xrank]) = seq; }
+	__syncthreads();
+	if (threadIdx.x < D.xworld) st_release_sys(reinterpret_cast<uint32_t*>(D.xb[threadIdx.x] + row_off + 128 * D.xrank), seq);
+}
+__device__ __forceinline__ uint32_t xb_slice(const RadDev& D) { return (D.P + D.xworld - 1) / D.xworld; }   // patches per rank slice
 
 __device__ __forceinline__ float len2(float x, float y, float z) { return x * x + y * y + z * z; }   // Vector.h:356-359
 
@@ -310,13 +331,7 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	if (fused) {
 		xseq = *reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]);
 		if (MODE == 1) dB_out = xb_planes(D, D.xrank, (xseq + 1) & 1u);
-		if (MODE == 2) {
-			if (threadIdx.x < D.xworld) {
-				const uint32_t* flag = reinterpret_cast<const uint32_t*>(D.xb[D.xrank] + 128 + 128 * threadIdx.x);
-				while ((int32_t)(ld_acquire_sys(flag) - xseq) < 0) { }
-			}
-			__syncthreads();
-		}
+		if (MODE == 2) xb_wait(D, D.xtwo ? RAD_XB_FLAG2 : 128, xseq);
 	}
 	for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < P; i0 += gridDim.x * blockDim.x) {
 		const uint32_t i = i0 + threadIdx.x;
@@ -339,7 +354,10 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 		float bx = D.rad[i], by = D.rad[P + i], bz = D.rad[2 * (size_t)P + i];
 		if (MODE == 0) gather_transfer(D, s_em, 0, k, P, i, rho, bx, by, bz);
 		else if (!fused) { bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i]; }
-		else {
+		else if (D.xtwo) {                                    // two-shot: the slice owner has already summed the ranks' planes
+			const float* red = xb_reduced(D, i / xb_slice(D));
+			bx += __ldcg(red + i); by += __ldcg(red + D.xPmax + i); bz += __ldcg(red + 2 * (size_t)D.xPmax + i);
+		} else {
 			float sx = 0.0f, sy = 0.0f, sz = 0.0f;
 			for (uint32_t r = 0; r < D.xworld; r++) {         // peer loads over NVLink, L1 bypassed
 				const float* pl = xb_planes(D, r, xseq & 1u);
@@ -362,14 +380,7 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	if (MODE == 1) {
 		if (!fused) return;
 		// the last block to finish publishes the planes: seq + 1 into this rank's flag slot on every peer
-		__shared__ bool s_lastblk;
-		__syncthreads();
-		if (threadIdx.x == 0) { __threadfence_system(); const uint32_t done = atomicAdd(&D.ctl->ticket, 1u); s_lastblk = done == gridDim.x - 1; if (s_lastblk) D.ctl->ticket = 0; }
-		__syncthreads();
-		if (!s_lastblk) return;
-		if (threadIdx.x == 0) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(D.xb[D.xrank]) = xseq + 1; }
-		__syncthreads();
-		if (threadIdx.x < D.xworld) st_release_sys(reinterpret_cast<uint32_t*>(D.xb[threadIdx.x] + 128 + 128 * D.xrank), xseq + 1);
+		xb_publish_last(D, 128, xseq + 1, true);
 		return;
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) { D.ctl->batches_done += 1; D.ctl->shots_done += s_nvalid; }
@@ -384,6 +395,25 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 		__syncthreads();
 		if (s_lastblk) camera_block(D, 0, parity ^ 1, &s_e);
 	}
+}
+
+// Two-shot exchange, first shot (large P): this rank sums the G ranks' dB planes over ITS slice of the patches, in rank
+// order, into its `red` region, and publishes the second flag; the update kernel then reads every slice from its owner
+// (2 (G-1)/G P values cross NVLink per rank instead of (G-1) P).
+__global__ void __launch_bounds__(256) xreduce_kernel(RadDev D) {
+	const uint32_t xseq = *reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]);
+	xb_wait(D, 128, xseq);
+	const uint32_t sz = xb_slice(D), lo = D.xrank * sz, hi = min(D.P, lo + sz);
+	float* red = xb_reduced(D, D.xrank);
+	for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+		float sx = 0.0f, sy = 0.0f, sz3 = 0.0f;
+		for (uint32_t r = 0; r < D.xworld; r++) {
+			const float* pl = xb_planes(D, r, xseq & 1u);
+			sx += __ldcg(pl + i); sy += __ldcg(pl + D.xPmax + i); sz3 += __ldcg(pl + 2 * (size_t)D.xPmax + i);
+		}
+		red[i] = sx; red[D.xPmax + i] = sy; red[2 * (size_t)D.xPmax + i] = sz3;
+	}
+	xb_publish_last(D, RAD_XB_FLAG2, xseq, false);
 }
 
 } // namespace
@@ -449,6 +479,12 @@ void rad_launch_delta(rad_ctx* c) {
 	const RadDev& D = c->d;
 	const uint32_t T = apply_threads(D.P);
 	apply_kernel<1><<<patch_grid(D.P, T), T, D.k * sizeof(EmLite), c->stream>>>(D, 0, 0);
+	c->launches++;
+}
+void rad_launch_xreduce(rad_ctx* c) {
+	const RadDev& D = c->d;
+	const uint32_t slice = (D.P + D.xworld - 1) / D.xworld;
+	xreduce_kernel<<<patch_grid(slice, 256), 256, 0, c->stream>>>(D);
 	c->launches++;
 }
 void rad_launch_finish(rad_ctx* c, bool fuse_select) {

@@ -50,6 +50,27 @@ for nb in (batches, 2 * 8 + 3, batches):
 dist.barrier()                                  # nobody unmaps while a peer may still be reading
 ctx3.close()
 
+# the two-shot form of the same exchange (reduce-scatter kernel + all-gather inside the update kernel; chosen
+# automatically for large P, forced here): same results bit for bit on every rank, same as NCCL within rounding
+os.environ["RAD_XTWO"] = "1"
+ctx4 = api.context_for_scene(scene, N, k, device=local, select_mode=api.SELECT_TOPK)
+multi.init_peer(ctx4, dist)
+del os.environ["RAD_XTWO"]
+ctx4.save_state()
+for nb in (batches, 8 + 2):
+    ctx4.restore_state()
+    st4 = ctx4.shoot(nb)
+    assert st4.batches_done == nb and st4.queue_overflow == 0
+    rad4, illum4 = ctx4.download_state()
+    t4 = torch.from_numpy(np.concatenate([rad4, illum4]).copy()).cuda()
+    lst4 = [torch.zeros_like(t4) for _ in range(world)]
+    dist.all_gather(lst4, t4)
+    assert all(torch.equal(lst4[0], x) for x in lst4), "ranks diverged (two-shot peer exchange)"
+    if nb == batches:
+        assert rel_l2(rad4, rad) < 1e-6 and rel_l2(illum4, illum) < 1e-6, (rel_l2(rad4, rad), rel_l2(illum4, illum))
+dist.barrier()
+ctx4.close()
+
 # host-mediated variant of the same batches (dB through torch.distributed instead of the in-library NCCL call)
 ctx2 = api.context_for_scene(scene, N, k, device=local, select_mode=api.SELECT_TOPK)
 ctx2.set_partition(rank, world)
