@@ -86,14 +86,24 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
 	D.P = 0; D.h0 = 0; D.h1 = D.k;
 	D.reflectivity = cfg->reflectivity;
-	// work lists sized for a whole batch at once when it fits: 2 triangle records and 5 (patch, face) pairs per patch and hemicube
-	// is the worst case the grouping in raster.cu plans with (the real load is a fraction of it)
+	// work lists sized for the worst case the grouping in raster.cu plans with — 2 records and 5 (patch, face) pairs per
+	// patch and hemicube, for the (at most 64) hemicubes one launch group renders; the real load is a fraction of it.  This
+	// is tens of GB for a 1 M-patch scene: HBM capacity is what a B200 has to spare, and a whole batch per launch group is
+	// worth it.  Bounded by a third of the free memory (the raster then falls back to smaller hemicube groups).
 	{
-		const uint64_t want = 2ull * cfg->max_patches * cfg->hemicubes;
-		const uint32_t rec = (uint32_t)(want < (1u << 20) ? (1u << 20) : (want > (1u << 24) ? (1u << 24) : want));
-		const uint64_t wantp = 5ull * cfg->max_patches * cfg->hemicubes;
-		D.q_tri_cap = rec; D.q_sm_cap = rec; D.q_ent_cap = 2u * rec;
-		D.pairs_cap = (uint32_t)(wantp < (1u << 20) ? (1u << 20) : (wantp > (1u << 26) ? (1u << 26) : wantp));
+		const uint64_t kk = cfg->hemicubes < 64 ? cfg->hemicubes : 64;
+		size_t free_b = 0, total_b = 0;
+		cudaMemGetInfo(&free_b, &total_b);
+		const uint64_t budget = (uint64_t)free_b / 3;                         // bytes for the four lists
+		uint64_t want = 2ull * cfg->max_patches * kk, wantp = 5ull * cfg->max_patches * kk;
+		if (want < (1u << 20)) want = 1u << 20;
+		if (wantp < (1u << 20)) wantp = 1u << 20;
+		const uint64_t bytes = want * (sizeof(RadBigTri) + sizeof(RadSmallQuad) + 2 * sizeof(RadQueueEntry)) + wantp * 4;
+		if (bytes > budget && budget > 0) { const double f = (double)budget / (double)bytes; want = (uint64_t)(want * f); wantp = (uint64_t)(wantp * f); }
+		if (want > (1ull << 30)) want = 1ull << 30;
+		if (wantp > (1ull << 31)) wantp = 1ull << 31;
+		D.q_tri_cap = (uint32_t)want; D.q_sm_cap = (uint32_t)want; D.q_ent_cap = (uint32_t)(2 * want);
+		D.pairs_cap = (uint32_t)wantp;
 	}
 	D.kbase = 0; D.inline_area = 64;
 	D.small_steps = D.k == 1 ? 16 : RAD_SMALL_STEPS; D.tile = D.k == 1 ? 16 : RAD_TILE;
