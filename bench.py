@@ -221,13 +221,32 @@ def main():
     v, _, c, r, il = scene.arrays()
     P = scene.P
     mode = api.SELECT_TOPK if k > 1 else api.SELECT_REFERENCE
-    ctx = api.Context(N, k, P, device=local, select_mode=mode)
-    ctx.set_formfactors(api.formfactors(N))
-    ctx.upload_scene(v, c, r, il)
+    def make_context():
+        cx = api.Context(N, k, P, device=local, select_mode=mode)
+        cx.set_formfactors(api.formfactors(N))
+        cx.upload_scene(v, c, r, il)
+        return cx
+
+    ctx = make_context()
+    exchange = args.exchange
     if world > 1:
-        if args.exchange == "peer":
-            multi.init_peer(ctx, dist)
-        else:
+        if exchange == "peer":
+            # CUDA IPC mapping of the peers' exchange buffers; if any rank cannot map them (container without IPC between
+            # the ranks), every rank falls back to the in-library NCCL all-reduce together
+            ok = 1
+            try:
+                multi.init_peer(ctx, dist)
+            except Exception as e:               # noqa: BLE001
+                print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({e}); falling back to NCCL", file=sys.stderr)
+                ok = 0
+            t_ok = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            if int(t_ok[0]) == 0:
+                dist.barrier()
+                ctx.close()
+                ctx = make_context()
+                exchange = "nccl"
+        if exchange == "nccl":
             multi.init_nccl(ctx, dist)
     ctx.save_state()
     shots_per_step = batches * k
@@ -354,7 +373,7 @@ def main():
                 "config": {"workload": desc, "patches": P, "hemicube": N, "atlas": [2 * N, N + N // 2], "k": k, "batches_per_step": batches,
                            "shots_per_step": shots_per_step, "schedule": "topk" if k > 1 else "reference",
                            "parallelism": (f"{k_rank} of the batch's {k} shooters per rank, dB combined once per batch by " +
-                                           ("the fused peer-memory update kernel (NVLink, CUDA IPC)" if args.exchange == "peer" else "ncclAllReduce") if world > 1 else "1gpu"),
+                                           ("the fused peer-memory update kernel (NVLink, CUDA IPC)" if exchange == "peer" else "ncclAllReduce") if world > 1 else "1gpu"),
                            "l2": "256 MB write between timed iterations (flush)", "timing": "CUDA events on the launching stream inside rad_shoot, max over ranks",
                            "wall_s_incl_flush": wall},
                 "clocks": clocks,

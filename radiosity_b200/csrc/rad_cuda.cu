@@ -700,6 +700,7 @@ int rad_peer_init(rad_ctx* c, int rank, int world, const void* handles /* world 
 
 int rad_batch_partial(rad_ctx* c) {
 	int r = need_ready(c, "rad_batch_partial"); if (r) return r;
+	if (c->peer_mode) { c->err = "rad_batch_partial: the host-mediated exchange is not available after rad_peer_init (dB lives in the exchange buffer)"; return RAD_E_STATE; }
 	const bool keep = (c->cfg.flags & RAD_FLAG_KEEP_ITEMBUFFER) != 0;
 	rad_launch_select(c);
 	rad_launch_raster_process(c, keep);

@@ -32,10 +32,18 @@ def init_nccl(ctx, dist):
 
 
 def init_peer(ctx, dist):
-    """Fused exchange over peer memory: all-gather the ranks' CUDA IPC handles, map the peers' exchange buffers."""
+    """Fused exchange over peer memory: all-gather the ranks' CUDA IPC handles, map the peers' exchange buffers.
+    Raises on EVERY rank if any rank could not export its buffer (the all-gather itself always completes); a rank whose
+    mapping of a peer fails raises on its own — callers that want a common fallback agree on it afterwards (bench.py)."""
     rank, world = dist.get_rank(), dist.get_world_size()
+    try:
+        mine = ctx.peer_handle()
+    except Exception:                            # noqa: BLE001 — reported below, on all ranks
+        mine = None
     handles = [None] * world
-    dist.all_gather_object(handles, ctx.peer_handle())
+    dist.all_gather_object(handles, mine)
+    if any(h is None for h in handles):
+        raise RuntimeError("rad_peer_handle failed on rank(s) " + ", ".join(str(i) for i, h in enumerate(handles) if h is None))
     ctx.peer_init(rank, world, handles)
     return rank, world
 
