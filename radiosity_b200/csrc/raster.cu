@@ -467,7 +467,8 @@ __device__ __forceinline__ void edge_origin(int ax, int ay, int bx, int by, int&
 
 // persistent warps drain both queues.
 //  1. small-quad queue: FOUR records per warp step, one quarter warp (8 lanes) each.  A record holds both triangles of a
-//     patch, A = (0,1,2) and B = (0,2,3); the common bbox is walked ONCE as one linear run of w*h pixels, 8 per step,
+//     patch, A = (0,1,2) and B = (0,2,3); the common bbox is walked ONCE as one linear run of w * ceil(h/2) two-row
+//     columns, 8 per step (16 pixels per quarter warp and step),
 //     with the five distinct int32 edge functions (the diagonal is shared: B's edge (0->2) is minus A's edge (2->0)).
 //     A pixel belongs to A or to B (never both: they lie on opposite sides of the diagonal and the top-left rule gives
 //     the diagonal itself to exactly one) and takes its depth from that triangle's plane — the same integers and the
@@ -484,7 +485,8 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 		const int W = (int)D.W;
 		for (uint32_t base = gw * 4; base < nsm; base += nw * 4) {
 			const uint32_t i = base + sub;
-			int npx = 0, w8 = 1, q8 = 0, r8 = 0, x = 0, y = 0;
+			int npx = 0, w8 = 1, hh = 0, q8 = 0, r8 = 0, x = 0, y = 0;
+			int a0y2 = 0, a1y2 = 0, a2y2 = 0, b0y2 = 0, b1y2 = 0;
 			int a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0;                         // biased edge values at the bbox origin
 			int a0x = 0, a1x = 0, a2x = 0, b0x = 0, b1x = 0, a0y = 0, a1y = 0, a2y = 0, b0y = 0, b1y = 0;
 			int bA1 = 0, bA2 = 0, bB1 = 0, bB2 = 0;
@@ -509,29 +511,38 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 				const uint32_t slot = r2.w & 0xFFFFu, rcpw = r2.w >> 16;
 				const int px0 = (int)(r3.x & 0xFFFFu), py0 = (int)(r3.x >> 16);
 				w8 = (int)(r3.y & 0xFFu);
-				npx = w8 * (int)((r3.y >> 8) & 0xFFu);
+				hh = (int)((r3.y >> 8) & 0xFFu);
+				npx = w8 * ((hh + 1) >> 1);                               // positions of the walk: every one is a column of TWO rows
 				q8 = (int)((8u * rcpw) >> 15); r8 = 8 - q8 * w8;          // 8 / w, 8 % w
-				y = (int)(((uint32_t)l8 * rcpw) >> 15); x = l8 - y * w8;   // this lane's first pixel of the linear run
+				y = (int)(((uint32_t)l8 * rcpw) >> 15); x = l8 - y * w8;   // this lane's first position (y counts row pairs)
 				kp = D.keys + (size_t)(slot - D.kbase) * D.RES + (size_t)py0 * D.W + px0;
+				a0y2 = 2 * a0y; a1y2 = 2 * a1y; a2y2 = 2 * a2y; b0y2 = 2 * b0y; b1y2 = 2 * b1y;
 			}
 			int msteps = (npx + 7) >> 3;
 			msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 8)); msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 16));
 			int idx = l8;
+			// one covered-pixel test + depth + RED; the unbiased A edge (2->0) is minus B's edge (0->2)
+			auto pixel = [&](int e0, int e1, int e2, int f0, int f1, int off) {
+				const int e1u = e1 - bA1;
+				const int f2 = bB2 - e1u;
+				const bool inA = (e0 | e1 | e2) >= 0, inB = (f0 | f1 | f2) >= 0;
+				if (inA || inB) {
+					const float inv = inA ? invA : invB;
+					const float l1 = (float)(inA ? e1u : f1 - bB1) * inv, l2 = (float)(inA ? e2 - bA2 : -e1u) * inv;
+					float z = (Z0 + l1 * (inA ? dA1 : dA2)) + l2 * (inA ? dA2 : dB2);
+					z = fminf(fmaxf(z, 0.0f), 1.0f);
+					const uint32_t dq = __float2uint_rn(z * 16777215.0f);
+					if (dq < 0xFFFFFFu) atomicMin(kp + off, ((unsigned long long)(tagsh | dq) << 32) | id1);
+				}
+			};
 			for (int s = 0; s < msteps; s++) {
 				if (idx < npx) {
-					const int e0 = a0 + x * a0x + y * a0y, e1 = a1 + x * a1x + y * a1y, e2 = a2 + x * a2x + y * a2y;
-					const int f0 = b0 + x * b0x + y * b0y, f1 = b1 + x * b1x + y * b1y;
-					const int e1u = e1 - bA1;                        // unbiased A edge (2->0) == minus B's edge (0->2)
-					const int f2 = bB2 - e1u;
-					const bool inA = (e0 | e1 | e2) >= 0, inB = (f0 | f1 | f2) >= 0;
-					if (inA || inB) {
-						const float inv = inA ? invA : invB;
-						const float l1 = (float)(inA ? e1u : f1 - bB1) * inv, l2 = (float)(inA ? e2 - bA2 : -e1u) * inv;
-						float z = (Z0 + l1 * (inA ? dA1 : dA2)) + l2 * (inA ? dA2 : dB2);
-						z = fminf(fmaxf(z, 0.0f), 1.0f);
-						const uint32_t dq = __float2uint_rn(z * 16777215.0f);
-						if (dq < 0xFFFFFFu) atomicMin(kp + (y * W + x), ((unsigned long long)(tagsh | dq) << 32) | id1);
-					}
+					// rows 2y and 2y + 1 of column x: the second row's edge values are one add away from the first's
+					const int e0 = a0 + x * a0x + y * a0y2, e1 = a1 + x * a1x + y * a1y2, e2 = a2 + x * a2x + y * a2y2;
+					const int f0 = b0 + x * b0x + y * b0y2, f1 = b1 + x * b1x + y * b1y2;
+					const int off = 2 * y * W + x;
+					pixel(e0, e1, e2, f0, f1, off);
+					if (2 * y + 1 < hh) pixel(e0 + a0y, e1 + a1y, e2 + a2y, f0 + b0y, f1 + b1y, off + W);
 				}
 				idx += 8; x += r8; y += q8;
 				if (x >= w8) { x -= w8; y++; }
