@@ -125,6 +125,10 @@ def reference_arm(args, wl):
         return
     from oracle import orc
     area, N, k, batches, desc = wl
+    if args.gpus > 1 and args.scaling == "weak" and k > 1:
+        import re
+        k = k * args.gpus                        # the same batch as the GPU arm at N ranks: the top-(64 N) list
+        desc = re.sub(r"(\d+) shots \(k=64 x (\d+) batch", lambda m: f"up to {k * int(m.group(2))} shots (k={k} = 64 per rank x {m.group(2)} batch", desc)
     v, c, r, il = orc.scene_cornell(area)
     P = v.shape[0]
     threads = orc.max_threads()
@@ -133,15 +137,16 @@ def reference_arm(args, wl):
 
     def step():
         nonlocal rad, illum
-        rad, illum, *_ = orc.shoot(v, c, rad, illum, N, k, sample_batches, select_mode=1 if k > 1 else 0, threads=threads)
+        rad, illum, sched, *_ = orc.shoot(v, c, rad, illum, N, k, sample_batches, select_mode=1 if k > 1 else 0, threads=threads)
+        return int((sched != 0xFFFFFFFF).sum())          # NULL slots of a list that is not full are not shots
 
     for _ in range(args.warmup):
         step()
+    shots = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        shots += step()
     dt = time.perf_counter() - t0
-    shots = args.steps * sample_batches * k
     value = shots / dt
     line = {"impl": "reference", "metric": "hemicubes_per_sec", "value": value, "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -169,8 +174,8 @@ def cpu_baseline(wl, budget_s=20.0):
         rad, illum = r.copy(), il.copy()
         nb = 1 if k > 1 else 16
         while True:
-            rad, illum, *_ = orc.shoot(v, c, rad, illum, N, k, nb, select_mode=mode, threads=th)
-            done += nb * k
+            rad, illum, sched, *_ = orc.shoot(v, c, rad, illum, N, k, nb, select_mode=mode, threads=th)
+            done += int((sched != 0xFFFFFFFF).sum())
             if time.perf_counter() - t0 > budget_s / 2 or done >= 256:
                 break
         res[th] = (done / (time.perf_counter() - t0), done)
