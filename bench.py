@@ -149,7 +149,8 @@ def reference_arm(args, wl):
     dt = time.perf_counter() - t0
     value = shots / dt
     line = {"impl": "reference", "metric": "hemicubes_per_sec", "value": value, "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": args.scaling if (args.gpus > 1 and k > 1) else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "patches": P, "hemicube": N, "k": k, "schedule": "topk" if k > 1 else "reference",
                        "note": "reference's algorithm restated on the CPU (oracle port: reference host code semantics + GL raster / CL kernel restatement); the reference's GL+CL stack cannot run in this image"},
