@@ -12,8 +12,9 @@
  *     printing to cerr, Main.cpp:291-294,409-412,846-855.)
  *   - the caller owns all host arrays; the library copies on upload/download and owns all device
  *     memory (reference: GL/CL own device objects, Main.cpp:605-607,665-667).
- *   - a context is bound to one GPU and one CUDA stream and is NOT thread-safe (reference: one GL
- *     context + one in-order CL queue, Main.cpp:431).
+ *   - a context is bound to one GPU and is NOT thread-safe (reference: one GL context + one in-order
+ *     CL queue, Main.cpp:431).  It owns its CUDA streams: one for the calls below, plus the raster
+ *     lanes rad_shoot forks from it and joins back into it.
  *   - there is no CPU fallback: without a CUDA device rad_create fails with RAD_E_CUDA.
  *   - patch id = index into the flat scene arrays (ModelContainer.cpp:81-155).  Item buffers hold
  *     `id + 1` per pixel, 0 = nothing rendered (the reference packs the same number into an RGBA8
@@ -162,6 +163,10 @@ int rad_comm_init(rad_ctx* ctx, int rank, int world, const void* id128);
  * it applies them.  All ranks must have finished shooting before any of them calls rad_destroy. */
 int rad_peer_handle(rad_ctx* ctx, void* handle64_out /* 64 bytes */);
 int rad_peer_init(rad_ctx* ctx, int rank, int world, const void* handles /* world x 64 bytes, rank order */);
+/* With world > 1 (any of the three modes) a RAD_SELECT_TOPK list is DEALT OUT to the ranks when world divides k: list
+ * entry j goes to slot (j % world) * (k / world) + j / world, so that every rank renders the same mix of strong and weak
+ * shooters (rad_select returns ids in slot order).  The batch's result does not depend on the slot order beyond the
+ * order of float additions. */
 /* partition-only mode (no NCCL): shard like `world` ranks and expose the partial dB so that a
  * host-side collective (e.g. torch.distributed gloo in CPU tests) can combine it */
 int rad_set_partition(rad_ctx* ctx, int rank, int world);
