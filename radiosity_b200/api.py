@@ -150,10 +150,14 @@ def _f32c(a):
 class Scene:
     """ModelContainer of the host library (reference API: ModelContainer.h)."""
 
-    def __init__(self, area=0.5, obj=None):
+    def __init__(self, area=0.5, obj=None, static_mesh=None, scale=0.01, flip=False, emissive_material=-1):
         self.lib = host_lib()
         self.h = self.lib.radhost_scene_new()
-        if obj is None:
+        if static_mesh is not None:                              # TestModel.h-style export (StaticMeshModel.h, SURVEY 8f-4)
+            self.lib.radhost_scene_load_static_mesh.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_float, ctypes.c_int, ctypes.c_int]
+            if not self.lib.radhost_scene_load_static_mesh(self.h, os.fsencode(static_mesh), float(scale), 1 if flip else 0, int(emissive_material)):
+                raise RadError(f"cannot load static mesh {static_mesh}")
+        elif obj is None:
             self.lib.radhost_scene_load_cornell(self.h)          # ModelContainer::load()
         elif not self.lib.radhost_scene_load_obj(self.h, os.fsencode(obj)):
             raise RadError(f"cannot load OBJ scene {obj}")

@@ -23,6 +23,12 @@ bool ModelContainer::load(const std::string& objPath) {
 	return m->getPatches(0)->size() > 0;
 }
 
+bool ModelContainer::loadStaticMesh(const std::string& headerPath, float scale, bool flip, int emissiveMaterial) {
+	StaticMeshModel* m = new StaticMeshModel(headerPath, scale, flip, emissiveMaterial);
+	addModel(m);
+	return m->triangleCount() > 0;
+}
+
 int ModelContainer::addModel(Model* m) { needRefresh = true; models.push_back(m); return (int)models.size() - 1; }
 
 void ModelContainer::removeModel(int i) {

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include "PrimitiveModel.h"
 #include "WaveFrontModel.h"
+#include "StaticMeshModel.h"
 #include "Vector.h"
 
 class ModelContainer {
@@ -15,6 +16,7 @@ public:
 
 	void load();                            // the built-in Cornell box: room, closure, cube, block
 	bool load(const std::string& objPath);  // extension: a Wavefront OBJ scene (see WaveFrontModel.h)
+	bool loadStaticMesh(const std::string& headerPath, float scale = 0.01f, bool flip = false, int emissiveMaterial = -1);   // TestModel.h-style export (StaticMeshModel.h)
 
 	int addModel(Model* m);                 // takes ownership; returns its index
 	void removeModel(int i);

@@ -18,6 +18,9 @@ void* radhost_scene_new() { return new ModelContainer(); }
 void radhost_scene_free(void* s) { delete (ModelContainer*)s; }
 void radhost_scene_load_cornell(void* s) { ((ModelContainer*)s)->load(); }
 int radhost_scene_load_obj(void* s, const char* path) { return ((ModelContainer*)s)->load(std::string(path)) ? 1 : 0; }
+int radhost_scene_load_static_mesh(void* s, const char* path, float scale, int flip, int emissive_material) {
+	return ((ModelContainer*)s)->loadStaticMesh(std::string(path), scale, flip != 0, emissive_material) ? 1 : 0;
+}
 void radhost_scene_set_area(void* s, double area) { ((ModelContainer*)s)->maxPatchArea = area; }
 unsigned radhost_scene_patch_count(void* s) { return ((ModelContainer*)s)->getPatchesCount(); }
 

@@ -98,3 +98,28 @@ def test_obj_scene_with_emitter_extension(api, orc, tmp_path):
     orad, oillum, *_ = orc.shoot(v, c, r, il, N, 1, 30)
     assert rel_l2(rad, orad) < 1e-3 and rel_l2(illum, oillum) < 1e-3
     ctx.close()
+
+
+def test_static_mesh_scene_shot_on_the_gpu(api, orc):
+    """a TestModel.h-style static export (tests/golden/static_mesh_fixture.h: closed room of triangles + a
+    lamp) through the adapter, subdivided, shot on the GPU and compared with the oracle on the same arrays."""
+    import os
+    fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "static_mesh_fixture.h")
+    scene = api.Scene(0.02, static_mesh=fixture, scale=0.01, flip=True, emissive_material=1)
+    v, _, c, r, il = scene.arrays()
+    assert scene.P > 100 and r.sum() > 0
+    N = 128
+    ctx = api.context_for_scene(scene, N, 1)
+    ids, valid = ctx.select()
+    em = int(ids[0])
+    assert r[em, 0] > 0
+    ctx.render()
+    got = ctx.read_itembuffer(0)
+    exp = orc.render_hemicube(v, em, N)
+    assert (got == exp).all()
+    st = ctx.shoot(24)
+    assert st.batches_done == 24 and st.queue_overflow == 0
+    rad, illum = ctx.download_state()
+    orad, oillum, *_ = orc.shoot(v, c, r, il, N, 1, 24)
+    assert rel_l2(rad, orad) < 1e-3 and rel_l2(illum, oillum) < 1e-3
+    ctx.close()
