@@ -4,6 +4,8 @@
 //   select <reference|topk>     shooter selection semantics (include/rad_cuda.h)
 //   device <n>    CUDA device ordinal
 //   obj <path>    load a Wavefront OBJ scene instead of the built-in Cornell box
+//   mesh <path>   load a "static 3DS export" header such as the reference's TestModel.h (StaticMeshModel.h);
+//                 mesh_scale <f> (default 0.01), mesh_flip <0|1>, mesh_emit <material index> go with it
 //   dump <path>   write "id Bx By Bz Ix Iy Iz" per patch when done
 //   save <path>   checkpoint the scene + energies when done (portable .rr, SceneFile.h; the reference's Ctrl+S)
 //   load <path>   resume from a checkpoint instead of building a scene (the reference's Ctrl+O; also reads its raw dumps)
@@ -23,6 +25,7 @@ int main(int argc, const char** argv) {
 	if ((argc - 1) % 2 > 0) { std::cerr << "Wrong number of arguments (expected key value pairs)" << std::endl; return -1; }
 	long shots = -1; int device = 0; unsigned int select = RAD_SELECT_REFERENCE;
 	const char* obj = NULL; const char* dump = NULL; const char* save = NULL; const char* load = NULL;
+	const char* mesh = NULL; float mesh_scale = 0.01f; bool mesh_flip = false; int mesh_emit = -1;
 	for (int i = 1; i < argc; i += 2) {
 		const char* k = argv[i]; const char* v = argv[i + 1];
 		if (!strcmp(k, "area")) Config::setMaxPatchArea(atof(v));
@@ -33,6 +36,10 @@ int main(int argc, const char** argv) {
 		else if (!strcmp(k, "device")) device = atoi(v);
 		else if (!strcmp(k, "select")) select = !strcmp(v, "topk") ? RAD_SELECT_TOPK : RAD_SELECT_REFERENCE;
 		else if (!strcmp(k, "obj")) obj = v;
+		else if (!strcmp(k, "mesh")) mesh = v;
+		else if (!strcmp(k, "mesh_scale")) mesh_scale = (float)atof(v);
+		else if (!strcmp(k, "mesh_flip")) mesh_flip = atoi(v) != 0;
+		else if (!strcmp(k, "mesh_emit")) mesh_emit = atoi(v);
 		else if (!strcmp(k, "dump")) dump = v;
 		else if (!strcmp(k, "save")) save = v;
 		else if (!strcmp(k, "load")) load = v;
@@ -42,6 +49,7 @@ int main(int argc, const char** argv) {
 	ModelContainer scene;
 	if (load) { if (!LoadFromFile(std::string(load), scene)) { std::cerr << "Unable to load checkpoint '" << load << "'" << std::endl; return -1; } }
 	else if (obj) { if (!scene.load(std::string(obj))) { std::cerr << "Unable to load '" << obj << "'" << std::endl; return -1; } }
+	else if (mesh) { if (!scene.loadStaticMesh(std::string(mesh), mesh_scale, mesh_flip, mesh_emit)) { std::cerr << "Unable to load '" << mesh << "'" << std::endl; return -1; } }
 	else scene.load();
 	if (!load) scene.maxPatchArea = Config::MAX_PATCH_AREA();
 	std::cout << "patches: " << scene.getPatchesCount() << ", hemicube " << Config::HEMICUBE_W() << ", atlas "
