@@ -91,7 +91,9 @@ int rad_set_formfactors(rad_ctx* ctx, const float* ff, uint32_t n);
 
 /* scene upload: glBufferData of scene.getVertices() (Main.cpp:19) + the per-patch state the
  * reference reads through Patch* (Patch.h:46-54).  verts12 = float[P*12] (4 verts x xyz),
- * color3 / radiosity3 / illumination3 = float[P*3]. */
+ * color3 / radiosity3 / illumination3 = float[P*3].  Page-locked host arrays (cudaHostAlloc, cudaHostRegister, torch
+ * pin_memory) are read by the copy engine directly, pageable ones go through the context's pinned staging buffer; the
+ * same holds for rad_upload_state and, for the output arrays, rad_download_state.  One synchronisation per call. */
 int rad_upload_scene(rad_ctx* ctx, const float* verts12, const float* color3, const float* radiosity3,
                      const float* illumination3, uint32_t P);
 /* re-upload only B and I (restart a run on the same geometry) */

@@ -275,8 +275,15 @@ class Context:
         rad, illum = _f32c(rad), _f32c(illum)
         self._ck(self.lib.rad_upload_state(self.h, _ptr(rad), _ptr(illum)), "rad_upload_state")
 
-    def download_state(self):
-        rad = np.zeros((self.P, 3), np.float32); illum = np.zeros((self.P, 3), np.float32)
+    def download_state(self, out=None):
+        """(radiosity[P,3], illumination[P,3]); `out` = a pair of preallocated float32 arrays (page-locked ones are
+        written by the copy engine directly)"""
+        if out is not None:
+            rad, illum = out
+            assert rad.dtype == np.float32 and illum.dtype == np.float32 and rad.size == 3 * self.P and illum.size == 3 * self.P
+            assert rad.flags["C_CONTIGUOUS"] and illum.flags["C_CONTIGUOUS"]
+        else:
+            rad = np.zeros((self.P, 3), np.float32); illum = np.zeros((self.P, 3), np.float32)
         self._ck(self.lib.rad_download_state(self.h, _ptr(rad), _ptr(illum)), "rad_download_state")
         return rad, illum
 

@@ -221,12 +221,27 @@ static int d2h_aos3(rad_ctx* c, const float* src_planes, float* dst, size_t P) {
 	return RAD_OK;
 }
 
-// enqueue only (no synchronisation): B and I from staging floats [off, off + 6P)
+// Page-locked caller memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) is copied from / to directly; pageable
+// memory goes through the context's pinned staging buffer first.
+static bool is_pinned(const void* p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+}
+// host floats -> device staging floats [off, off + n): enqueue only
+static int enqueue_h2d(rad_ctx* c, const float* src, size_t off_floats, size_t n) {
+	const float* from = src;
+	if (!is_pinned(src)) { memcpy(c->h_stage + off_floats, src, n * 4); from = c->h_stage + off_floats; }
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage + off_floats, from, n * 4, cudaMemcpyHostToDevice, c->stream));
+	return RAD_OK;
+}
+
+// enqueue only (no synchronisation): B and I through staging floats [off, off + 6P)
 static int enqueue_state_upload(rad_ctx* c, const float* rad3, const float* illum3, size_t off_floats) {
 	const size_t P = c->d.P;
-	memcpy(c->h_stage + off_floats, rad3, 3 * P * 4);
-	memcpy(c->h_stage + off_floats + 3 * P, illum3, 3 * P * 4);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage + off_floats, c->h_stage + off_floats, 6 * P * 4, cudaMemcpyHostToDevice, c->stream));
+	int r;
+	if ((r = enqueue_h2d(c, rad3, off_floats, 3 * P))) return r;
+	if ((r = enqueue_h2d(c, illum3, off_floats + 3 * P, 3 * P))) return r;
 	rad_launch_aos3_to_planes(c, c->d_stage + off_floats, c->d.rad, (uint32_t)P);
 	rad_launch_aos3_to_planes(c, c->d_stage + off_floats + 3 * P, c->d.illum, (uint32_t)P);
 	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.ctl, 0, sizeof(RadControl), c->stream));
@@ -253,9 +268,8 @@ int rad_upload_scene(rad_ctx* c, const float* verts12, const float* color3, cons
 	int r = stage_dev(c, (size_t)P * 21 * 4); if (r) return r;
 	// staging layout (floats): [0, 12P) quads | [12P, 15P) colour | [15P, 21P) B, I
 	// 48-byte quad records -> three float4 streams (coalesced 16 B loads per lane in the rasteriser)
-	memcpy(c->h_stage, verts12, (size_t)P * 48);
-	memcpy(c->h_stage + (size_t)P * 12, color3, (size_t)P * 12);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, c->h_stage, (size_t)P * 60, cudaMemcpyHostToDevice, c->stream));
+	if ((r = enqueue_h2d(c, verts12, 0, (size_t)P * 12))) return r;
+	if ((r = enqueue_h2d(c, color3, (size_t)P * 12, (size_t)P * 3))) return r;
 	rad_launch_split_quads(c, c->d_stage, P);
 	rad_launch_aos3_to_planes(c, c->d_stage + (size_t)P * 12, (float*)c->d.color, P);
 	RAD_CUDA_TRY(c, cudaMemsetAsync(c->d.F, 0, (size_t)c->d.k * P * 4, c->stream));
@@ -274,10 +288,12 @@ int rad_download_state(rad_ctx* c, float* rad3, float* illum3) {
 	int r = stage_dev(c, 21 * P * 4); if (r) return r;
 	rad_launch_planes_to_aos3(c, c->d.rad, c->d_stage, (uint32_t)P);
 	rad_launch_planes_to_aos3(c, c->d.illum, c->d_stage + 3 * P, (uint32_t)P);
-	RAD_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_stage, 6 * P * 4, cudaMemcpyDeviceToHost, c->stream));
+	const bool pr = is_pinned(rad3), pi = is_pinned(illum3);
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(pr ? rad3 : c->h_stage, c->d_stage, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(pi ? illum3 : c->h_stage + 3 * P, c->d_stage + 3 * P, 3 * P * 4, cudaMemcpyDeviceToHost, c->stream));
 	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-	memcpy(rad3, c->h_stage, 3 * P * 4);
-	memcpy(illum3, c->h_stage + 3 * P, 3 * P * 4);
+	if (!pr) memcpy(rad3, c->h_stage, 3 * P * 4);
+	if (!pi) memcpy(illum3, c->h_stage + 3 * P, 3 * P * 4);
 	return RAD_OK;
 }
 
