@@ -181,11 +181,12 @@ __device__ __forceinline__ void cmpx_stage(unsigned long long& a0, unsigned long
 	a1 = ((a1 > b1) == (first == d1)) ? a1 : b1;
 }
 // best `keep` of the block's 2048 keys, sorted descending, left in elements [0, keep) (a0 of threads t < keep)
-__device__ __forceinline__ void block_topk(unsigned long long& a0, unsigned long long& a1, unsigned long long* s, int t, int keep, bool groups_sorted) {
+// (`span` = number of leading elements that can hold non-zero keys, rounded up to a power of two: groups beyond it are empty)
+__device__ __forceinline__ void block_topk(unsigned long long& a0, unsigned long long& a1, unsigned long long* s, int t, int keep, bool groups_sorted, int span = kTopChunk) {
 	if (!groups_sorted)
 		for (int k = 2; k <= keep; k <<= 1)
 			for (int j = k >> 1; j > 0; j >>= 1) cmpx_stage(a0, a1, s, t, j, k == keep ? 0 : k);   // last pass: every group descending
-	for (int g = keep; g < kTopChunk; g <<= 1) {
+	for (int g = keep; g < span; g <<= 1) {
 		// prune: groups (L, L + g/keep) -> element i of the first takes max with element g-1-i ... of the second
 		__syncthreads();
 		s[t] = a0; s[t + 1024] = a1;
@@ -232,7 +233,9 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 		const uint32_t nc = gridDim.x * (uint32_t)keep;
 		a[0] = (uint32_t)t < nc ? __ldcg(out + t) : 0ull;
 		a[1] = (uint32_t)t + 1024 < nc ? __ldcg(out + t + 1024) : 0ull;
-		block_topk(a[0], a[1], s, t, keep, true);
+		int span = keep;
+		while ((uint32_t)span < nc) span <<= 1;
+		block_topk(a[0], a[1], s, t, keep, true, span);
 	}
 	if ((uint32_t)t < D.k) {
 		const uint32_t G = D.deal, slot = G > 1 ? ((uint32_t)t % G) * (D.k / G) + (uint32_t)t / G : (uint32_t)t;
