@@ -10,12 +10,15 @@
 // PINNING.  The reference ships no tests or golden vectors.  The host-side parts
 // restated here (scene, subdivision, selection, camera/MVP, form-factor table, colour codec) are
 // pinned bit-for-bit against the reference's own code compiled into oracle/_ref/libref_host.so
-// (tests/test_oracle_vs_ref.py) and against tests/golden/ fixtures generated from it.  The two
-// pieces whose arithmetic lives in GPU drivers that are not in /root/reference — the OpenGL
-// rasteriser and the OpenCL runtime executing Kernel_ProcessHemicube.h — are restated from the
-// reference's call sites plus the OpenGL 3.3 rasterisation rules; for THOSE parity is unpinned by
-// any reference-run output (no GL/CL stack exists in this image), and is anchored on invariants
-// (closed box: sum F == sum dFF, F[self] == 0, every decoded id < P, codec round trip).
+// (tests/test_golden_reference.py) and against tests/golden/ fixtures generated from it.  The
+// ProcessHemicube kernel restated here is pinned on the reference's own kernel TEXT, compiled from
+// the reference header and run on the CPU (oracle/ref_kernel.cpp): identical record streams.  The
+// one piece whose arithmetic lives in a GPU driver that is not in /root/reference — the OpenGL
+// rasteriser — is restated from the reference's call sites plus the OpenGL 3.3 rasterisation
+// rules; for THAT parity is unpinned by any reference-run output (no GL stack exists in this
+// image).  It is anchored on invariants (closed box: sum F == sum dFF, F[self] == 0, every decoded
+// id < P, codec round trip) and pinned against an independent restatement of the same rules in
+// plain Python (tests/test_oracle_raster_rules.py).
 //
 // All float arithmetic is IEEE single, evaluated in the order written, never contracted
 // (compile with -ffp-contract=off); the CUDA path is written to the same operation order so that

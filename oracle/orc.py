@@ -78,6 +78,9 @@ def ref():
         L.refp_load_rr.argtypes = [ctypes.c_char_p]; L.refp_load_rr.restype = _u32
         L.refp_smooth_shade.argtypes = [_vp]
         L.refp_scene_set_illumination.argtypes = [_vp]
+        if hasattr(L, "refp_process_hemicube_kernel"):
+            L.refp_process_hemicube_kernel.argtypes = [_u32, _vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp]
+            L.refp_process_hemicube_kernel.restype = _u32
         _ref = L
     return _ref
 
@@ -155,6 +158,24 @@ def process_cl(ids, ff, side, P, hemicubes=1, workitems_x=4):
         bad += L.orc_gather_records(P, nrec, _ptr(h), _ptr(ii), _ptr(e), hi, _ptr(F))
         out.append(F)
     return out, nrec, bad
+
+
+def process_cl_records(ids, ff, side, P, hemicubes=1, workitems_x=4, reference_kernel=False):
+    """The raw record stream (hemicubes[], ids[], energies[], write index) of one kernel launch over an RGBA8 atlas encoded
+    from `ids`: the oracle's restatement, or — reference_kernel=True — the reference's OWN kernel text compiled by
+    oracle/ref_build.sh and run on the CPU (oracle/ref_kernel.cpp)."""
+    L = lib()
+    ids = np.ascontiguousarray(ids, np.uint32); ff = np.ascontiguousarray(ff, np.float32)
+    n = ids.size
+    rgba = np.zeros(n * 4, np.uint8)
+    L.orc_encode_atlas(P, _ptr(ids), n, _ptr(rgba))
+    h = np.zeros(n + 8, np.uint32); ii = np.zeros(n + 8, np.uint32); e = np.zeros(n + 8, np.float32)
+    W, H = 2 * side, side + side // 2
+    if reference_kernel:
+        nrec = ref().refp_process_hemicube_kernel(P, _ptr(rgba), _ptr(ff), W, H, hemicubes, workitems_x, _ptr(h), _ptr(ii), _ptr(e))
+    else:
+        nrec = L.orc_process_hemicube_cl(P, _ptr(rgba), _ptr(ff), W, H, hemicubes, workitems_x, _ptr(h), _ptr(ii), _ptr(e))
+    return h[:nrec], ii[:nrec], e[:nrec], nrec
 
 
 def shoot(verts, color, rad, illum, side, k, n_batches, select_mode=0, via_codec=False, stop_test=False, threads=1):

@@ -12,7 +12,8 @@
 # Units built: Vector Transform Patch Model PrimitiveModel WaveFrontModel
 # LoadingModel ModelContainer Config Colors FormFactors Camera.   Units that cannot be built
 # (need Win32/WGL/GL/CL): Main OpenGL30Drv FrameBuffer Shaders — the GL raster and the OpenCL
-# kernel are therefore restated in oracle/oracle.cpp ("port").
+# kernel are therefore restated in oracle/oracle.cpp ("port").  The OpenCL kernel's TEXT, however, is plain C apart from
+# a few built-ins: it is compiled here too and run on the CPU (oracle/ref_kernel.cpp) to pin the restatement.
 set -euo pipefail
 REF=${REF_SRC:-/root/reference/source}
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -68,5 +69,11 @@ for u in $UNITS; do
   OBJS="$OBJS $TMP/$u.o"
 done
 g++ $CXXFLAGS -c "$HERE/ref_probe.cpp" -o "$TMP/ref_probe.o"
-g++ -shared -o "$OUT/libref_host.so" $OBJS "$TMP/ref_probe.o"
+# the reference's OpenCL kernel TEXT (Kernel_ProcessHemicube.h), printed from the reference header into the temp dir and
+# compiled as C++ with the built-ins of oracle/ref_kernel.cpp; one syntactic fix: the vector literal (int2)(x, y)
+printf '#include <cstdio>\n#include "Kernel_ProcessHemicube.h"\nint main() { fputs(kernel_processHemicube, stdout); return 0; }\n' > "$TMP/kgen.cpp"
+g++ -w -I"$REF" "$TMP/kgen.cpp" -o "$TMP/kgen"
+"$TMP/kgen" | sed -e 's/(int2)(/make_int2(/g' -e '/#pragma OPENCL/d' > "$TMP/src/kernel_body.inc"
+g++ $CXXFLAGS -c "$HERE/ref_kernel.cpp" -o "$TMP/ref_kernel.o"
+g++ -shared -o "$OUT/libref_host.so" $OBJS "$TMP/ref_probe.o" "$TMP/ref_kernel.o"
 echo "ref_build: wrote $OUT/libref_host.so"

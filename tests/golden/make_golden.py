@@ -36,6 +36,21 @@ def seeded_radiosity(P, seed):
     return q.reshape(P, 3)
 
 
+def kernel_cases():
+    """(name, ids, ff, N, P, hemicubes): item buffers fed — as RGBA8 atlases — to the ProcessHemicube kernel"""
+    v, c, r, il = orc.scene_cornell(0.5)
+    P = v.shape[0]
+    ids = np.concatenate([orc.render_hemicube(v, s, 32).ravel() for s in (323, 0)])
+    yield "box_area0.5_N32_s323_s0", ids, orc.formfactors(32, 2), 32, P, 2
+    for P, N in ((502, 16), (16469, 16), (250063, 32), (1021554, 32)):        # every colour bit layout the configs use
+        n = 3 * N * N
+        x = (np.arange(n, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(12345)) >> np.uint64(7)
+        yield f"hash_P{P}_N{N}", ((x % np.uint64(P + 1))).astype(np.uint32), orc.formfactors(N, 1), N, P, 1     # no coherence, some empty pixels
+        yield f"const_P{P}_N{N}", np.full(n, P, np.uint32), orc.formfactors(N, 1), N, P, 1                       # one id everywhere (the last patch)
+        runs = (np.arange(n, dtype=np.uint32) // 5) % np.uint32(P) + 1
+        yield f"runs5_P{P}_N{N}", runs.astype(np.uint32), orc.formfactors(N, 1), N, P, 1                          # runs that straddle the 4 work-item spans
+
+
 def main():
     R = orc.ref()
     assert R is not None, "build oracle/_ref first (bash oracle/ref_build.sh)"
@@ -125,6 +140,13 @@ def main():
     R.refp_scene_set_radiosity(vp(rad)); R.refp_scene_set_illumination(vp(ill))
     assert R.refp_save_rr(os.path.join(ROOT, "tests", "golden", "ref_area0.5_lp64.rr").encode())
     ref["rr"] = {"file": "ref_area0.5_lp64.rr", "P": P, "bytes": 8 + 184 * P, "rad_sha256": sha(rad), "illum_sha256": sha(ill)}
+
+    # ---- the reference's own OpenCL kernel TEXT run on the CPU (oracle/ref_kernel.cpp): record streams ----
+    ref["kernel"] = {}
+    for name, ids, ff, N, P, k in kernel_cases():
+        h, ii, e, nrec = orc.process_cl_records(ids, ff, N, P, hemicubes=k, reference_kernel=True)
+        ref["kernel"][name] = {"N": N, "P": P, "hemicubes": k, "records": int(nrec), "hemicubes_sha256": sha(h), "ids_sha256": sha(ii),
+                               "energies_sha256": sha(e), "sum_energy": float(e.sum(dtype=np.float64))}
 
     # ---- oracle regression (NOT reference outputs) ----
     reg = g["oracle_regression"]

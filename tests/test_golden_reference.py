@@ -195,3 +195,42 @@ def test_live_against_reference_build(orc, api, ref):
     for N in (32, 64):
         a = np.zeros(3 * N * N, np.float32); ref.refp_formfactors(N, 1, vp(a))
         assert (bits(a) == bits(orc.formfactors(N))).all() and (bits(a) == bits(api.formfactors(N))).all()
+
+
+def _kernel_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m.kernel_cases()
+
+
+def test_process_hemicube_kernel_restatement_equals_reference_kernel_text(orc, golden):
+    """the record stream of Kernel_ProcessHemicube.h.  The golden digests were produced by the reference's
+    OWN kernel text, compiled from the reference header by oracle/ref_build.sh and run on the CPU (oracle/ref_kernel.cpp);
+    the oracle's restatement must emit the same records — hemicube, id and float energy, in the same order — for real item
+    buffers and for the synthetic extremes (no coherence, one id, runs across the work-item spans) in every colour layout."""
+    g = golden["reference"]["kernel"]
+    n = 0
+    for name, ids, ff, N, P, k in _kernel_cases():
+        h, ii, e, nrec = orc.process_cl_records(ids, ff, N, P, hemicubes=k)
+        assert int(nrec) == g[name]["records"], name
+        assert sha(h) == g[name]["hemicubes_sha256"] and sha(ii) == g[name]["ids_sha256"] and sha(e) == g[name]["energies_sha256"], name
+        # ... and gathering the records (Main.cpp:1257-1269) gives the per-patch sums of the decoded-id path
+        F_cl, _, bad = orc.process_cl(ids, ff, N, P, hemicubes=k)
+        assert bad == 0
+        per = ids.size // k
+        for hi in range(k):
+            F_ids = orc.process_ids(ids[hi * per:(hi + 1) * per], ff[:per], N, P)
+            assert np.abs(F_cl[hi] - F_ids).max() <= 1e-6 * max(1.0, float(np.abs(F_ids).max())), name
+        n += 1
+    assert n == len(g)
+
+
+def test_process_hemicube_kernel_live(orc, ref):
+    """The same comparison against the reference kernel compiled here (skipped where oracle/_ref did not travel)."""
+    if not hasattr(ref, "refp_process_hemicube_kernel"):
+        pytest.skip("libref_host.so built before the kernel was added")
+    for name, ids, ff, N, P, k in _kernel_cases():
+        a = orc.process_cl_records(ids, ff, N, P, hemicubes=k)
+        b = orc.process_cl_records(ids, ff, N, P, hemicubes=k, reference_kernel=True)
+        assert a[3] == b[3] and (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2].view(np.uint32) == b[2].view(np.uint32)).all(), name
