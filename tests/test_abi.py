@@ -86,3 +86,23 @@ def test_headless_driver_fails_loudly_without_gpu():
     assert p.returncode != 0 and "no CUDA device" in p.stderr
     p = subprocess.run([exe, "area"], capture_output=True, text=True)       # odd argument count, as the reference rejects it
     assert p.returncode != 0
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/rad_cuda.h is the drop-in boundary: it must compile as C (no C++, no CUDA, no torch types) and every
+    declared function must resolve against librad_cuda.so at link time."""
+    import re
+    import subprocess
+    hdr = open(os.path.join(ROOT, "include", "rad_cuda.h")).read()
+    names = sorted(set(re.findall(r"\b(rad_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    src = tmp_path / "use.c"
+    body = "\n".join(f"\tp[{i}] = (void*){n};" for i, n in enumerate(names))
+    src.write_text('#include "rad_cuda.h"\n#include <stdio.h>\nint main(void) {\n\tvoid* p[%d];\n%s\n\tprintf("%%p %%s\\n", p[0], rad_version());\n\treturn 0;\n}\n' % (len(names), body))
+    exe = tmp_path / "use"
+    lib_dir = os.path.join(ROOT, "radiosity_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", lib_dir, "-lrad_cuda", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "radiosity_b200" in r.stdout
