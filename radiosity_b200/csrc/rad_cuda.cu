@@ -2,6 +2,7 @@
 // device-resident shooting loop (CUDA graph), kernel benchmarks, and the NCCL plumbing of the
 // batched multi-GPU mode.  Kernels live in raster.cu / process.cu / select_update.cu.
 #include "rad_internal.cuh"
+#include "tile_walk.cuh"
 #include <vector>
 #include <cstring>
 #include <cstdio>
@@ -81,6 +82,8 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->ev_fork = nullptr; for (int l = 0; l < RAD_MAX_LANES; l++) { c->lane_stream[l] = nullptr; c->ev_lane[l] = nullptr; }
 	c->inline_area_forced = false; c->l2_group_mb = 1u << 20;   // default: the whole batch in one group (measured faster than L2-sized groups)
 	if (const char* e = getenv("RAD_L2_GROUP_MB")) { const int v = atoi(e); if (v >= 1) c->l2_group_mb = (uint32_t)v; }   // tuning knob
+	c->tile_mode = false; memset(&c->tl, 0, sizeof(c->tl));
+	if (const char* e = getenv("RAD_RASTER")) c->tile_mode = strcmp(e, "tiles") == 0;   // opt-in: tile-binned rasteriser (raster_tiles.cu)
 	RadDev& D = c->d;
 	memset(&D, 0, sizeof(D));
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
@@ -126,6 +129,16 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.emlite, 2 * (size_t)D.k)); A(dalloc(D.ctl, 1));
 	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap)); A(dalloc(D.pairs, (size_t)D.pairs_cap)); A(dalloc(D.nb, 8 * Pm)); A(dalloc(D.shade_e, 3 * Pm));
 	A(dalloc(D.ework, Pm < RAD_MAX_HEMICUBES ? (size_t)RAD_MAX_HEMICUBES : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(proj, 16));
+	if (c->tile_mode) {
+		RadTiles& T = c->tl;
+		T.tx = (D.W + RAD_TILE_W - 1) / RAD_TILE_W; T.ty = (D.H + RAD_TILE_H - 1) / RAD_TILE_H; T.T = T.tx * T.ty;
+		uint64_t cap = 2ull * ((uint64_t)D.q_sm_cap + D.q_tri_cap);    // a record lies in 1.3 tiles on average
+		if (cap > (1ull << 31)) cap = 1ull << 31;
+		T.refs_cap = (uint32_t)cap;
+		const size_t nl = (size_t)D.k * T.T * 2u;
+		A(dalloc(T.cnt, nl)); A(dalloc(T.base, nl + RAD_MAX_LANES + 1)); A(dalloc(T.refs, (size_t)T.refs_cap));
+		if (ok) A(cudaMemset(T.cnt, 0, nl * 4));
+	}
 	#undef A
 	if (!ok) {
 		g_create_err = std::string("rad_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -163,6 +176,9 @@ int rad_destroy(rad_ctx* c) {
 	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
 	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.emlite); cudaFree(D.ctl);
 	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.pairs); cudaFree(D.nb); cudaFree(D.shade_e); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
+	if (c->tl.cnt) cudaFree(c->tl.cnt);
+	if (c->tl.base) cudaFree(c->tl.base);
+	if (c->tl.refs) cudaFree(c->tl.refs);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->saved) cudaFree(c->saved);
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);

@@ -119,9 +119,22 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	float* shade_e;               // [3][P] colour (.) (I + B) scratch of the display stage
 };
 
+// Tile-binned rasteriser (raster_tiles.cu; opt-in, RAD_RASTER=tiles): the atlas of every hemicube is cut into tiles of
+// RAD_TILE_W x RAD_TILE_H pixels (tile_walk.cuh); the parked records of a launch group are binned per (slot, tile) and one
+// CTA per tile resolves visibility in shared memory and feeds ProcessHemicube from there — no key buffer, no item buffer.
+// Every (slot, tile) has two lists: 0 = small-quad records, 1 = large triangles.
+struct RadTiles {
+	uint32_t* cnt;                // [slots][T][2] records per list (zero between launches)
+	uint32_t* base;               // [slots * T * 2 + 1] exclusive scan of cnt = first reference of every list
+	uint32_t* refs;               // record indices (list 0: into q_sm, list 1: into q_tri), grouped by list
+	uint32_t refs_cap;
+	uint32_t tx, ty, T;           // tiles per atlas row / column / hemicube
+};
+
 struct rad_ctx {
 	rad_config cfg;
 	RadDev d;
+	bool tile_mode; RadTiles tl;  // RAD_RASTER=tiles: the fused path (rad_shoot) runs the tile-binned rasteriser
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1;
 	// raster lanes: a batch's hemicube slots are split into `lanes` groups that run cull -> set-up -> queues -> process
@@ -171,6 +184,8 @@ void rad_launch_xreduce(rad_ctx* c);                // multi-GPU, fused two-shot
 void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update
 void rad_launch_argmax(rad_ctx* c);                 // k==1: prime selkey[parity] from the current B
 void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out);
+void rad_launch_tiles_view(rad_ctx* c, const RadDev& V, const RadTiles& T, cudaStream_t st, uint32_t s0, uint32_t n, bool keep_items,
+                           const std::function<void(int)>& mark);   // raster_tiles.cu: bins + tile CTAs (visibility + ProcessHemicube)
 void rad_launch_atomic_bench(rad_ctx* c, uint32_t pattern, uint32_t steps, uint32_t blocks);   // raster.cu
 void rad_launch_aos3_to_planes(rad_ctx* c, const float* aos, float* planes, uint32_t P);   // layout.cu
 void rad_launch_planes_to_aos3(rad_ctx* c, const float* planes, float* aos, uint32_t P);

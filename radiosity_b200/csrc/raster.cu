@@ -678,13 +678,16 @@ static RadDev lane_view(const rad_ctx* c, uint32_t lane, uint32_t L) {
 }
 
 // slots [D.h0 + s0, +n) of the view V on stream st
-static void launch_setup(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n, uint32_t kbase) {
+static void launch_setup(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n, uint32_t kbase, bool tiles = false) {
 	RadDev D = V;
 	D.h0 = V.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
 	// only bboxes of a few pixels are walked by the set-up lane itself; everything else goes through the balanced queues
 	// measured: with a few pixels per patch (1 M patches at hemicube 1024) the queues' per-record overhead is not worth it
 	// and the owning lane walks bboxes up to 64 px itself; from ~8 pixels per patch on, everything above 2 px is parked
 	if (!c->inline_area_forced) D.inline_area = D.RES / (D.P ? D.P : 1u) >= 8u ? 2u : 64u;
+	// tile-binned form (raster_tiles.cu): every triangle is parked (nothing touches the global key buffer), a large
+	// triangle gets one chunk entry (unused there: the bins cut it by atlas tile)
+	if (tiles) { D.inline_area = 0u; D.tile = 1u << 15; }
 	raster_cull_kernel<<<dim3((D.P + 255) / 256, 1, n), 256, 0, st>>>(D);
 	// exact stage: persistent grid over the surviving pairs (their number is only known on the device)
 	uint64_t want = ((uint64_t)D.P * n * 2 + 127) / 128;      // typically ~1 of 5 (patch, face) pairs survives
@@ -760,11 +763,21 @@ void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::fu
 		cudaStream_t st = L > 1 ? c->lane_stream[lane] : c->stream;
 		if (L > 1) cudaStreamWaitEvent(st, c->ev_fork, 0);
 		RadDev V = lane_view(c, lane, L);
+		RadTiles TV = c->tl;                                 // tile mode: the lane's share of the bins
+		if (c->tile_mode) {
+			TV.cnt += (size_t)ls0 * TV.T * 2u; TV.base += (size_t)ls0 * TV.T * 2u + lane;
+			TV.refs_cap = c->tl.refs_cap / L; TV.refs += (size_t)lane * TV.refs_cap;
+		}
 		uint32_t j = 0;
 		for (uint32_t s0 = ls0; s0 < ls1; s0 += g, j++) {
 			const uint32_t n = ls1 - s0 < g ? ls1 - s0 : g;
 			const uint32_t kbase = c->d.h0 + s0 - ls0;       // key buffer = lane's first buffer (ls0) + position in the group
 			V.tag = tags[j]; c->d.tag = tags[j];
+			if (c->tile_mode) {
+				launch_setup(c, V, st, s0, n, kbase, true); if (mark) mark(1);
+				rad_launch_tiles_view(c, V, TV, st, s0, n, keep_items, mark);
+				continue;
+			}
 			launch_setup(c, V, st, s0, n, kbase); if (mark) mark(1);
 			launch_chunks(c, V, st, kbase); if (mark) mark(2);
 			rad_launch_process_view(c, V, st, s0, n, kbase, keep_items); if (mark) mark(4);
