@@ -69,6 +69,32 @@ __device__ void build_mvp(const Quad& q, int face, const float* __restrict__ pro
 	mat_product(out, proj, mv);     // t_projection * t_modelview (Main.cpp:1183)
 }
 
+// The view basis (right, up, -dir rows of the LookAt matrix) a face really gets: the same float32 operations as build_mvp
+// above (Camera.cpp:19-52, Transform.cpp:26-46), kept separate so that the MVP code stays as verified.
+__device__ void look_basis(const Quad& q, int face, V3& right, V3& up, V3& dir) {
+	V3 eye = mk((q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f, (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f, (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f);
+	V3 normal = rcross(vsub(q.b, q.a), vsub(q.d, q.a));
+	V3 pup = vsub(q.d, q.a);
+	V3 target;
+	switch (face) {
+	case 0: target = pup; up = vneg(normal); break;
+	case 1: target = vneg(pup); up = normal; break;
+	case 2: target = vneg(rcross(normal, pup)); up = pup; break;
+	case 3: target = rcross(normal, pup); up = pup; break;
+	default: target = normal; up = pup; break;
+	}
+	dir = vnormalize(vsub(vadd(target, eye), eye));
+	right = vnormalize(rcross(dir, up));
+	up = rcross(right, dir);
+}
+// length of the part of w that does not lie along its dominant axis of the orthonormal frame ax (rows s, t, f)
+__device__ __forceinline__ float off_axis(const float* __restrict__ ax, V3 w) {
+	const float a = w.x * ax[0] + w.y * ax[1] + w.z * ax[2], b = w.x * ax[3] + w.y * ax[4] + w.z * ax[5], c = w.x * ax[6] + w.y * ax[7] + w.z * ax[8];
+	const float sa = a * a, sb = b * b, sc = c * c;
+	const float mx = fmaxf(sa, fmaxf(sb, sc));
+	return sqrtf(sa == mx ? sb + sc : (sb == mx ? sa + sc : sa + sb));
+}
+
 // thread 0 of a block: emitter record of slot h.  sel_parity >= 0 (k == 1 only): the emitter is first decoded from the
 // fused argmax key selkey[sel_parity] (all-zero energies leave key 0 == patch 0, the reference's seeded entry) and the
 // other key is recycled.  Loads bypass L1: in the update kernel's tail the state was just written by other blocks.
@@ -95,6 +121,17 @@ __device__ __forceinline__ RadEmitter camera_emitter(const RadDev& D, uint32_t h
 		e.ax[0] = sx.x * ls; e.ax[1] = sx.y * ls; e.ax[2] = sx.z * ls;
 		e.ax[3] = u.x * lt; e.ax[4] = u.y * lt; e.ax[5] = u.z * lt;
 		e.ax[6] = n.x * lf; e.ax[7] = n.y * lf; e.ax[8] = n.z * lf;
+		// The faces' real bases come out of the reference's float32 LookAt(eye, target + eye, up): for a small patch |target|
+		// is tiny against |eye| (a side face's target is n x u, ~edge^3) and "target + eye - eye" turns the face by up to a few
+		// degrees — faithfully reproduced in the MVPs.  The conservative culls work in the ideal frame above, so their margin
+		// is widened by the largest deviation of a real basis vector from it (1e-4 at 16 k patches, 2e-3 at 250 k).
+		float dev = 0.0f;
+		for (int face = 0; face < RAD_NFACES; face++) {
+			V3 fr, fu, fd; look_basis(q, face, fr, fu, fd);
+			dev = fmaxf(dev, fmaxf(off_axis(e.ax, fr), fmaxf(off_axis(e.ax, fu), off_axis(e.ax, fd))));
+		}
+		const float margin = 2e-3f + 3.0f * dev;
+		e.ctol = margin * margin;
 	} else e.valid = 0;
 	D.em[h] = e;
 	D.emlite[2 * h] = make_float4(e.S[0], e.S[1], e.S[2], __uint_as_float(e.valid ? (1u | (e.order << 1)) : 0u));

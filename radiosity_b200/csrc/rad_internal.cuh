@@ -72,6 +72,8 @@ struct RadEmitter {               // per hemicube slot
 	float nrm[3];
 	float ax[9];                  // orthonormal shooter frame s, t, f (rows) for the conservative culls
 	uint32_t order;               // position in the selection list (== slot unless the list is dealt out to ranks, see RadDev::deal)
+	float ctol;                   // squared relative margin of the conservative culls: (2e-3 + 3 * deviation of the faces' real
+	                              // float32 view bases from the ideal frame ax)^2, see camera_emitter
 };
 
 struct RadDev {                   // device pointers + sizes, passed by value to kernels

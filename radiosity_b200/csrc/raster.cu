@@ -277,7 +277,8 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 }
 
 // ---- stage 1: conservative culling, one lane per (patch, hemicube) ---------------------------------------------------
-// Emits the (patch, face) pairs that MAY produce pixels.  Every test has a wide margin (1e-3 of the distance to the eye,
+// Emits the (patch, face) pairs that MAY produce pixels.  Every test has a wide margin (2e-3 of the distance to the eye
+// plus the deviation of the faces' real float32 view bases from the ideal frame, RadEmitter::ctol;
 // ~6 degrees for facing) and only ever drops work that the exact stage would drop too:
 //  - both triangles clearly face away from the eye: the exact path would get a negative window-space area on every face;
 //  - per face, all four vertices clearly outside one side plane of the face's 90-degree frustum, or clearly below the
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D) {
 				const float a = r.x * em.ax[0] + r.y * em.ax[1] + r.z * em.ax[2];
 				const float b = r.x * em.ax[3] + r.y * em.ax[4] + r.z * em.ax[5];
 				const float c = r.x * em.ax[6] + r.y * em.ax[7] + r.z * em.ax[8];
-				const float tol = 4e-6f * (r.x * r.x + r.y * r.y + r.z * r.z);       // (2e-3 |r|)^2
+				const float tol = em.ctol * (r.x * r.x + r.y * r.y + r.z * r.z);     // ((2e-3 + 3 dev) |r|)^2, see camera_emitter
 				const float h[17] = { c, c - a, c + a, c - b, c + b, b - a, b + a, b - c, -b - a, -b + a, -b - c, a - b, a + b, a - c, -a - b, -a + b, -a - c };
 				#pragma unroll
 				for (int k = 0; k < 17; k++) if (h[k] < 0.0f && h[k] * h[k] > tol) out[k] |= 1u << v;

@@ -21,6 +21,7 @@
 #include "rad_internal.cuh"
 #include "segadd.cuh"
 #include "tile_walk.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -114,8 +115,9 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(RadDev D, RadTiles T, ui
 	if (threadIdx.x == 0) { T.base[n] = carry; if (carry > T.refs_cap) D.ctl->q_overflow = 1; }
 }
 
-// one CTA per (tile, hemicube slot of the launch group)
-__global__ void __launch_bounds__(128) tile_kernel(RadDev D, RadTiles T, int keep_items) {
+// one CTA of THREADS threads per (tile, hemicube slot of the launch group)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) tile_kernel(RadDev D, RadTiles T, int keep_items) {
 	__shared__ __align__(16) unsigned long long skeys[RAD_TILE_PIX];
 	const uint32_t ls = blockIdx.y, slot = D.h0 + ls, tile = blockIdx.x;
 	// last consumer of the lane's work lists: recycle them for the next launch group (as process_kernel does)
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(128) tile_kernel(RadDev D, RadTiles T, int kee
 	{
 		const uint4* __restrict__ qsm = reinterpret_cast<const uint4*>(D.q_sm);
 		const int sub = lane >> 3, l8 = lane & 7;
-		for (uint32_t r0 = b0 + 4u * warp; r0 < b1; r0 += 16u) {
+		for (uint32_t r0 = b0 + 4u * warp; r0 < b1; r0 += THREADS / 8) {
 			const uint32_t r = r0 + sub;
 			tw::QuadWalk q; q.none();
 			if (r < b1) {
@@ -166,22 +168,22 @@ __global__ void __launch_bounds__(128) tile_kernel(RadDev D, RadTiles T, int kee
 			for (int s = 0; s < msteps; s++) q.step(emit);
 		}
 	}
-	// large triangles: the CTA's four warps share the 8x4-pixel steps of (bbox) n (tile)
+	// large triangles: the CTA's warps share the 8x4-pixel steps of (bbox) n (tile)
 	for (uint32_t r = b1; r < b2; r++) {
 		const RadBigTri rt = D.q_tri[T.refs[r]];
 		const tw::BigTri t = load_big(rt);
 		tw::BigWalk w; w.init(t, tx0, ty0, tw_, th_);
-		for (int s = warp; s < w.nsteps; s += 4) w.step(t, s, lane, emit);
+		for (int s = warp; s < w.nsteps; s += THREADS / 32) w.step(t, s, lane, emit);
 	}
 	__syncthreads();
 	// ProcessHemicube on the resolved tile: 4 consecutive pixels per lane and step, 16 lanes per tile row
 	float* __restrict__ F = D.F + (size_t)slot * D.P;
 	const float4* __restrict__ ff4 = reinterpret_cast<const float4*>(D.ff);
-	constexpr int kSteps = RAD_TILE_PIX / 4 / 128;
+	constexpr int kSteps = RAD_TILE_PIX / 4 / THREADS;
 	uint4 id[kSteps]; float4 v[kSteps];
 	#pragma unroll
 	for (int it = 0; it < kSteps; it++) {
-		const int q = it * 128 + (int)threadIdx.x;
+		const int q = it * THREADS + (int)threadIdx.x;
 		const int row = q >> 4, c4 = q & 15;
 		const bool inb = 4 * c4 < tw_ && row < th_;
 		id[it] = make_uint4(0u, 0u, 0u, 0u); v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -212,7 +214,9 @@ void rad_launch_tiles_view(rad_ctx* c, const RadDev& V, const RadTiles& T, cudaS
 	bin_scan_kernel<<<1, 1024, 0, st>>>(D, T, nlists);
 	bin_kernel<true><<<148 * 4, 256, 0, st>>>(D, T);
 	if (mark) mark(2);
-	tile_kernel<<<dim3(T.T, n), 128, 0, st>>>(D, T, keep_items ? 1 : 0);
+	static const int threads = [] { const char* e = getenv("RAD_TILE_THREADS"); const int v = e ? atoi(e) : 128; return v == 256 ? 256 : 128; }();   // tuning knob
+	if (threads == 256) tile_kernel<256><<<dim3(T.T, n), 256, 0, st>>>(D, T, keep_items ? 1 : 0);
+	else tile_kernel<128><<<dim3(T.T, n), 128, 0, st>>>(D, T, keep_items ? 1 : 0);
 	if (mark) mark(4);
 	c->launches += 4;
 	c->keys_dirty = false;

@@ -45,6 +45,14 @@ def test_config3_size_invariants_and_oracle_spot_check(api, orc):
     assert agree >= 0.999
     assert agree == 1.0
     assert rel_l2(ctx.read_formfactors(0), orc.process_ids(exp, ff, N, P)) < 1e-5
+    # a shooter on the slanted x = 5.5 wall: its side faces are turned by 0.13 degrees by the reference's float32 LookAt
+    # (target + eye - eye); the conservative culls dropped 57 visible pixels here before their margin followed that
+    # (RadEmitter::ctol).  This hemicube also looks out of the box through the crack along the slanted wall: 797 empty pixels
+    ctx.set_emitters([158100])
+    ctx.render()
+    got2 = ctx.read_itembuffer(0)
+    exp2 = orc.render_hemicube(v, 158100, N, threads=8)
+    assert (got2 == exp2).all(), int((got2 != exp2).sum())
     ctx.close()
 
 

@@ -432,3 +432,28 @@ def test_itembuffer_random_quad_soup(api, orc, seed, n, size, N):
         Fo = np.bincount(exp.ravel(), weights=ff.astype(np.float64), minlength=P + 1)[1:]
         assert np.abs(F - Fo).max() <= 1e-5 * max(1.0, Fo.max())
     ctx.close()
+
+
+def test_itembuffer_small_shooter_rotated_side_faces(api, orc):
+    """Regression (found with the tile path's soup test): the reference builds a face's view matrix from
+    LookAt(eye, target + eye, up) in float32; for a small shooter |target| of the side faces (n x u, ~edge^3) is tiny
+    against |eye| and the face comes out turned by up to a few degrees.  The MVPs reproduce that bit for bit, so the
+    conservative culls — which work in the ideal shooter frame — must widen their margin by that deviation
+    (RadEmitter::ctol).  Shooter 5302 of this soup lost one pixel of patch 14680 on its LEFT face before."""
+    seed, n, size, N = 4, 20000, 0.05, 256
+    v = random_soup(seed, n, size)
+    P = v.shape[0]
+    c = np.full((P, 3), 0.5, np.float32); r = np.zeros((P, 3), np.float32); il = np.zeros((P, 3), np.float32)
+    ctx = api.Context(N, 8, P)
+    ctx.set_formfactors(api.formfactors(N))
+    ctx.upload_scene(v, c, r, il)
+    rng = np.random.default_rng(100 + seed)
+    shooters = [int(x) for x in rng.choice(P, 8, replace=False)]
+    assert 5302 in shooters
+    ctx.set_emitters(shooters)
+    ctx.render()
+    for hi, sh in enumerate(shooters):
+        exp = orc.render_hemicube(v, sh, N)
+        got = ctx.read_itembuffer(hi)
+        assert (got == exp).all(), (sh, int((got != exp).sum()))
+    ctx.close()

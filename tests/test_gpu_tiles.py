@@ -2,19 +2,14 @@
 oracle and against the default global-key path.  Same bars: item buffers bit for bit, radiosity within 1e-5 rel-L2 of
 the default path on the same schedule.
 
-The tile path is opt-in and was written without GPU time left in its round: these tests run only with
-RAD_TEST_TILES=1 until the path has been confirmed on a B200 (the CPU check of its walk arithmetic always runs:
-tests/test_tile_walk_cpu.py)."""
-import os
-
+The arithmetic of the tile walks is also checked without a GPU: tests/test_tile_walk_cpu.py."""
 import numpy as np
 import pytest
 
 from util import rel_l2
 from test_gpu_parity import make_ctx, random_soup
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("RAD_TEST_TILES") != "1", reason="opt-in path: set RAD_TEST_TILES=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
