@@ -16,7 +16,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--sides", type=int, nargs="+", default=[256, 512, 1024, 2048])
 ap.add_argument("--area", type=float, default=0.0035)
 ap.add_argument("--k", type=int, default=64)
+ap.add_argument("--raster", default="keys", help="keys (global key buffers, default path) or tiles (tile-binned rasteriser)")
 a = ap.parse_args()
+os.environ["RAD_RASTER"] = a.raster
 peak = 6545.3
 try:
     peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -34,11 +36,15 @@ for N in a.sides:
     for _ in range(nb):
         prof += ctx.profile_batch()
     prof /= nb
+    ctx.restore_state()
+    st = ctx.shoot(16)                             # the real thing: CUDA graph, raster lanes
+    graph_ms = st.gpu_ms / 16
     ctx.restore_state(); ctx.select(); ctx.render()
     k2_ms = ctx.bench_process(10)
     RES = 3 * N * N
     px = a.k * RES
-    rows.append({"hemicube": N, "patches": scene.P, "k": a.k, "pixels_per_batch": px,
+    rows.append({"hemicube": N, "patches": scene.P, "k": a.k, "raster": a.raster, "pixels_per_batch": px,
+                 "graph_batch_ms": graph_ms, "graph_shots_per_s": a.k / (graph_ms * 1e-3),
                  "raster_setup_ms": float(prof[1]), "raster_chunks_ms": float(prof[2]), "fused_process_ms": float(prof[4]),
                  "select_ms": float(prof[0]), "apply_ms": float(prof[5]),
                  "batch_ms": float(prof.sum()), "shots_per_s": a.k / (float(prof.sum()) * 1e-3),
