@@ -375,6 +375,10 @@ def main():
                     "peak_source": peak_src,
                     "note": "the dominant kernel (K1 raster) is bound by set-up arithmetic, instruction issue and L2 atomics, not by HBM: its algorithmic bytes are tiny; "
                             "the HBM-bound kernel of the path is K2 (ProcessHemicube), reported in process_hemicube against the same peak"}
+        raster_mode = "tiles" if os.environ.get("RAD_RASTER") == "tiles" else "keys"
+        if raster_mode == "tiles":      # opt-in tile-binned rasteriser: the stage slots hold other kernels
+            roofline["note"] = ("RAD_RASTER=tiles: in `kernels`, queue_ms = bin_kernel x2 + bin_scan_kernel, 'process_hemicube (K2, fused key form)' = tile_kernel "
+                                "(visibility in shared memory + fused ProcessHemicube); atomic_roofline does not apply")
         kk = k_rank                                      # item buffers one launch of this rank covers
         k2_bytes = kk * 8.0 * RES + kk * 4.0 * P
         k2 = {"gpix_per_s": kk * RES / (k2_ms * 1e-3) / 1e9, "ms_per_launch": k2_ms, "pixels_per_launch": kk * RES,
@@ -389,7 +393,7 @@ def main():
                            "parallelism": (f"{k_rank} of the batch's {k} shooters per rank, dB combined once per batch by " +
                                            ("the fused peer-memory update kernel (NVLink, CUDA IPC)" if exchange == "peer" else "ncclAllReduce") if world > 1 else "1gpu"),
                            "l2": "256 MB write between timed iterations (flush)", "timing": "CUDA events on the launching stream inside rad_shoot, max over ranks",
-                           "wall_s_incl_flush": wall},
+                           "wall_s_incl_flush": wall, "raster": raster_mode},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": int(P * 84 + 0), "d2h_bytes_per_step": int(P * 24),
                         "note": "rad_upload_scene (page-locked host arrays -> HBM, layout conversion on the GPU) + rad_shoot + rad_download_state (-> page-locked host arrays) per step, wall clock"},
