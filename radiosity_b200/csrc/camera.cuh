@@ -69,9 +69,11 @@ __device__ void build_mvp(const Quad& q, int face, const float* __restrict__ pro
 	mat_product(out, proj, mv);     // t_projection * t_modelview (Main.cpp:1183)
 }
 
-// The view basis (right, up, -dir rows of the LookAt matrix) a face really gets: the same float32 operations as build_mvp
-// above (Camera.cpp:19-52, Transform.cpp:26-46), kept separate so that the MVP code stays as verified.
-__device__ void look_basis(const Quad& q, int face, V3& right, V3& up, V3& dir) {
+// The view basis (rows right, up, -dir of the LookAt matrix) of a face.  ideal == false: what the face really gets — the same
+// float32 operations as build_mvp above (Camera.cpp:19-52, Transform.cpp:26-46; kept separate so that the MVP code stays
+// as verified).  ideal == true: the same without the round trip of the target through eye; these vectors are +-axes of the
+// orthonormal shooter frame the conservative culls work in.
+__device__ void look_basis(const Quad& q, int face, bool ideal, V3& right, V3& up, V3& dir) {
 	V3 eye = mk((q.a.x + q.b.x + q.c.x + q.d.x) / 4.0f, (q.a.y + q.b.y + q.c.y + q.d.y) / 4.0f, (q.a.z + q.b.z + q.c.z + q.d.z) / 4.0f);
 	V3 normal = rcross(vsub(q.b, q.a), vsub(q.d, q.a));
 	V3 pup = vsub(q.d, q.a);
@@ -83,16 +85,32 @@ __device__ void look_basis(const Quad& q, int face, V3& right, V3& up, V3& dir) 
 	case 3: target = rcross(normal, pup); up = pup; break;
 	default: target = normal; up = pup; break;
 	}
-	dir = vnormalize(vsub(vadd(target, eye), eye));
+	dir = vnormalize(ideal ? target : vsub(vadd(target, eye), eye));
 	right = vnormalize(rcross(dir, up));
 	up = rcross(right, dir);
 }
-// length of the part of w that does not lie along its dominant axis of the orthonormal frame ax (rows s, t, f)
-__device__ __forceinline__ float off_axis(const float* __restrict__ ax, V3 w) {
-	const float a = w.x * ax[0] + w.y * ax[1] + w.z * ax[2], b = w.x * ax[3] + w.y * ax[4] + w.z * ax[5], c = w.x * ax[6] + w.y * ax[7] + w.z * ax[8];
-	const float sa = a * a, sb = b * b, sc = c * c;
-	const float mx = fmaxf(sa, fmaxf(sb, sc));
-	return sqrtf(sa == mx ? sb + sc : (sb == mx ? sa + sc : sa + sb));
+__device__ __forceinline__ float vdist(V3 a, V3 b) { const V3 d = vsub(a, b); return sqrtf(d.x * d.x + d.y * d.y + d.z * d.z); }
+
+// Squared relative margin of the conservative culls for shooter q (RadEmitter::ctol).
+// The reference builds a face's view matrix from LookAt(eye, target + eye, up) in float32: for a small patch |target| is
+// tiny against |eye| (a side face's target is n x u, ~edge^3) and "target + eye - eye" turns the face — 1e-4 rad at 16 k
+// patches, 0.13 degrees at 250 k, 0.9 degrees at 1 M, anything (axes swapped) for patches a thousand times smaller than
+// the scene — faithfully reproduced in the MVPs.  The culls work in the ideal frame, and every plane they test is spanned
+// by at most two basis vectors of a face, so a vertex that is outside an ideal plane by more than 2 * dev * |r| is outside
+// the real one: margin = 2e-3 + 3 * dev, dev = the largest |real - ideal| over the 15 basis vectors.  A margin^2 >= 2 switches
+// the frustum and horizon culls off (|h| <= sqrt(2) |r|); the facing cull does not depend on the frame.
+__device__ float face_deviation(const Quad& q, int face) {        // largest |real - ideal| over one face's three basis vectors
+	V3 rr, ru, rd, ir, iu, id;
+	look_basis(q, face, false, rr, ru, rd);
+	look_basis(q, face, true, ir, iu, id);
+	return fmaxf(vdist(rr, ir), fmaxf(vdist(ru, iu), vdist(rd, id)));
+}
+__device__ __forceinline__ float margin2_of(float dev) { const float margin = 2e-3f + 3.0f * dev; return margin * margin; }
+// serial form (camera_block below spreads the faces over five lanes); also what the CPU check of the margin evaluates
+__device__ float cull_margin2(const Quad& q) {
+	float dev = 0.0f;
+	for (int face = 0; face < RAD_NFACES; face++) dev = fmaxf(dev, face_deviation(q, face));
+	return margin2_of(dev);
 }
 
 // thread 0 of a block: emitter record of slot h.  sel_parity >= 0 (k == 1 only): the emitter is first decoded from the
@@ -121,30 +139,27 @@ __device__ __forceinline__ RadEmitter camera_emitter(const RadDev& D, uint32_t h
 		e.ax[0] = sx.x * ls; e.ax[1] = sx.y * ls; e.ax[2] = sx.z * ls;
 		e.ax[3] = u.x * lt; e.ax[4] = u.y * lt; e.ax[5] = u.z * lt;
 		e.ax[6] = n.x * lf; e.ax[7] = n.y * lf; e.ax[8] = n.z * lf;
-		// The faces' real bases come out of the reference's float32 LookAt(eye, target + eye, up): for a small patch |target|
-		// is tiny against |eye| (a side face's target is n x u, ~edge^3) and "target + eye - eye" turns the face by up to a few
-		// degrees — faithfully reproduced in the MVPs.  The conservative culls work in the ideal frame above, so their margin
-		// is widened by the largest deviation of a real basis vector from it (1e-4 at 16 k patches, 2e-3 at 250 k).
-		float dev = 0.0f;
-		for (int face = 0; face < RAD_NFACES; face++) {
-			V3 fr, fu, fd; look_basis(q, face, fr, fu, fd);
-			dev = fmaxf(dev, fmaxf(off_axis(e.ax, fr), fmaxf(off_axis(e.ax, fu), off_axis(e.ax, fd))));
-		}
-		const float margin = 2e-3f + 3.0f * dev;
-		e.ctol = margin * margin;
 	} else e.valid = 0;
 	D.em[h] = e;
 	D.emlite[2 * h] = make_float4(e.S[0], e.S[1], e.S[2], __uint_as_float(e.valid ? (1u | (e.order << 1)) : 0u));
 	D.emlite[2 * h + 1] = make_float4(e.color[0], e.color[1], e.color[2], __uint_as_float(e.id));
 	return e;
 }
-// whole block: slot h's emitter record (thread 0) and its five MVPs (threads 0..4)
+// whole block: slot h's emitter record (thread 0), its five MVPs and the cull margin (threads 0..4: one face each; the
+// margin is written into the record afterwards — the culls that read it run in a later kernel)
 __device__ __forceinline__ void camera_block(const RadDev& D, uint32_t h, int sel_parity, RadEmitter* s_e) {
 	if (threadIdx.x == 0) *s_e = camera_emitter(D, h, sel_parity);
 	__syncthreads();
+	float dev = 0.0f;
 	if (s_e->valid && threadIdx.x < RAD_NFACES) {
 		const Quad q = load_quad(D, s_e->id);
 		build_mvp(q, threadIdx.x, D.proj, D.mvp + ((size_t)h * RAD_NFACES + threadIdx.x) * 16);
+		dev = face_deviation(q, threadIdx.x);
+	}
+	if (threadIdx.x < 32) {                       // first warp, all of its lanes: max over lanes 0..7 ends up in lane 0
+		#pragma unroll
+		for (int o = 4; o >= 1; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xFFFFFFFFu, dev, o));
+		if (threadIdx.x == 0 && s_e->valid) D.em[h].ctol = margin2_of(dev);
 	}
 }
 

@@ -28,23 +28,28 @@ def shooter_frame(v, sh):
     return eye, n, u, ax
 
 
+def _look_basis(eye, n, u, face, ideal):
+    if face == 0: target, up = u, -n
+    elif face == 1: target, up = -u, n
+    elif face == 2: target, up = -rcross(n, u), u
+    elif face == 3: target, up = rcross(n, u), u
+    else: target, up = n, u
+    dirv = vnormalize(target.astype(f32) if ideal else ((target + eye).astype(f32) - eye).astype(f32))
+    right = vnormalize(rcross(dirv, up))
+    return right, rcross(right, dirv), dirv
+
+
 def frame_deviation(v, sh):
-    """camera_emitter: largest off-axis part of a basis vector of the faces' REAL view bases (the reference's float32
-    LookAt(eye, target + eye, up), Camera.cpp:19-52, Transform.cpp:26-46) in the ideal shooter frame"""
+    """camera_emitter: largest |real - ideal| over the basis vectors of the five faces, real = the reference's float32
+    LookAt(eye, target + eye, up) (Camera.cpp:19-52, Transform.cpp:26-46), ideal = the same without the round trip through
+    eye (its vectors are +-axes of the shooter frame the culls work in)"""
     eye, n, u, ax = shooter_frame(v, sh)
     dev = 0.0
     for face in range(5):
-        if face == 0: target, up = u, -n
-        elif face == 1: target, up = -u, n
-        elif face == 2: target, up = -rcross(n, u), u
-        elif face == 3: target, up = rcross(n, u), u
-        else: target, up = n, u
-        dirv = vnormalize(((target + eye).astype(f32) - eye).astype(f32))
-        right = vnormalize(rcross(dirv, up))
-        up2 = rcross(right, dirv)
-        for w in (dirv, right, up2):
-            comp = np.sort((ax @ w) ** 2)
-            dev = max(dev, float(np.sqrt(comp[0] + comp[1])))
+        real = _look_basis(eye, n, u, face, False); ideal = _look_basis(eye, n, u, face, True)
+        for wr, wi in zip(real, ideal):
+            d = (wr - wi).astype(f32)
+            dev = max(dev, float(np.sqrt((d * d).sum(dtype=f32))))
     return dev
 
 

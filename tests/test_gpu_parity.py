@@ -457,3 +457,23 @@ def test_itembuffer_small_shooter_rotated_side_faces(api, orc):
         got = ctx.read_itembuffer(hi)
         assert (got == exp).all(), (sh, int((got != exp).sum()))
     ctx.close()
+
+
+@pytest.mark.parametrize("seed,n,size,N,shooter", [(5, 30000, 0.03, 256, 23181), (6, 8000, 0.02, 128, 6044)])
+def test_itembuffer_shooter_with_swapped_camera_axes(api, orc, seed, n, size, N, shooter):
+    """Shooters a thousand times smaller than the scene (found by scripts/fuzz_parity.py): target + eye - eye leaves so
+    little of the target that the reference's face cameras come out with their axes swapped.  The MVPs follow the
+    reference; the conservative culls must notice and stand down (RadEmitter::ctol >= 2)."""
+    v = random_soup(seed, n, size)
+    P = v.shape[0]
+    c = np.full((P, 3), 0.5, np.float32); z = np.zeros((P, 3), np.float32)
+    ctx = api.Context(N, 2, P)
+    ctx.set_formfactors(api.formfactors(N))
+    ctx.upload_scene(v, c, z, z)
+    ctx.set_emitters([shooter, (shooter + 1) % P])
+    ctx.render()
+    for hi, sh in enumerate([shooter, (shooter + 1) % P]):
+        exp = orc.render_hemicube(v, sh, N)
+        got = ctx.read_itembuffer(hi)
+        assert (got == exp).all(), (sh, int((got != exp).sum()))
+    ctx.close()
