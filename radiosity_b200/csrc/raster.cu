@@ -475,6 +475,10 @@ __device__ __forceinline__ void edge_origin(int ax, int ay, int bx, int by, int&
 //     the diagonal itself to exactly one) and takes its depth from that triangle's plane — the same integers and the
 //     same float operations as two separate triangle walks, in about half the pixel visits;
 //  2. chunk queue: one warp per (triangle, chunk) of at most tile x tile pixels, 8x4 pixels per step.
+// PF (opt-in, RAD_QUEUE_PREFETCH=1): the four records of a warp's NEXT step are fetched into shared memory with cp.async
+// while the current ones are walked (no registers held across the walk), for the ~20 % of the stall samples that wait for
+// the record load.  Not measured yet.
+template <bool PF>
 __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
 	const uint32_t tagsh = D.tag << 24;
@@ -484,7 +488,26 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 		const uint4* __restrict__ qsm = reinterpret_cast<const uint4*>(D.q_sm);
 		const int sub = lane >> 3, l8 = lane & 7;
 		const int W = (int)D.W;
-		for (uint32_t base = gw * 4; base < nsm; base += nw * 4) {
+		__shared__ __align__(16) uint4 s_rec[PF ? 4 : 1][2][16];      // [warp][buffer][4 records x 4 words]
+		const int wib = threadIdx.x >> 5;
+		// lanes 0..15 copy one 16-byte word each of the records base .. base + 3
+		auto prefetch = [&](uint32_t b, int buf) {
+			const uint32_t rec = b + (uint32_t)(lane >> 2);
+			if (lane < 16 && rec < nsm) {
+				const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_rec[wib][buf][lane]);
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(qsm + 4 * (size_t)rec + (lane & 3)) : "memory");
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+		};
+		uint32_t it = 0;
+		if (PF && gw * 4 < nsm) prefetch(gw * 4, 0);
+		for (uint32_t base = gw * 4; base < nsm; base += nw * 4, it++) {
+			if (PF) {
+				__syncwarp();                                         // every lane has read the buffer that is refilled now
+				prefetch(base + nw * 4, (int)((it + 1) & 1));         // (an empty group past the end of the queue)
+				asm volatile("cp.async.wait_group 1;" ::: "memory");
+				__syncwarp();
+			}
 			const uint32_t i = base + sub;
 			int npx = 0, w8 = 1, hh = 0, q8 = 0, r8 = 0, x = 0, y = 0;
 			int a0y2 = 0, a1y2 = 0, a2y2 = 0, b0y2 = 0, b1y2 = 0;
@@ -494,8 +517,14 @@ __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 			float Z0 = 0, dA1 = 0, dA2 = 0, dB2 = 0, invA = 0, invB = 0;
 			uint32_t id1 = 0; unsigned long long* kp = nullptr;
 			if (i < nsm) {
-				const uint4 r0 = __ldg(qsm + 4 * (size_t)i), r1 = __ldg(qsm + 4 * (size_t)i + 1), r2 = __ldg(qsm + 4 * (size_t)i + 2);
-				const uint2 r3 = __ldg(reinterpret_cast<const uint2*>(qsm + 4 * (size_t)i + 3));
+				uint4 r0, r1, r2; uint2 r3;
+				if (PF) {
+					const uint4* sr = &s_rec[wib][it & 1][4 * sub];
+					r0 = sr[0]; r1 = sr[1]; r2 = sr[2]; r3 = *reinterpret_cast<const uint2*>(sr + 3);
+				} else {
+					r0 = __ldg(qsm + 4 * (size_t)i); r1 = __ldg(qsm + 4 * (size_t)i + 1); r2 = __ldg(qsm + 4 * (size_t)i + 2);
+					r3 = __ldg(reinterpret_cast<const uint2*>(qsm + 4 * (size_t)i + 3));
+				}
 				const int x0 = (int)(r0.x << 16) >> 16, y0 = (int)r0.x >> 16, x1 = (int)(r0.y << 16) >> 16, y1 = (int)r0.y >> 16;
 				const int x2 = (int)(r0.z << 16) >> 16, y2 = (int)r0.z >> 16, x3 = (int)(r0.w << 16) >> 16, y3 = (int)r0.w >> 16;
 				int bA0, bB0;
@@ -704,7 +733,9 @@ static void launch_chunks(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t
 	RadDev D = V;
 	D.kbase = kbase;
 	static const int ctas = [] { const char* e = getenv("RAD_QUEUE_CTAS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();   // tuning knob: persistent CTAs per SM
-	raster_queue_kernel<<<148 * ctas, 128, 0, st>>>(D);
+	static const bool pf = [] { const char* e = getenv("RAD_QUEUE_PREFETCH"); return e && atoi(e) != 0; }();   // tuning knob (not measured yet)
+	if (pf) raster_queue_kernel<true><<<148 * ctas, 128, 0, st>>>(D);
+	else raster_queue_kernel<false><<<148 * ctas, 128, 0, st>>>(D);
 	c->launches++;
 }
 
