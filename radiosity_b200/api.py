@@ -134,6 +134,7 @@ def host_lib():
         lib.radhost_solver_shade.argtypes = [_vp, _vp]
         lib.radhost_scene_save.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int]
         lib.radhost_scene_load.argtypes = [_vp, ctypes.c_char_p]
+        lib.radhost_scene_export_ply.argtypes = [_vp, _vp, ctypes.c_char_p, ctypes.c_float]
         lib.radhost_sizeof_patch.restype = _u32
         _host = lib
     return _host
@@ -203,6 +204,14 @@ class Scene:
         out = np.zeros((self.P, 12), np.float32)
         self.lib.radhost_scene_smooth_shade(self.h, _ptr(out))
         return out
+
+    def export_ply(self, path, colors12, exposure=1.0):
+        """ExportPly (MeshExport.h): the scene's quads with the display stage's vertex colours as a binary PLY"""
+        c = _f32c(colors12)
+        if c.size != self.P * 12:
+            raise RadError("export_ply: colours must be float[P, 12]")
+        if not self.lib.radhost_scene_export_ply(self.h, _ptr(c), os.fsencode(path), float(exposure)):
+            raise RadError(f"cannot write {path}")
 
     def select(self, count):
         """ModelContainer::getHighestRadiosityPatchesId -> (ids, is_null)"""

@@ -8,6 +8,8 @@
 //                 mesh_scale <f> (default 0.01), mesh_flip <0|1>, mesh_emit <material index> go with it
 //   dump <path>   write "id Bx By Bz Ix Iy Iz" per patch when done
 //   save <path>   checkpoint the scene + energies when done (portable .rr, SceneFile.h; the reference's Ctrl+S)
+//   ply <path>    write the shaded scene (vertex colours of the display stage, computed on the GPU) as a binary PLY;
+//                 exposure <f> scales the colours before the [0, 1] clamp (default 1)
 //   load <path>   resume from a checkpoint instead of building a scene (the reference's Ctrl+O; also reads its raw dumps)
 #include <cstdio>
 #include <cstdlib>
@@ -20,11 +22,14 @@
 #include "ModelContainer.h"
 #include "Radiosity.h"
 #include "SceneFile.h"
+#include "MeshExport.h"
+#include <vector>
 
 int main(int argc, const char** argv) {
 	if ((argc - 1) % 2 > 0) { std::cerr << "Wrong number of arguments (expected key value pairs)" << std::endl; return -1; }
 	long shots = -1; int device = 0; unsigned int select = RAD_SELECT_REFERENCE;
 	const char* obj = NULL; const char* dump = NULL; const char* save = NULL; const char* load = NULL;
+	const char* ply = NULL; float exposure = 1.0f;
 	const char* mesh = NULL; float mesh_scale = 0.01f; bool mesh_flip = false; int mesh_emit = -1;
 	for (int i = 1; i < argc; i += 2) {
 		const char* k = argv[i]; const char* v = argv[i + 1];
@@ -43,6 +48,8 @@ int main(int argc, const char** argv) {
 		else if (!strcmp(k, "dump")) dump = v;
 		else if (!strcmp(k, "save")) save = v;
 		else if (!strcmp(k, "load")) load = v;
+		else if (!strcmp(k, "ply")) ply = v;
+		else if (!strcmp(k, "exposure")) exposure = (float)atof(v);
 	}
 	Config::freeze();
 
@@ -72,6 +79,11 @@ int main(int argc, const char** argv) {
 	std::cout << "gpu time " << gpu_ms << " ms, " << std::setprecision(6) << (cycles / (gpu_ms * 1e-3)) << " hemicubes/s" << std::endl;
 	if (!solver.syncToScene()) { std::cerr << solver.error() << std::endl; return -1; }
 	if (save && !SaveToFile(std::string(save), scene)) { std::cerr << "Unable to write '" << save << "'" << std::endl; return -1; }
+	if (ply) {     // display stage on the device (K5), then the mesh the reference would have drawn
+		std::vector<float> colors((size_t)scene.getPatchesCount() * 12);
+		if (!solver.shadeVertices(colors.data())) { std::cerr << solver.error() << std::endl; return -1; }
+		if (!ExportPly(std::string(ply), scene, colors.data(), exposure)) { std::cerr << "Unable to write '" << ply << "'" << std::endl; return -1; }
+	}
 	if (dump) {
 		std::ofstream out(dump);
 		Patch** pp = scene.getPatches();

@@ -11,6 +11,7 @@
 #include "Radiosity.h"
 #include "Colors.h"
 #include "SceneFile.h"
+#include "MeshExport.h"
 
 extern "C" {
 
@@ -140,6 +141,8 @@ int radhost_solver_shade(void* s, float* out12) { return ((RadiositySolver*)s)->
 
 int radhost_scene_save(void* s, const char* path, int format) { return SaveToFile(std::string(path), *(ModelContainer*)s, (RRFormat)format) ? 1 : 0; }
 int radhost_scene_load(void* s, const char* path) { return LoadFromFile(std::string(path), *(ModelContainer*)s) ? 1 : 0; }
+
+int radhost_scene_export_ply(void* s, const float* colors12, const char* path, float exposure) { return ExportPly(std::string(path), *(ModelContainer*)s, colors12, exposure) ? 1 : 0; }
 
 unsigned radhost_sizeof_patch() { return (unsigned)sizeof(Patch); }
 
