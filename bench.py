@@ -318,7 +318,9 @@ def main():
         stage /= nprof
         # ProcessHemicube alone on the k item buffers of a real batch
         ctx.restore_state()
-        ctx.select(); ctx.render()
+        _, k2_valid = ctx.select(); ctx.render()
+        lo = rank * k_rank if world > 1 else 0
+        k2_slots = int(np.count_nonzero(k2_valid[lo:lo + k_rank]))      # NULL emitters render nothing and are skipped by the kernel
         k2_ms = ctx.bench_process(20)
         # display stage: Colors::smoothShadePatch for every patch on the device
         ctx.upload_neighbours(scene.neighbours())
@@ -379,7 +381,7 @@ def main():
         if raster_mode == "tiles":      # opt-in tile-binned rasteriser: the stage slots hold other kernels
             roofline["note"] = ("RAD_RASTER=tiles: in `kernels`, queue_ms = bin_kernel x2 + bin_scan_kernel, 'process_hemicube (K2, fused key form)' = tile_kernel "
                                 "(visibility in shared memory + fused ProcessHemicube); atomic_roofline does not apply")
-        kk = k_rank                                      # item buffers one launch of this rank covers
+        kk = k2_slots                                    # item buffers one launch of this rank covers (non-NULL emitters only)
         k2_bytes = kk * 8.0 * RES + kk * 4.0 * P
         k2 = {"gpix_per_s": kk * RES / (k2_ms * 1e-3) / 1e9, "ms_per_launch": k2_ms, "pixels_per_launch": kk * RES,
               "achieved_gbs": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak_gbs": peak, "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak,

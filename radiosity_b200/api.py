@@ -91,7 +91,7 @@ def cuda_lib():
     """librad_cuda.so with typed signatures."""
     global _cuda
     if _cuda is None:
-        lib = _load("librad_cuda.so")
+        lib = _load(os.environ.get("RAD_CUDA_LIB", "librad_cuda.so"))   # (RAD_CUDA_LIB: A/B builds of the same library, scripts/ only)
         for name, (res, args) in CUDA_SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args

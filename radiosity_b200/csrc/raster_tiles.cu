@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(RadDev D, RadTiles T, int
 	if (b2 <= b0) {                                       // nothing was binned here: every pixel is empty, F gets nothing
 		if (keep_items)
 			for (int q = threadIdx.x; q < RAD_TILE_PIX / 4; q += blockDim.x) {
-				const int row = q >> 4, c4 = q & 15;
+				const int row = q / (RAD_TILE_W / 4), c4 = q % (RAD_TILE_W / 4);
 				if (4 * c4 < tw_ && row < th_) items4[((size_t)(ty0 + row) * D.W + tx0) / 4 + c4] = make_uint4(0u, 0u, 0u, 0u);
 			}
 		return;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(RadDev D, RadTiles T, int
 	#pragma unroll
 	for (int it = 0; it < kSteps; it++) {
 		const int q = it * THREADS + (int)threadIdx.x;
-		const int row = q >> 4, c4 = q & 15;
+		const int row = q / (RAD_TILE_W / 4), c4 = q % (RAD_TILE_W / 4);
 		const bool inb = 4 * c4 < tw_ && row < th_;
 		id[it] = make_uint4(0u, 0u, 0u, 0u); v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
 		if (inb) {

@@ -16,8 +16,12 @@
 #define RAD_HD inline
 #endif
 
+#ifndef RAD_TILE_W
 #define RAD_TILE_W 64             // a tile is RAD_TILE_W x RAD_TILE_H atlas pixels, its keys live in shared memory
+#endif
+#ifndef RAD_TILE_H
 #define RAD_TILE_H 32
+#endif
 #define RAD_TILE_PIX (RAD_TILE_W * RAD_TILE_H)
 
 namespace tw {
