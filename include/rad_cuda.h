@@ -117,7 +117,10 @@ int rad_process_hemicubes(rad_ctx* ctx);
 int rad_apply(rad_ctx* ctx, float* last_energy_len);
 
 /* the whole loop `for shoot < SHOOTS_PER_CYCLE` (Main.cpp:1137-1309), device resident: no host
- * round trip per shot.  stop_test != 0 honours the 0.1 termination (checked between graph replays). */
+ * round trip per shot.  stop_test != 0 honours the 0.1 termination exactly like the reference's loop condition
+ * (`&& computeRadiosity`, Main.cpp:1137,1297-1300): the batch whose last emitter had |B| < 0.1 is the last one applied —
+ * every state-changing kernel checks a device-side gate, so the batches a CUDA-graph replay still holds after it are
+ * no-ops; batches_done / shots_done count what was really shot.  The call starts with the test re-armed. */
 int rad_shoot(rad_ctx* ctx, uint32_t n_batches, int stop_test, rad_stats* out);
 
 /* device-side snapshot / restore of (B, I): restart a run from the same state with no host traffic */

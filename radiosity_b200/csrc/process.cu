@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kWarps * 32, FROM_KEYS ? 6 : 8) process_kernel
 	constexpr int kPxPiece = 16 / PXB;                                 // pixels per piece: 2 / 4
 	extern __shared__ __align__(128) unsigned char smem[];
 	if (FROM_KEYS && blockIdx.x == 0 && threadIdx.x == 0 && (D.qc->q_tris | D.qc->q_small | D.qc->n_pairs)) { D.qc->parked = D.qc->q_tris + D.qc->q_small; D.qc->q_tris = 0; D.qc->q_entries = 0; D.qc->q_small = 0; D.qc->n_pairs = 0; }
+	if (FROM_KEYS && D.stop_gate && D.ctl->gate) return;              // the stop test fired in an earlier batch of this replay
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t s_ff = smem_u32(smem), s_id = s_ff + kChunk * 4 + warp * Smem<PXB>::kWarp;
 	const uint32_t bar_id = s_ff + Smem<PXB>::kBars + warp * 8, bar_ff = s_ff + Smem<PXB>::kBars + kWarps * 8;

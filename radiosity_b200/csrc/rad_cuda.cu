@@ -72,7 +72,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->have_ff = c->have_scene = c->emitters_ready = c->rendered = c->processed = c->keys_dirty = false;
 	c->parity = 0; c->selkey_valid = false; c->cam_valid = false; c->have_nb = false;
 	c->graph_exec = nullptr; c->graph_batches = 0; c->graph_keep_items = false;
-	c->h_stage = nullptr; c->h_stage_bytes = 0; c->d_stage = nullptr; c->d_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0;
+	c->h_stage = nullptr; c->h_stage_bytes = 0; c->d_stage = nullptr; c->d_stage_bytes = 0; c->saved = nullptr; c->graph_launches = 0; c->graph_parity0 = 0; c->graph_stop = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr; c->partition_only = false;
 	c->peer_mode = false; c->xbuf = nullptr; c->xbuf_bytes = 0; for (int r = 0; r < RAD_MAX_PEERS; r++) c->peer_ptr[r] = nullptr;
 	c->launches = 0; c->epoch = 254; c->multi_graph = true;
@@ -280,7 +280,7 @@ int rad_upload_scene(rad_ctx* c, const float* verts12, const float* color3, cons
 	if (!c || !verts12 || !color3 || !rad3 || !illum3) return RAD_E_ARG;
 	if (P < 1 || P > c->cfg.max_patches) { c->err = "rad_upload_scene: P out of range (max_patches)"; return RAD_E_ARG; }
 	cudaSetDevice(c->cfg.device);
-	if (P != c->d.P) drop_graph(c);           // the captured launches carry P (nothing else of the scene)
+	if (P != c->d.P) { drop_graph(c); c->have_nb = false; }   // the captured launches carry P (nothing else of the scene); the neighbour planes are strided by P
 	int r = stage_dev(c, (size_t)P * 21 * 4); if (r) return r;
 	// staging layout (floats): [0, 12P) quads | [12P, 15P) colour | [15P, 21P) B, I
 	// 48-byte quad records -> three float4 streams (coalesced 16 B loads per lane in the rasteriser)
@@ -421,18 +421,29 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 	RadControl ctl0; if ((r = read_ctl(c, &ctl0))) return r;
 	c->launches = 0;
 	uint64_t launches = 0;
+	// stop test: every kernel that changes state checks a device-side gate, so a CUDA-graph replay ends with the batch
+	// whose |lastEnergy| < 0.1 fired, exactly like the reference's loop (Main.cpp:1137,1297-1300); the call starts armed and clean
+	c->d.stop_gate = stop_test ? 1u : 0u;
+	struct Disarm { rad_ctx* c; ~Disarm() { c->d.stop_gate = 0; } } disarm{ c };
+	if (stop_test) RAD_CUDA_TRY(c, cudaMemsetAsync(&c->d.ctl->stopped, 0, sizeof(uint32_t), c->stream));
+	if (stop_test) RAD_CUDA_TRY(c, cudaMemsetAsync(&c->d.ctl->gate, 0, sizeof(uint32_t), c->stream));
 	if (c->keys_dirty) rad_launch_clear_keys(c);
 	RAD_CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
 	uint32_t done = 0; bool stopped = false;
+	if (c->world > 1 && !c->nccl_comm && !c->peer_mode) {
+		c->err = "rad_shoot: this context only holds a partition (rad_set_partition) and no exchange (rad_comm_init / rad_peer_init): use rad_batch_partial / rad_read_delta / rad_write_delta / rad_batch_finish";
+		return RAD_E_STATE;
+	}
 	if (c->world > 1) {
 		// sharded batches: the same CUDA-graph replay as on one GPU, the ncclAllReduce of every batch captured inside it
 		// (RAD_MULTI_GRAPH=0 falls back to direct launches)
 		const uint32_t GB = 8;
 		if (c->multi_graph && (c->nccl_comm || c->peer_mode) && n_batches >= GB) {
-			if (!c->graph_exec || c->graph_batches != GB || c->graph_keep_items != keep) {
+			if (!c->graph_exec || c->graph_batches != GB || c->graph_keep_items != keep || c->graph_stop != c->d.stop_gate) {
 				drop_graph(c);
 				cudaGraph_t g = nullptr;
 				const uint32_t l0 = c->launches;
+				c->graph_stop = c->d.stop_gate;
 				RAD_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
 				rad_launch_clear_keys(c);
 				for (uint32_t b = 0; b < GB; b++) if ((r = enqueue_batch_multi(c, keep))) { cudaGraph_t junk; cudaStreamEndCapture(c->stream, &junk); return r; }
@@ -462,8 +473,9 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 		// steady state: a CUDA graph of GB batches (even, so that the k==1 key ping-pong returns to its start)
 		const uint32_t GB = 16;
 		if (n_batches >= GB) {
-			if (!c->graph_exec || c->graph_batches != GB || c->graph_keep_items != keep || c->graph_parity0 != c->parity) {
+			if (!c->graph_exec || c->graph_batches != GB || c->graph_keep_items != keep || c->graph_parity0 != c->parity || c->graph_stop != c->d.stop_gate) {
 				drop_graph(c);
+				c->graph_stop = c->d.stop_gate;
 				cudaGraph_t g = nullptr;
 				const uint32_t parity0 = c->parity; const bool sk0 = c->selkey_valid, cam0 = c->cam_valid; const uint32_t l0 = c->launches;
 				c->cam_valid = false;              // a replay starts with the camera kernel (it cannot know what ran before it)
@@ -498,6 +510,7 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 	if ((r = sync_check(c))) return r;
 	c->emitters_ready = c->rendered = c->processed = false;
 	RadControl ctl; if ((r = read_ctl(c, &ctl))) return r;
+	if (stop_test && ctl.stopped) { c->selkey_valid = false; c->cam_valid = false; }   // gated batches did not prepare the next shooter
 	if (out) {
 		out->batches_done = ctl.batches_done - ctl0.batches_done;
 		out->shots_done = ctl.shots_done - ctl0.shots_done;

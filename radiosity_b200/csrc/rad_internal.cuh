@@ -57,7 +57,8 @@ struct RadControl {               // small device-resident control block
 	float last_energy_len;
 	uint32_t batches_done;
 	uint32_t shots_done;
-	uint32_t pad;
+	uint32_t gate;                // stop test armed (RadDev::stop_gate) and `stopped` seen at the start of a batch: the rest of the
+	                              // replay is a no-op (the loop of Main.cpp:1137 ends with the batch that stopped)
 	RadQueueCtl lane[RAD_MAX_LANES];
 	uint32_t ticket;              // blocks finished ("last block merges" pattern of the selection / update kernels)
 	uint32_t pad2;
@@ -86,6 +87,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	uint32_t tag;                 // epoch tag (top byte of every key written / accepted by this launch)
 	uint32_t inline_area;         // bbox area (px) up to which the owning lane rasterises alone; larger -> chunk queue
 	uint32_t small_steps;         // longest quarter-warp walk (8 px per step) accepted by the small-quad queue
+	uint32_t stop_gate;           // rad_shoot(stop_test): batches enqueued after the one whose stop test fired do nothing (RadControl::gate)
 	uint32_t tile;                // chunk edge (px) of the chunk queue.  k == 1 is latency-bound (one hemicube cannot fill the
 	                              // GPU): shorter walks and smaller chunks there, longer ones for batches
 	float reflectivity;
@@ -151,7 +153,7 @@ struct rad_ctx {
 	bool selkey_valid;            // selkey[parity] holds the argmax of the current B
 	bool cam_valid;               // ... and the fused update's tail has already prepared that shooter's camera (k == 1)
 	// CUDA graph of the steady-state loop
-	cudaGraphExec_t graph_exec; uint32_t graph_batches; bool graph_keep_items; uint32_t graph_launches, graph_parity0;
+	cudaGraphExec_t graph_exec; uint32_t graph_batches; bool graph_keep_items; uint32_t graph_launches, graph_parity0, graph_stop;
 	float* saved;                 // device snapshot of (B, I) for rad_save_state / rad_restore_state
 	// host staging
 	float* h_stage; size_t h_stage_bytes;      // pinned

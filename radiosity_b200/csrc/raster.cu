@@ -31,6 +31,7 @@ namespace {
 // one block per hemicube slot: lanes 0..4 build the face matrices, lane 0 takes the snapshot (camera.cuh)
 __global__ void camera_kernel(RadDev D, int sel_parity) {
 	__shared__ RadEmitter s_e;
+	if (D.stop_gate && blockIdx.x == 0 && threadIdx.x == 0 && D.ctl->stopped) D.ctl->gate = 1;   // the previous batch was the last one (Main.cpp:1137,1298)
 	camera_block(D, blockIdx.x, sel_parity, &s_e);
 }
 
@@ -289,6 +290,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 __global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D) {
 	const uint32_t slot = D.h0 + blockIdx.z;
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (D.stop_gate && p == 0 && blockIdx.z == 0 && D.ctl->stopped) D.ctl->gate = 1;   // first raster kernel of a batch: latch the stop test (k == 1 has no camera kernel)
 	const bool live = p < D.P;
 	Quad q;
 	if (live) q = load_quad(D, p);
@@ -635,7 +637,7 @@ __global__ void queue_reset_kernel(RadDev D, int first_group) {
 // (see RadDev::tag), so nothing is ever cleared in the steady state.  Also recycles the queues.
 __global__ void __launch_bounds__(256) resolve_kernel(RadDev D) {
 	const uint32_t slot = D.h0 + blockIdx.y;
-	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.qc->q_tris | D.qc->q_small)) { D.qc->parked = D.qc->q_tris + D.qc->q_small; D.qc->q_tris = 0; D.qc->q_entries = 0; D.qc->q_small = 0; D.qc->n_pairs = 0; }
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.qc->q_tris | D.qc->q_small | D.qc->n_pairs)) { D.qc->parked = D.qc->q_tris + D.qc->q_small; D.qc->q_tris = 0; D.qc->q_entries = 0; D.qc->q_small = 0; D.qc->n_pairs = 0; }
 	const unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
 	uint32_t* __restrict__ items = D.items + (size_t)slot * D.RES;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < D.RES; i += gridDim.x * blockDim.x) {
@@ -785,9 +787,14 @@ void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::fu
 		g = queue_group(V);
 		const uint64_t cap = ((uint64_t)c->l2_group_mb << 20) / ((uint64_t)V.RES * 8ull);
 		if (cap >= 1 && cap < g) g = (uint32_t)cap;
+		if (g < (lane_slots + 253) / 254) g = (lane_slots + 253) / 254;   // at most 254 groups: one epoch tag each
 	}
 	uint32_t tags[RAD_MAX_HEMICUBES];
 	const uint32_t ngroups = (lane_slots + g - 1) / g;
+	// the groups of a batch recycle the same key buffers, so their tags must be strictly decreasing: if fewer tags are left
+	// than the batch has groups, start over from cleared keys (a wrap in the middle would hand a later group a LARGER tag
+	// and its keys would lose against the stale ones of an earlier group)
+	if (c->epoch < ngroups) rad_launch_clear_keys(c);
 	for (uint32_t j = 0; j < ngroups; j++) tags[j] = rad_next_tag(c);
 	if (L > 1) cudaEventRecord(c->ev_fork, c->stream);
 	for (uint32_t lane = 0; lane < L; lane++) {

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(RadDev D, RadTiles T, int
 	// last consumer of the lane's work lists: recycle them for the next launch group (as process_kernel does)
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.qc->q_tris | D.qc->q_small | D.qc->n_pairs)) { D.qc->parked = D.qc->q_tris + D.qc->q_small; D.qc->q_tris = 0; D.qc->q_entries = 0; D.qc->q_small = 0; D.qc->n_pairs = 0; }
 	if (!D.em[slot].valid) return;
+	if (D.stop_gate && D.ctl->gate) { if (threadIdx.x < 2) T.cnt[(ls * T.T + tile) * 2u + threadIdx.x] = 0u; return; }   // the stop test fired in an earlier batch of this replay
 	const uint32_t j = (ls * T.T + tile) * 2u;
 	const uint32_t b0 = T.base[j], b1 = T.base[j + 1], b2 = min(T.base[j + 2], T.refs_cap);
 	if (threadIdx.x < 2) T.cnt[j + threadIdx.x] = 0u;

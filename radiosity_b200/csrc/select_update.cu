@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	__shared__ int s_slot[256];            // first emitter slot of each patch of the current chunk (INT_MAX: none)
 	__shared__ int s_last_h, s_dups; __shared__ uint32_t s_nvalid;
 	const uint32_t P = D.P, k = D.k;
+	if (D.stop_gate && D.ctl->gate) return;     // the stop test fired in an earlier batch of this replay: the loop has ended (Main.cpp:1137)
 	if (threadIdx.x == 0) { s_last_h = -1; s_dups = 0; s_nvalid = 0; }
 	__syncthreads();
 	for (uint32_t h = threadIdx.x; h < k; h += blockDim.x) {
@@ -404,6 +405,7 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 // order, into its `red` region, and publishes the second flag; the update kernel then reads every slice from its owner
 // (2 (G-1)/G P values cross NVLink per rank instead of (G-1) P).
 __global__ void __launch_bounds__(256) xreduce_kernel(RadDev D) {
+	if (D.stop_gate && D.ctl->gate) return;
 	const uint32_t xseq = *reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]);
 	xb_wait(D, 128, xseq);
 	const uint32_t sz = xb_slice(D), lo = D.xrank * sz, hi = min(D.P, lo + sz);

@@ -15,6 +15,13 @@ struct Rec { float v[12], color[3], rad[3], illum[3]; uint32_t nb[8]; };
 struct Layout { size_t count_bytes, rec_bytes, off_rad, off_illum, off_rel, off_vec, off_color; };
 const Layout kWin32 = { 4, 148, 0, 12, 24, 24 + 32 + 8 * 4, 24 + 32 + 8 * 4 + 48 };
 const Layout kLP64 = { 8, 184, 0, 12, 24, 24 + 32 + 8 * 8, 24 + 32 + 8 * 8 + 48 };
+const Layout kWin64 = { 4, 184, 0, 12, 24, 24 + 32 + 8 * 8, 24 + 32 + 8 * 8 + 48 };   // LLP64: 8-byte pointers, 4-byte unsigned long count
+
+// does a file of `size` bytes hold exactly `count` records of layout L after its count field?  (count comes from the file:
+// derived from the size instead of multiplied, so that a crafted count cannot wrap the product)
+bool holds(uint64_t size, uint64_t hdr, uint64_t rec_bytes, uint64_t count) {
+	return size >= hdr && (size - hdr) % rec_bytes == 0 && (size - hdr) / rec_bytes == count;
+}
 
 void gather(ModelContainer& scene, std::vector<Rec>& out) {
 	const unsigned P = scene.getPatchesCount();
@@ -98,7 +105,7 @@ bool LoadFromFile(const std::string& path, ModelContainer& scene) {
 	if (size >= 16 && memcmp(&data[0], "RRB2", 4) == 0) {
 		uint32_t version; uint64_t count;
 		memcpy(&version, &data[4], 4); memcpy(&count, &data[8], 8);
-		if (version != 1 || (uint64_t)size != 16 + count * sizeof(Rec)) return false;
+		if (version != 1 || !holds((uint64_t)size, 16, sizeof(Rec), count)) return false;
 		recs.resize((size_t)count);
 		if (count) memcpy(&recs[0], &data[16], (size_t)count * sizeof(Rec));
 	} else {
@@ -106,8 +113,9 @@ bool LoadFromFile(const std::string& path, ModelContainer& scene) {
 		uint32_t c32 = 0; uint64_t c64 = 0;
 		if (size >= 4) memcpy(&c32, &data[0], 4);
 		if (size >= 8) memcpy(&c64, &data[0], 8);
-		if (size >= 8 && (uint64_t)size == 8 + c64 * kLP64.rec_bytes) { L = &kLP64; count = c64; }
-		else if (size >= 4 && (uint64_t)size == 4 + (uint64_t)c32 * kWin32.rec_bytes) { L = &kWin32; count = c32; }
+		if (size >= 8 && holds((uint64_t)size, 8, kLP64.rec_bytes, c64)) { L = &kLP64; count = c64; }
+		else if (size >= 4 && holds((uint64_t)size, 4, kWin32.rec_bytes, c32)) { L = &kWin32; count = c32; }
+		else if (size >= 4 && holds((uint64_t)size, 4, kWin64.rec_bytes, c32)) { L = &kWin64; count = c32; }
 		if (!L) return false;
 		recs.resize((size_t)count);
 		for (size_t i = 0; i < recs.size(); i++) {

@@ -18,7 +18,7 @@ extern "C" {
 void* radhost_scene_new() { return new ModelContainer(); }
 void radhost_scene_free(void* s) { delete (ModelContainer*)s; }
 void radhost_scene_load_cornell(void* s) { ((ModelContainer*)s)->load(); }
-int radhost_scene_load_obj(void* s, const char* path) { return ((ModelContainer*)s)->load(std::string(path)) ? 1 : 0; }
+int radhost_scene_load_obj(void* s, const char* path) { try { return ((ModelContainer*)s)->load(std::string(path)) ? 1 : 0; } catch (...) { return 0; } }
 int radhost_scene_load_static_mesh(void* s, const char* path, float scale, int flip, int emissive_material) {
 	return ((ModelContainer*)s)->loadStaticMesh(std::string(path), scale, flip != 0, emissive_material) ? 1 : 0;
 }
@@ -139,8 +139,9 @@ void radhost_scene_smooth_shade(void* sv, float* out12) {
 }
 int radhost_solver_shade(void* s, float* out12) { return ((RadiositySolver*)s)->shadeVertices(out12) ? 0 : -1; }
 
-int radhost_scene_save(void* s, const char* path, int format) { return SaveToFile(std::string(path), *(ModelContainer*)s, (RRFormat)format) ? 1 : 0; }
-int radhost_scene_load(void* s, const char* path) { return LoadFromFile(std::string(path), *(ModelContainer*)s) ? 1 : 0; }
+// (file contents are untrusted input: nothing may throw across the C ABI)
+int radhost_scene_save(void* s, const char* path, int format) { try { return SaveToFile(std::string(path), *(ModelContainer*)s, (RRFormat)format) ? 1 : 0; } catch (...) { return 0; } }
+int radhost_scene_load(void* s, const char* path) { try { return LoadFromFile(std::string(path), *(ModelContainer*)s) ? 1 : 0; } catch (...) { return 0; } }
 
 int radhost_scene_export_ply(void* s, const float* colors12, const char* path, float exposure) { return ExportPly(std::string(path), *(ModelContainer*)s, colors12, exposure) ? 1 : 0; }
 

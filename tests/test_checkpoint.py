@@ -57,6 +57,39 @@ def test_rejects_garbage(api, tmp_path):
     assert s.P == 502                                     # scene untouched
 
 
+def test_rejects_crafted_counts(api, tmp_path):
+    """a count field chosen so that count * record size wraps modulo 2^64 onto the file size must be refused, not allocated"""
+    import struct
+    s = api.Scene(0.5)
+    for name, blob in (
+            ("wrap_portable.rr", b"RRB2" + struct.pack("<IQ", 1, (1 << 64) // 104 + 1) + b"\0" * 8),      # 16 + count * 104 wraps
+            ("wrap_lp64.rr", struct.pack("<Q", ((1 << 64) + 184 * 2) // 184 + (1 << 61)) + b"\0" * 368),
+            ("short.rr", struct.pack("<Q", 3) + b"\0" * 184)):
+        p = tmp_path / name
+        p.write_bytes(blob)
+        try:
+            s.load(str(p))
+            assert False, name
+        except api.RadError:
+            pass
+        assert s.P == 502
+
+
+def test_reads_win64_layout(api, tmp_path):
+    """LLP64 dump of the reference (MSVC x64): 4-byte count, 184-byte records — same fields as the LP64 file"""
+    import struct
+    s = api.Scene(0.5)
+    lp = tmp_path / "lp64.rr"
+    s.save(str(lp), 2)
+    raw = lp.read_bytes()
+    (count,) = struct.unpack("<Q", raw[:8])
+    w = tmp_path / "win64.rr"
+    w.write_bytes(struct.pack("<I", count) + raw[8:])
+    t = api.Scene(0.5)
+    t.load(str(w))
+    assert t.P == s.P and _same(t.arrays(), s.arrays()) and (t.neighbours() == s.neighbours()).all()
+
+
 def test_live_exchange_with_reference_build(api, ref, tmp_path):
     """my LP64 file -> the reference's LoadingModel; the reference's dump -> my loader."""
     s = api.Scene(0.02)
