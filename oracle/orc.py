@@ -189,6 +189,42 @@ def shoot(verts, color, rad, illum, side, k, n_batches, select_mode=0, via_codec
     return rad, illum, sched, n, last.value
 
 
+def reference_tail_batches(area, rad, illum, side, k, n_batches):
+    """`n_batches` batches of the shooting loop with every host-side step on the reference's OWN code (oracle/_ref):
+    ModelContainer::getHighestRadiosityPatchesId for the emitters, the reference's kernel text for the record stream, and
+    the text of Main.cpp:1161,1251-1303 (snapshot, record gather, energy transfer, emitter update, stop test; refp_main_tail)
+    for the rest.  Only the item buffers come from the oracle's raster restatement (there is no GL here).
+    Returns (rad, illum, batches_done, last_energy_len, stopped); stops like Main.cpp:1137 when the stop test fires."""
+    R = ref()
+    P = int(R.refp_scene_build(ctypes.c_double(area)))
+    R.refp_main_tail.argtypes = [_u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]; R.refp_main_tail.restype = ctypes.c_int
+    R.refp_scene_get_state.argtypes = [_vp, _vp]
+    rad = np.ascontiguousarray(rad, np.float32); illum = np.ascontiguousarray(illum, np.float32)
+    R.refp_scene_set_radiosity(_ptr(rad)); R.refp_scene_set_illumination(_ptr(illum))
+    v = np.zeros((P, 12), np.float32)
+    R.refp_scene_get(_ptr(v), None, None, None, None)
+    ff = formfactors(side, k)
+    RES = 3 * side * side
+    last = ctypes.c_float(); done = 0; stopped = False
+    for _ in range(n_batches):
+        ids = np.zeros(k, np.uint32); nul = np.zeros(k, np.int32)
+        R.refp_select(k, _ptr(ids), _ptr(nul))
+        atlas = np.zeros(k * RES, np.uint32)
+        for h in range(k):
+            if not nul[h]:
+                atlas[h * RES:(h + 1) * RES] = render_hemicube(v, int(ids[h]), side).ravel()
+        rh, ri, re, nrec = process_cl_records(atlas, ff, side, P, hemicubes=k, reference_kernel=True)
+        rh = np.ascontiguousarray(rh); ri = np.ascontiguousarray(ri); re = np.ascontiguousarray(re)
+        go = R.refp_main_tail(k, _ptr(ids), _ptr(nul), int(nrec), _ptr(rh), _ptr(ri), _ptr(re), ctypes.byref(last))
+        done += 1
+        if not go:
+            stopped = True
+            break
+    out_r = np.zeros((P, 3), np.float32); out_i = np.zeros((P, 3), np.float32)
+    R.refp_scene_get_state(_ptr(out_r), _ptr(out_i))
+    return out_r, out_i, done, last.value, stopped
+
+
 def smooth_shade(color, rad, illum, nb8):
     color = np.ascontiguousarray(color, np.float32); rad = np.ascontiguousarray(rad, np.float32)
     illum = np.ascontiguousarray(illum, np.float32); nb8 = np.ascontiguousarray(nb8, np.int32)

@@ -68,6 +68,12 @@ for u in $UNITS; do
   g++ $CXXFLAGS -c "$TMP/src/$u.cpp" -o "$TMP/$u.o"
   OBJS="$OBJS $TMP/$u.o"
 done
+# the CPU tail of a batch (Main.cpp:1161, 1251-1279, 1284-1303) as TEXT for oracle/ref_probe.cpp's refp_main_tail: printed from
+# the reference's Main.cpp into the temp dir, profiling MARK lines dropped; Main.cpp itself cannot be compiled (Win32/GL/CL)
+sed -n '/p_tmp_radiosities\[hi\] = p_emitters\[hi\]->radiosity;/p' "$REF/Main.cpp" > "$TMP/src/main_tail_snapshot.inc"
+sed -n '/MARK("clEnqueueReleaseGLObjects");/,/MARK("energies update");/p' "$REF/Main.cpp" | sed -e '/MARK(/d' > "$TMP/src/main_tail_transfer.inc"
+sed -n '/Vector3f lastEnergy;/,/MARK("emitters update");/p' "$REF/Main.cpp" | sed -e '/MARK(/d' > "$TMP/src/main_tail_update.inc"
+for f in snapshot transfer update; do [ -s "$TMP/src/main_tail_$f.inc" ] || { echo "ref_build: could not extract main_tail_$f from Main.cpp" >&2; exit 1; }; done
 g++ $CXXFLAGS -c "$HERE/ref_probe.cpp" -o "$TMP/ref_probe.o"
 # the reference's OpenCL kernel TEXT (Kernel_ProcessHemicube.h), printed from the reference header into the temp dir and
 # compiled as C++ with the built-ins of oracle/ref_kernel.cpp; one syntactic fix: the vector literal (int2)(x, y)

@@ -220,4 +220,52 @@ unsigned refp_load_rr(const char* path) {
 
 unsigned refp_sizeof_patch() { return (unsigned)sizeof(Patch); }
 
+// ---- the CPU tail of a batch, run on the reference's OWN text ------------------------------------------------------
+// oracle/ref_build.sh prints three pieces of Main.cpp into its temp dir (nothing is copied into the repo):
+//   main_tail_snapshot.inc   the statement `p_tmp_radiosities[hi] = p_emitters[hi]->radiosity;`            (Main.cpp:1161)
+//   main_tail_transfer.inc   record gather into p_tmp_formfactors + energy transfer, per hemicube          (Main.cpp:1251-1279)
+//   main_tail_update.inc     emitter update, lastEnergy, stop test                                         (Main.cpp:1284-1303)
+// with the MARK(...) profiling lines dropped.  This function only declares the variables that text uses, under the
+// names Main.cpp gives them (Main.cpp:301,311,605-607,1115-1116,1140,1232), and runs it on the probe's scene.
+//   em_ids / em_null   the emitter list of the batch as getHighestRadiosityPatchesId returned it
+//   rec_*              the kernel's record stream (hemicube, patch id, energy), n_records = write index
+// Returns computeRadiosity (0 after the stop test fired); *last_len = lastEnergy.f_Length().
+#define MARK(x)
+int refp_main_tail(unsigned k, const unsigned* em_ids, const int* em_null, unsigned n_records,
+                   const unsigned* rec_hemicubes, const unsigned* rec_ids, const float* rec_energies, float* last_len) {
+	Config::frozen = false;
+	Config::setHemicubesCount(k);
+	Config::freeze();
+	ModelContainer& scene = *g_scene;
+	Patch** scenePatches = scene.getPatches();
+	unsigned int scenePatchesCount = scene.getPatchesCount();
+	std::vector<Patch*> emitters(k);
+	for (unsigned i = 0; i < k; i++) emitters[i] = em_null[i] ? NULL : scenePatches[em_ids[i]];
+	Patch** p_emitters = &emitters[0];
+	std::vector<Vector3f> tmp_radiosities(k);
+	Vector3f* p_tmp_radiosities = &tmp_radiosities[0];
+	std::vector<float> tmp_formfactors(scenePatchesCount, 0.0f);
+	float* p_tmp_formfactors = &tmp_formfactors[0];
+	const unsigned int* p_ocl_hemicubes = rec_hemicubes; const unsigned int* p_ocl_pids = rec_ids; const float* p_ocl_energies = rec_energies;
+	unsigned int n_last_index = n_records;
+	bool computeRadiosity = true, debugOutput = false;
+	unsigned int passCounter = 0, shoot = 0;
+	struct { double f_Time() const { return 0.0; } } timer; double t_start = 0.0;
+	std::streambuf* quiet = std::cout.rdbuf(NULL);          // the "Done in ..." line of the stop test
+	for (unsigned int hi = 0; hi < Config::HEMICUBES_CNT(); hi++) {
+		if (p_emitters[hi] == NULL) continue;               // Main.cpp:1157-1158
+#include "main_tail_snapshot.inc"
+	}
+	{
+#include "main_tail_transfer.inc"
+	}
+#include "main_tail_update.inc"
+	std::cout.rdbuf(quiet);
+	(void)passCounter; (void)shoot; (void)debugOutput; (void)t_start;
+	*last_len = lastEnergy.f_Length();
+	return computeRadiosity ? 1 : 0;
+}
+// patch state back out (after refp_main_tail)
+void refp_scene_get_state(float* rad3, float* illum3) { refp_scene_get(NULL, NULL, NULL, rad3, illum3); }
+
 } // extern "C"

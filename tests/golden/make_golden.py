@@ -51,6 +51,19 @@ def kernel_cases():
         yield f"runs5_P{P}_N{N}", runs.astype(np.uint32), orc.formfactors(N, 1), N, P, 1                          # runs that straddle the 4 work-item spans
 
 
+def tail_cases():
+    """(name, area, hemicube side, k, batches, initial radiosity, initial illumination): batches of the shooting loop whose
+    host side runs on the reference's own text (orc.reference_tail_batches)"""
+    v, c, r, il = orc.scene_cornell(0.5)
+    P = v.shape[0]
+    yield "fresh_k1_x6", 0.5, 32, 1, 6, r, il
+    yield "fresh_k4_x3", 0.5, 32, 4, 3, r, il
+    yield "fresh_k10_x2", 0.5, 32, 10, 2, r, il                                  # the reference's default `hemicubes 10`: 4 lights + NULL slots
+    yield "seeded_k7_x2", 0.5, 16, 7, 2, seeded_radiosity(P, 3), seeded_radiosity(P, 4)   # ties and zeros in the list
+    yield "stops_k4", 0.5, 32, 4, 10, (r * np.float32(0.06)).astype(np.float32), il   # the stop test fires at batch 4
+    yield "stops_k1", 0.5, 32, 1, 20, (r * np.float32(0.06)).astype(np.float32), il   # ... at batch 13
+
+
 def main():
     R = orc.ref()
     assert R is not None, "build oracle/_ref first (bash oracle/ref_build.sh)"
@@ -147,6 +160,13 @@ def main():
         h, ii, e, nrec = orc.process_cl_records(ids, ff, N, P, hemicubes=k, reference_kernel=True)
         ref["kernel"][name] = {"N": N, "P": P, "hemicubes": k, "records": int(nrec), "hemicubes_sha256": sha(h), "ids_sha256": sha(ii),
                                "energies_sha256": sha(e), "sum_energy": float(e.sum(dtype=np.float64))}
+
+    # ---- the CPU tail of the loop on the reference's own TEXT (Main.cpp:1161,1251-1303; oracle/ref_probe.cpp refp_main_tail) ----
+    ref["tail"] = {}
+    for name, area, N, k, nb, rad0, il0 in tail_cases():
+        rad, illum, done, last, stopped = orc.reference_tail_batches(area, rad0, il0, N, k, nb)
+        ref["tail"][name] = {"N": N, "k": k, "batches_asked": nb, "batches_done": int(done), "stopped": bool(stopped),
+                             "last_bits": int(np.float32(last).view(np.uint32)), "rad_sha256": sha(rad), "illum_sha256": sha(illum)}
 
     # ---- oracle regression (NOT reference outputs) ----
     reg = g["oracle_regression"]
