@@ -1,7 +1,7 @@
 # round 2 quick pass: GPU tests (optional, TESTS=1), then one short bench line per "NAME=VALUE[,NAME=VALUE...]" argument ("base" = no knob)
 mkdir -p gpurun_out
 if [ "${TESTS:-0}" = "1" ]; then timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8; fi
-run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps ${STEPS:-6} --warmup 3 --no-cpu-baseline ${WL:+--workload $WL} > gpurun_out/q_$tag.json 2> gpurun_out/q_$tag.err || tail -3 gpurun_out/q_$tag.err
+run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps ${STEPS:-6} --warmup 3 --no-cpu-baseline ${EXTRAS:---no-extras} ${WL:+--workload $WL} > gpurun_out/q_$tag.json 2> gpurun_out/q_$tag.err || tail -3 gpurun_out/q_$tag.err
 python - "$tag" <<'PY'
 import json,sys
 t=sys.argv[1]
