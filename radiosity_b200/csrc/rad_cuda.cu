@@ -737,6 +737,8 @@ int rad_peer_init(rad_ctx* c, int rank, int world, const void* handles /* world 
 	// one shot (every rank reads all peers' planes) while that is a few MB, two shots (reduce-scatter + all-gather) beyond
 	c->d.xtwo = (world > 2 && (uint64_t)c->cfg.max_patches * 12ull * (uint64_t)(world - 1) > (4ull << 20)) ? 1u : 0u;
 	if (const char* e = getenv("RAD_XTWO")) c->d.xtwo = atoi(e) != 0 ? 1u : 0u;   // tuning knob
+	c->d.xnowait = 0u;
+	if (const char* e = getenv("RAD_XNOWAIT")) c->d.xnowait = atoi(e) != 0 ? 1u : 0u;   // measurement knob (wrong results)
 	c->peer_mode = true;
 	int r = rad_set_partition(c, rank, world);
 	c->partition_only = false;

@@ -106,6 +106,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	// xb[r] = rank r's buffer as seen from this GPU (xb[xrank] is the local one); xworld == 0: not in use
 	char* xb[RAD_MAX_PEERS];
 	uint32_t xrank, xworld, xPmax;
+	uint32_t xnowait;             // measurement knob RAD_XNOWAIT=1: do not wait for the peers' flags (results are garbage; shows what the waiting costs)
 	uint32_t xtwo;                // two-shot exchange (reduce-scatter kernel + all-gather in the update kernel) for large P
 	float* mvp;                   // [k][5][16] column-major
 	RadEmitter* em;               // [k]

@@ -33,7 +33,7 @@ __device__ __forceinline__ float* xb_planes(const RadDev& D, uint32_t r, uint32_
 __device__ __forceinline__ float* xb_reduced(const RadDev& D, uint32_t r) { return reinterpret_cast<float*>(D.xb[r] + RAD_XB_DATA) + (size_t)6 * D.xPmax; }
 // spin until every rank's flag in row `row_off` of this rank's exchange buffer has reached seq (threads 0 .. world-1)
 __device__ __forceinline__ void xb_wait(const RadDev& D, uint32_t row_off, uint32_t seq) {
-	if (threadIdx.x < D.xworld) {
+	if (threadIdx.x < D.xworld && !D.xnowait) {
 		const uint32_t* flag = reinterpret_cast<const uint32_t*>(D.xb[D.xrank] + row_off + 128 * threadIdx.x);
 		while ((int32_t)(ld_acquire_sys(flag) - seq) < 0) { }
 	}
@@ -90,58 +90,97 @@ __global__ void __launch_bounds__(256) argmax_kernel(RadDev D, int parity) {
 }
 
 // ---- reference list semantics for k > 1 (single block) --------------------------------------
+// ModelContainer::getHighestRadiosityPatchesId (ModelContainer.cpp:259-299) scans the patches in id order and keeps a list:
+// a patch is appended if the list is empty, or if its energy is > 0 and >= the energy of the list's LAST entry; after every
+// append the list is stable-sorted ascending and reversed (so the newcomer leads its tie group and every other tie group
+// flips), then cut to `count`.  The result depends on the whole history (the seeded patch 0, candidates refused below the
+// minimum while the list is not full, tie groups flipped by later appends), so the scan is emulated as it is — but each
+// append is O(1) for a warp: the list lives in the registers of warp 0 (lane l holds entries l and l + 32), the insert
+// position is a ballot + popc, the shift a shuffle, and tie groups (rare) are flipped through 512 bytes of shared memory.
+// The other warps only compute energies and pre-filter candidates against the minimum at the start of their 1024-patch chunk
+// (the minimum never decreases: a superset), so the serial part sees a few hundred candidates per call, not P.
 __global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
 	__shared__ float s_e[1024];
 	__shared__ unsigned s_flags[32];
-	__shared__ uint32_t l_id[65]; __shared__ float l_e[65];
+	__shared__ float s_le[64]; __shared__ uint32_t s_lid[64];
 	__shared__ int s_n; __shared__ float s_min;
 	const uint32_t count = D.k;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	if (threadIdx.x == 0) { s_n = 0; s_min = 0.0f; }
+	// warp 0: the list.  entry i < 32 in (eA, idA) of lane i, entry i >= 32 in (eB, idB) of lane i - 32
+	float eA = 0.0f, eB = 0.0f; uint32_t idA = 0u, idB = 0u; int n = 0;
 	__syncthreads();
 	for (uint32_t base = 0; base < D.P; base += 1024) {
 		const uint32_t i = base + threadIdx.x;
 		const float e = i < D.P ? len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i]) : 0.0f;
 		s_e[threadIdx.x] = e;
-		// superset of the accepted candidates: the list minimum never decreases
 		const bool cand = i < D.P && ((s_n == 0 && i == 0) || (e > 0.0f && e >= s_min));
-		const unsigned b = __ballot_sync(FULL, cand);
-		if (lane == 0) s_flags[w] = b;
+		const unsigned bal = __ballot_sync(FULL, cand);
+		if (lane == 0) s_flags[w] = bal;
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			int n = s_n;
-			for (int ww = 0; ww < 32; ww++) {
-				unsigned m = s_flags[ww];
-				while (m) {
-					const int j = ww * 32 + __ffs(m) - 1;
-					m &= m - 1;
-					const float x = s_e[j];
-					if (!(n == 0 || (x > 0.0f && l_e[n - 1] <= x))) continue;
-					// every tie group is reversed by the stable-sort + reverse of the reference (ModelContainer.cpp:273-275)
-					for (int a = 0; a < n;) {
-						int z = a;
-						while (z + 1 < n && l_e[z + 1] == l_e[a]) z++;
-						for (int lo = a, hi = z; lo < hi; lo++, hi--) { const uint32_t t = l_id[lo]; l_id[lo] = l_id[hi]; l_id[hi] = t; }
-						a = z + 1;
+		if (w == 0) {
+			unsigned word = s_flags[lane];
+			for (;;) {
+				const unsigned any = __ballot_sync(FULL, word != 0u);
+				if (any == 0u) break;
+				const int ww = __ffs(any) - 1;                          // first warp-word with a candidate left
+				const unsigned m = __shfl_sync(FULL, word, ww);
+				const int j = ww * 32 + __ffs(m) - 1;
+				if (lane == ww) word &= word - 1u;
+				const float x = s_e[j];
+				const float last = n == 0 ? 0.0f : (n <= 32 ? __shfl_sync(FULL, eA, (n - 1) & 31) : __shfl_sync(FULL, eB, (n - 33) & 31));
+				if (!(n == 0 || (x > 0.0f && last <= x))) continue;     // ModelContainer.cpp:266-269
+				// every existing tie group is reversed by the stable sort + reverse (ModelContainer.cpp:273-275)
+				const bool vA = lane < n, vB = lane + 32 < n;
+				const float pA = __shfl_up_sync(FULL, eA, 1), pB0 = __shfl_sync(FULL, eA, 31), pBs = __shfl_up_sync(FULL, eB, 1);
+				const float pB = lane == 0 ? pB0 : pBs;
+				const unsigned hA = __ballot_sync(FULL, vA && (lane == 0 || eA != pA)), hB = __ballot_sync(FULL, vB && eB != pB);
+				const unsigned long long valid = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+				const unsigned long long heads = ((unsigned long long)hB << 32) | hA;
+				if (heads != valid) {                                   // some group has more than one member
+					s_le[lane] = eA; s_lid[lane] = idA; s_le[lane + 32] = eB; s_lid[lane + 32] = idB;
+					__syncwarp();
+					const unsigned long long hs = heads | (n >= 64 ? 0ull : (1ull << n));   // sentinel head behind the list
+					#pragma unroll
+					for (int half = 0; half < 2; half++) {
+						const int idx = lane + 32 * half;
+						if (idx < n) {
+							const int s0 = 63 - __clzll((long long)(heads & ((idx >= 63 ? ~0ull : ((2ull << idx) - 1ull)))));
+							const unsigned long long above = idx >= 63 ? 0ull : (hs >> (idx + 1));
+							const int t1 = above ? idx + __ffsll((long long)above) : n;      // first index of the next group
+							const int src = s0 + (t1 - 1) - idx;
+							if (half == 0) { eA = s_le[src]; idA = s_lid[src]; } else { eB = s_le[src]; idB = s_lid[src]; }
+						}
 					}
-					int pos = 0;
-					while (pos < n && l_e[pos] > x) pos++;      // the newcomer leads its tie group
-					for (int q = n; q > pos; q--) { l_id[q] = l_id[q - 1]; l_e[q] = l_e[q - 1]; }
-					l_id[pos] = base + j; l_e[pos] = x;
-					n++;
-					if (n > (int)count) n = (int)count;
+					__syncwarp();
 				}
+				// the newcomer leads its tie group: position = number of entries with a larger energy
+				const int pos = __popc(__ballot_sync(FULL, vA && eA > x)) + __popc(__ballot_sync(FULL, vB && eB > x));
+				const float sAe = __shfl_up_sync(FULL, eA, 1), sBe = __shfl_up_sync(FULL, eB, 1), cAe = __shfl_sync(FULL, eA, 31);
+				const uint32_t sAi = __shfl_up_sync(FULL, idA, 1), sBi = __shfl_up_sync(FULL, idB, 1), cAi = __shfl_sync(FULL, idA, 31);
+				if (lane > pos) { eA = sAe; idA = sAi; } else if (lane == pos) { eA = x; idA = base + (uint32_t)j; }
+				if (lane + 32 > pos) { eB = lane == 0 ? cAe : sBe; idB = lane == 0 ? cAi : sBi; } else if (lane + 32 == pos) { eB = x; idB = base + (uint32_t)j; }
+				n = min(n + 1, (int)count);                             // tops.erase(it, tops.end())
 			}
-			s_n = n;
-			s_min = n > 0 ? l_e[n - 1] : 0.0f;
+			if (lane == 0) {
+				s_n = n;
+			}
+			const float mn = n == 0 ? 0.0f : (n <= 32 ? __shfl_sync(FULL, eA, (n - 1) & 31) : __shfl_sync(FULL, eB, (n - 33) & 31));
+			if (lane == 0) s_min = mn;
 		}
 		__syncthreads();
 	}
-	if (threadIdx.x < count) {
-		const bool ok = (int)threadIdx.x < s_n;
-		D.em[threadIdx.x].id = ok ? l_id[threadIdx.x] : 0u;
-		D.em[threadIdx.x].valid = ok ? 1u : 0u;
-		D.em[threadIdx.x].order = threadIdx.x;
+	if (w == 0) {
+		#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			const uint32_t idx = (uint32_t)lane + 32u * half;
+			if (idx < count) {
+				const bool ok = (int)idx < n;
+				D.em[idx].id = ok ? (half ? idB : idA) : 0u;
+				D.em[idx].valid = ok ? 1u : 0u;
+				D.em[idx].order = idx;
+			}
+		}
 	}
 }
 
