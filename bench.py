@@ -543,32 +543,38 @@ def main():
         # stage times of one batch: [0] select+camera, [1] raster set-up, [2] raster queues, [4] fused ProcessHemicube, [5] apply
         # algorithmic bytes per launch: K3 12 B/patch; K1 48 B/patch/hemicube + 4 B/pixel (set-up + queue kernels together);
         # K2 8 B/pixel + 4 B/patch/hemicube (F); K4 36 B/patch + 4 B/patch/hemicube
-        stages = {"select+camera": (stage[0], 12.0 * P),
-                  "raster (K1: raster_setup + raster_queue)": (stage[1] + stage[2], nslots * (48.0 * P + 4.0 * RES)),
-                  "process_hemicube (K2, fused key form)": (stage[4], nslots * (8.0 * RES + 4.0 * P)),
-                  "apply_update (K4)": (stage[5], 36.0 * P + 4.0 * P * nslots)}
+        ring = stage[4] == 0 and stage[2] > 0           # ring path: walk + ProcessHemicube run in ONE kernel (raster_ring_kernel), timed together in [2]
+        k1n = "raster + process_hemicube (K1 + K2: raster_setup + raster_ring)" if ring else "raster (K1: raster_setup + raster_queue)"
+        stages = {"select+camera": (stage[0], 12.0 * P)}
+        if ring:
+            stages[k1n] = (stage[1] + stage[2], nslots * (48.0 * P + 4.0 * RES) + nslots * (8.0 * RES + 4.0 * P))
+        else:
+            stages[k1n] = (stage[1] + stage[2], nslots * (48.0 * P + 4.0 * RES))
+            stages["process_hemicube (K2, fused key form)"] = (stage[4], nslots * (8.0 * RES + 4.0 * P))
+        if world > 1:
+            stages["local dB + exchange (multi-GPU)"] = (stage[3], 12.0 * P + 4.0 * P * nslots)
+        stages["apply_update (K4)"] = (stage[5], 36.0 * P + (4.0 * P * nslots if world == 1 else 12.0 * P * world))
         total_stage = float(stage.sum())
         kern = {}
         for n_, (ms, b) in stages.items():
             kern[n_] = {"ms_per_batch": float(ms), "share": float(ms / total_stage), "algorithmic_bytes": b,
                         "achieved_gbs": float(b / (ms * 1e-3) / 1e9) if ms > 0 and b > 0 else None}
-        k1n = "raster (K1: raster_setup + raster_queue)"
         kern[k1n]["setup_ms"] = float(stage[1])
-        kern[k1n]["queue_ms"] = float(stage[2])
+        kern[k1n]["ring_ms" if ring else "queue_ms"] = float(stage[2])
         # every non-empty pixel needed at least one RED.MIN.64 (oracle statistics: 1.1 covered fragments per pixel on this scene)
         red_rate = nslots * RES / (float(stage[2]) * 1e-3) / 1e9 if stage[2] > 0 else 0.0
         kern[k1n]["red_rate"] = {
             "unit": "1e9 RED.MIN.64/s", "achieved_lower_bound": red_rate, "micro_benchmark": red_rate_ref, "ratio": red_rate / red_rate_ref if red_rate_ref else None,
             "key_footprint_mb": k * RES * 8 / 1e6,
-            "note": "NOT a roofline: micro_benchmark = rad_bench_atomics (quarter warps walking random 8x8 boxes of the same key buffers, no other work); the kernel's "
-                    "queue is roughly slot-ordered, so it can exceed that rate; achieved = atlas pixels of a batch / raster_queue time"}
+            "note": "NOT a roofline: micro_benchmark = rad_bench_atomics (quarter warps walking random 8x8 boxes over all k key buffers, no other work); "
+                    "achieved = atlas pixels of a batch / walk time" + (" (ring path: the walk shares the kernel with ProcessHemicube and its keys stay in a few L2-resident buffers)" if ring else "")}
         dom = max(kern, key=lambda n_: kern[n_]["ms_per_batch"])
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                traffic = tj.get(args.workload, {}).get(dom.split(" ")[0]) if world == 1 else None
+                traffic = tj.get(args.workload, {}).get("raster_ring" if ring else dom.split(" ")[0]) if world == 1 else None
                 traffic_src = tj.get("source")
             except Exception:
                 traffic = None
@@ -576,8 +582,8 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "traffic_source": (traffic_src or "none") + " — static: from the committed ncu capture of the same command, not measured in this run",
                     "peak_source": peak_src,
-                    "note": "the dominant kernel (K1 raster) is bound by instruction issue and the RED.MIN.64 path, not by HBM: its algorithmic bytes are tiny; "
-                            "the HBM-bound kernel of the path is K2 (ProcessHemicube), reported in process_hemicube against the same peak"}
+                    "note": "the dominant kernel (K1 raster walk, on the ring path fused with K2 in one launch) is bound by instruction issue and the RED.MIN.64 rate of L2, not by HBM: "
+                            "its algorithmic bytes are tiny; K2 (ProcessHemicube) alone is reported in process_hemicube against the same peak"}
         raster_mode = "tiles" if os.environ.get("RAD_RASTER") == "tiles" else "keys"
         if raster_mode == "tiles":      # opt-in tile-binned rasteriser: the stage slots hold other kernels
             roofline["note"] = ("RAD_RASTER=tiles: in `kernels`, queue_ms = bin_kernel x2 + bin_scan_kernel, 'process_hemicube (K2, fused key form)' = tile_kernel "
@@ -588,8 +594,9 @@ def main():
               "achieved_gbs": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak_gbs": peak, "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak,
               "dram_frac": (kk * 4.0 * RES) / (k2_ms * 1e-3) / 1e9 / peak,
               "algorithmic_bytes_per_pixel": 8, "itembuffer_bytes": kk * RES * 4,
-              "fused_form": {"ms_per_batch": float(stage[4]), "key_bytes": nslots * 8.0 * RES,
-                             "dram_frac": nslots * 8.0 * RES / (float(stage[4]) * 1e-3) / 1e9 / peak if stage[4] > 0 else None},
+              "fused_form": ({"ring": True, "note": "ring path: ProcessHemicube runs inside raster_ring_kernel on key buffers that stay in L2 (no HBM key traffic); see kernels"} if ring else
+                             {"ms_per_batch": float(stage[4]), "key_bytes": nslots * 8.0 * RES,
+                              "dram_frac": nslots * 8.0 * RES / (float(stage[4]) * 1e-3) / 1e9 / peak if stage[4] > 0 else None}),
               "note": "rad_bench_process: item buffers of a real batch (%.0f MB, %s L2), uint32 ids + the dFF table shared by all hemicubes.  frac counts SURVEY 8d's 8 B/pixel "
                       "(4 B id + 4 B dFF); the 3 MB dFF table stays in L2 (ncu: DRAM reads = the id bytes), so dram_frac counts 4 B/pixel: the share of the HBM peak this kernel really uses"
                       % (kk * RES * 4 / 1e6, "larger than" if kk * RES * 4 > 126e6 else "fits in")}
@@ -601,7 +608,7 @@ def main():
                 "data": "synthetic",
                 "config": config_dict(desc, P, N, k, "topk" if k > 1 else "reference"),
                 "run": {"batches_per_run": batches, "runs_per_step": runs, "shots_per_step": shots_timed // args.steps, "timed_region_s": ms_per_step * args.steps * 1e-3, "wall_s_incl_flush": wall,
-                        "raster": raster_mode,
+                        "raster": raster_mode + ("+ring" if ring else ""),
                         "parallelism": (f"{k_rank} of the batch's {k} shooters per rank, dB combined once per batch by " +
                                         ("the fused peer-memory update kernel (NVLink, CUDA IPC)" if B.exchange == "peer" else "ncclAllReduce") if world > 1 else "1gpu")},
                 "clocks": clocks,

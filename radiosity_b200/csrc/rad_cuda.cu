@@ -82,6 +82,12 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->ev_fork = nullptr; for (int l = 0; l < RAD_MAX_LANES; l++) { c->lane_stream[l] = nullptr; c->ev_lane[l] = nullptr; }
 	c->inline_area_forced = false; c->l2_group_mb = 1u << 20;   // default: the whole batch in one group (measured faster than L2-sized groups)
 	if (const char* e = getenv("RAD_L2_GROUP_MB")) { const int v = atoi(e); if (v >= 1) c->l2_group_mb = (uint32_t)v; }   // tuning knob
+	c->ring_failed = false;
+	c->ring_mode = false; c->ring_sg = c->ring_rs = c->ring_proc_layers = 0; c->ring_ctas_per_sm = 0;
+	if (const char* e = getenv("RAD_RING")) c->ring_mode = atoi(e) != 0;      // opt-in: L2-resident key ring (raster_ring_kernel; measured slower than the raster lanes)
+	if (const char* e = getenv("RAD_RING_SG")) { const int v = atoi(e); if (v >= 1 && v <= 16) c->ring_sg = (uint32_t)v; }     // tuning knobs
+	if (const char* e = getenv("RAD_RING_RS")) { const int v = atoi(e); if (v >= 2 && v <= 16) c->ring_rs = (uint32_t)v; }
+	if (const char* e = getenv("RAD_RING_PROC")) { const int v = atoi(e); if (v >= 1 && v <= 7) c->ring_proc_layers = (uint32_t)v; }
 	c->tile_mode = false; memset(&c->tl, 0, sizeof(c->tl));
 	if (const char* e = getenv("RAD_RASTER")) c->tile_mode = strcmp(e, "tiles") == 0;   // opt-in: tile-binned rasteriser (raster_tiles.cu)
 	RadDev& D = c->d;
@@ -126,7 +132,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(ff, (size_t)D.RES));
 	A(dalloc(D.keys, (size_t)D.k * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
 	A(dalloc(D.F, (size_t)D.k * Pm)); A(dalloc(D.dB, 3 * Pm));
-	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.emlite, 2 * (size_t)D.k)); A(dalloc(D.ctl, 1));
+	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.emlite, 2 * (size_t)D.k)); A(dalloc(D.ctl, 1)); A(dalloc(D.rc, 1));
 	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap)); A(dalloc(D.pairs, (size_t)D.pairs_cap)); A(dalloc(D.nb, 8 * Pm)); A(dalloc(D.shade_e, 3 * Pm));
 	A(dalloc(D.ework, Pm < RAD_MAX_HEMICUBES ? (size_t)RAD_MAX_HEMICUBES : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(proj, 16));
 	if (c->tile_mode) {
@@ -154,6 +160,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	cudaMemsetAsync(D.em, 0, (size_t)D.k * sizeof(RadEmitter), c->stream);
 	cudaMemsetAsync(D.emlite, 0, 2 * (size_t)D.k * sizeof(float4), c->stream);
 	cudaMemsetAsync(D.ctl, 0, sizeof(RadControl), c->stream);
+	cudaMemsetAsync(D.rc, 0, sizeof(RadRingCtl), c->stream);
 	if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete c; return RAD_E_CUDA; }
 	*out = c;
 	return RAD_OK;
@@ -174,7 +181,7 @@ int rad_destroy(rad_ctx* c) {
 	RadDev& D = c->d;
 	cudaFree((void*)D.v0); cudaFree((void*)D.v1); cudaFree((void*)D.v2); cudaFree((void*)D.color);
 	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
-	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.emlite); cudaFree(D.ctl);
+	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.emlite); cudaFree(D.ctl); cudaFree(D.rc);
 	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.pairs); cudaFree(D.nb); cudaFree(D.shade_e); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
 	if (c->tl.cnt) cudaFree(c->tl.cnt);
 	if (c->tl.base) cudaFree(c->tl.base);
@@ -523,6 +530,12 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 		out->queue_overflow = ctl.q_overflow;
 	}
 	if (ctl.q_overflow) { c->err = "rad_shoot: tile queue overflow"; return RAD_E_CUDA; }
+	if (ctl.ring_abort) {
+		cudaMemsetAsync(&c->d.ctl->ring_abort, 0, sizeof(uint32_t), c->stream);
+		c->err = "rad_shoot: the ring pipeline stalled (a stage hand-over inside raster_ring_kernel timed out); set RAD_RING=0 to use the lane path";
+		return RAD_E_CUDA;
+	}
+	if (c->ring_failed) { c->ring_failed = false; return RAD_E_CUDA; }      // the cooperative launch was refused (c->err says why)
 	return RAD_OK;
 }
 
@@ -611,7 +624,18 @@ int rad_profile_batch(rad_ctx* c, float* ms6) {
 	rad_launch_select(c); mark(0);
 	rad_launch_raster_process_marked(c, keep, [&](int st) { mark(st); });
 	const bool fuse = c->d.k == 1;
-	rad_launch_apply(c, fuse); mark(5);
+	if (c->world > 1 && (c->nccl_comm || c->peer_mode)) {
+		// sharded batch (collective: every rank profiles the same batch): [3] = local dB (+ the reduce-scatter kernel of the
+		// two-shot exchange / ncclAllReduce), [5] = the update kernel including its wait for the peers
+		rad_launch_delta(c);
+		if (c->peer_mode && c->d.xtwo) rad_launch_xreduce(c);
+		if (c->nccl_comm && !c->peer_mode) g_nccl.AllReduce(c->d.dB, c->d.dB, (size_t)3 * c->d.P, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream);
+		mark(3);
+		rad_launch_finish(c, false); mark(5);
+		c->selkey_valid = false;
+	} else {
+		rad_launch_apply(c, fuse); mark(5);
+	}
 	if (fuse) { c->parity ^= 1; c->selkey_valid = true; c->cam_valid = true; }
 	r = sync_check(c);
 	for (int i = 0; i < 6; i++) ms6[i] = 0.0f;

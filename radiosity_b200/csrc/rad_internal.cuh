@@ -42,6 +42,7 @@ struct __align__(16) RadSmallQuad {
 #define RAD_XB_DATA 4096           // byte offset of the dB planes inside an exchange buffer
 #define RAD_XB_FLAG2 2048          // byte offset of the second flag row (two-shot exchange: reduced slices ready)
 #define RAD_MAX_LANES 8            // concurrent raster lanes (streams) a batch can be split into
+#define RAD_RING_SLOTS 64          // hemicube slots one launch of the ring path renders (per-slot work lists, see RadRing)
 struct RadQueueCtl {              // work-list counters of one raster lane
 	uint32_t q_tris;              // chunk queue: triangles parked
 	uint32_t q_entries;           // chunk queue: (triangle, chunk) entries
@@ -61,7 +62,19 @@ struct RadControl {               // small device-resident control block
 	                              // replay is a no-op (the loop of Main.cpp:1137 ends with the batch that stopped)
 	RadQueueCtl lane[RAD_MAX_LANES];
 	uint32_t ticket;              // blocks finished ("last block merges" pattern of the selection / update kernels)
-	uint32_t pad2;
+	uint32_t ring_abort;          // ring path watchdog: a wait inside raster_ring_kernel timed out (never expected; the call fails instead of hanging)
+};
+// Ring path (RadRing): work-list counters per hemicube slot of the launch and the stage hand-over between walk and process
+// CTAs.  Zeroed before every launch (one memset node).  A stage's counter (CTAs that have finished it) and its ready flag
+// live on different 128-byte lines: the CTAs that wait poll the FLAG, so their loads never queue up in front of the
+// atomics of the CTAs that are still signalling.
+struct RadRingCtl {
+	RadQueueCtl slot[RAD_RING_SLOTS];
+	uint32_t walk_cnt[RAD_RING_SLOTS][32];
+	uint32_t proc_cnt[RAD_RING_SLOTS][32];
+	uint32_t walk_ready[RAD_RING_SLOTS][32];
+	uint32_t proc_ready[RAD_RING_SLOTS][32];
+	unsigned long long t_start, t_walk_end, t_proc_end, t_walk_wait, t_proc_wait;   // RAD_RING_DEBUG & 16: globaltimer stamps / summed wait time (ns)
 };
 
 struct RadEmitter {               // per hemicube slot
@@ -112,6 +125,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	RadEmitter* em;               // [k]
 	float4* emlite;               // [k][2] what the update kernel needs of an emitter: (S, valid | order << 1), (colour, id)
 	RadControl* ctl;
+	RadRingCtl* rc;               // ring path: per-slot work-list counters + stage hand-over (see RadRingCtl)
 	RadQueueCtl* qc;              // this launch's lane counters (= &ctl->lane[lane])
 	RadBigTri* q_tri; RadQueueEntry* q_ent;
 	uint32_t q_tri_cap, q_ent_cap;
@@ -122,6 +136,23 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	const float* proj;            // [16]
 	int32_t* nb;                  // [8][P] neighbour ids (display stage), plane j = neighbour j
 	float* shade_e;               // [3][P] colour (.) (I + B) scratch of the display stage
+};
+
+// Ring path of the steady state (raster.cu, raster_ring_kernel): the slots of a launch are rendered in STAGES of `sg` slots
+// through a ring of `rs` stages of key buffers (rs * sg buffers, sized to stay L2-resident).  One persistent kernel holds two
+// kinds of warps: walk warps rasterise the parked records of stage after stage into the ring, process warps follow one
+// stage behind and turn the finished key buffers into F (ProcessHemicube) — so a key is written by REDs that hit L2 and read
+// back from L2, and never crosses HBM.  The work lists are kept per slot (slot-ordered walks need them), the hand-over
+// between the two kinds of warps is a pair of counters per stage (RadControl::walk_done / proc_done).
+struct RadRing {
+	uint32_t nslots;              // slots of this launch: D.h0 .. D.h0 + nslots (<= RAD_RING_SLOTS)
+	uint32_t sg, rs, nst;         // slots per stage, stages in the ring, stages of this launch
+	uint32_t tag0;                // epoch tag of ring round 0; round r (stage / rs) writes tag0 - r
+	uint32_t cap_pairs, cap_sm, cap_tri, cap_ent;   // per-slot capacities of the four work lists
+	uint32_t walk_ctas;           // CTAs [0, walk_ctas) walk, the rest process
+	uint32_t nw_walk, nw_proc;    // warps of each kind
+	uint32_t keep_items;
+	uint32_t debug;               // measurement knob RAD_RING_DEBUG: 1 walk CTAs do not wait for the ring (results are garbage), 16 role time stamps (rad_profile_batch prints them)
 };
 
 // Tile-binned rasteriser (raster_tiles.cu; opt-in, RAD_RASTER=tiles): the atlas of every hemicube is cut into tiles of
@@ -166,6 +197,10 @@ struct rad_ctx {
 	uint32_t graph_epoch_after;   // epoch value after one replay of the captured graph
 	uint32_t epoch;               // next key epoch tag (254 .. 1, decreasing; 0 = clear the key buffers first)
 	bool inline_area_forced;      // RAD_INLINE_AREA set: do not auto-tune the inline tier
+	bool ring_mode;               // RAD_RING=1 (opt-in): steady state through the L2-resident key ring instead of raster lanes + whole-batch key buffers
+	uint32_t ring_sg, ring_rs, ring_proc_layers;   // tuning knobs (0 = automatic): RAD_RING_SG, RAD_RING_RS, RAD_RING_PROC
+	bool ring_failed;             // a raster_ring_kernel launch was refused since the last check
+	int ring_ctas_per_sm;         // resident CTAs per SM of raster_ring_kernel (occupancy query, once)
 	uint32_t l2_group_mb;         // key-buffer footprint (MB) of one hemicube group of the fused path
 };
 

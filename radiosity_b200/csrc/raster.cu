@@ -23,8 +23,11 @@
 // inside vertex; iw = 1/w, xw = (x*iw)*(N/2) + (vx+N/2); RNE snap to 1/256 px; keep signed area > 0 (CCW front,
 // GL_CULL_FACE back); pixel centres, exact int64 edge functions, top-left tie rule; depth =
 // barycentric interpolation of (z*iw)*0.5+0.5, RNE-quantised to 24 bit, d >= 0xFFFFFF fails (LESS vs 1.0).
+#include <stdio.h>
+#include <stdlib.h>
 #include "rad_internal.cuh"
 #include "camera.cuh"
+#include "segadd.cuh"
 
 namespace {
 
@@ -178,17 +181,31 @@ __device__ __forceinline__ SmallRec make_small(int X0, int Y0, int X1, int Y1, i
 }
 __device__ __forceinline__ int radius_about(int cx, int cy, int X, int Y) { return max(abs(X - cx), abs(Y - cy)); }
 
+// The work lists a set-up warp appends to: the lane's share of the context's lists (RadDev::qc ...) or, on the ring path,
+// the lists of ONE hemicube slot (all pairs of a warp step belong to the same slot there).
+struct QV { RadQueueCtl* qc; RadBigTri* q_tri; RadQueueEntry* q_ent; RadSmallQuad* q_sm; uint32_t q_tri_cap, q_ent_cap, q_sm_cap; };
+__device__ __forceinline__ QV qv_lane(const RadDev& D) {
+	QV q; q.qc = D.qc; q.q_tri = D.q_tri; q.q_ent = D.q_ent; q.q_sm = D.q_sm; q.q_tri_cap = D.q_tri_cap; q.q_ent_cap = D.q_ent_cap; q.q_sm_cap = D.q_sm_cap;
+	return q;
+}
+__device__ __forceinline__ QV qv_slot(const RadDev& D, const RadRing& R, uint32_t sl) {
+	QV q; q.qc = &D.rc->slot[sl];
+	q.q_tri = D.q_tri + (size_t)sl * R.cap_tri; q.q_ent = D.q_ent + (size_t)sl * R.cap_ent; q.q_sm = D.q_sm + (size_t)sl * R.cap_sm;
+	q.q_tri_cap = R.cap_tri; q.q_ent_cap = R.cap_ent; q.q_sm_cap = R.cap_sm;
+	return q;
+}
+
 // Warp-collective append to the small-quad queue: ONE atomic per warp.
-__device__ __forceinline__ void push_small(const RadDev& D, bool take, const SmallRec& r, int lane) {
+__device__ __forceinline__ void push_small(const RadDev& D, const QV& Q, bool take, const SmallRec& r, int lane) {
 	const unsigned ms = __ballot_sync(FULL, take);
 	if (ms == 0) return;
 	uint32_t sbase = 0;
-	if (lane == 0) sbase = atomicAdd(&D.qc->q_small, (uint32_t)__popc(ms));
+	if (lane == 0) sbase = atomicAdd(&Q.qc->q_small, (uint32_t)__popc(ms));
 	sbase = __shfl_sync(FULL, sbase, 0);
 	if (take) {
 		const uint32_t si = sbase + __popc(ms & ((1u << lane) - 1u));
-		if (si < D.q_sm_cap) {
-			uint4* dst = reinterpret_cast<uint4*>(D.q_sm + si);
+		if (si < Q.q_sm_cap) {
+			uint4* dst = reinterpret_cast<uint4*>(Q.q_sm + si);
 			dst[0] = r.a; dst[1] = r.b; dst[2] = r.c; dst[3] = r.d;
 		} else D.ctl->q_overflow = 1;
 	}
@@ -196,7 +213,7 @@ __device__ __forceinline__ void push_small(const RadDev& D, bool take, const Sma
 
 // Both triangles of an unclipped, front-facing patch whose common bbox is small: parked as ONE record, walked once.
 // Returns true when the quad was taken (the caller then skips its two triangles).
-__device__ __forceinline__ bool emit_quad(const RadDev& D, const Tri& ta, const Tri& tb, int areaA, int areaB, int X3, int Y3, float Z3,
+__device__ __forceinline__ bool emit_quad(const RadDev& D, const QV& Q, const Tri& ta, const Tri& tb, int areaA, int areaB, int X3, int Y3, float Z3,
                                           uint32_t id1, uint32_t slot, int lane) {
 	bool take = false;
 	int px0 = 0, py0 = 0, bw = 1, bh = 1;
@@ -212,7 +229,7 @@ __device__ __forceinline__ bool emit_quad(const RadDev& D, const Tri& ta, const 
 	if (!__any_sync(FULL, take)) return false;
 	SmallRec r;
 	if (take) r = make_small(ta.X0, ta.Y0, ta.X1, ta.Y1, ta.X2, ta.Y2, X3, Y3, ta.z0, ta.z1, ta.z2, Z3, ta.inv_area, tb.inv_area, id1, slot, px0, py0, bw, bh);
-	push_small(D, take, r, lane);
+	push_small(D, Q, take, r, lane);
 	return take;
 }
 
@@ -220,7 +237,7 @@ __device__ __forceinline__ bool emit_quad(const RadDev& D, const Tri& ta, const 
 // short int32-safe walks in the small-quad queue (as a quad whose second triangle is degenerate), the rest in the chunk
 // queue — bbox-relative chunks of tile x tile pixels (RadDev::tile), one warp each in raster_queue_kernel — so that no warp of
 // the set-up kernel ever carries a long pixel loop (load balance).  Queue slots are claimed with one atomic per warp.
-__device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
+__device__ __forceinline__ void emit_tri(const RadDev& D, const QV& Q, const Tri& tr, int area, uint32_t id1, uint32_t slot, int lane,
                                          unsigned long long* __restrict__ keys) {
 	const uint32_t tagsh = D.tag << 24;
 	const int bw = (tr.bx >> 16) - (tr.bx & 0xFFFF) + 1, bh = (tr.by >> 16) - (tr.by & 0xFFFF) + 1;
@@ -246,7 +263,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 		SmallRec q;
 		if (small) q = make_small(tr.X0, tr.Y0, tr.X1, tr.Y1, tr.X2, tr.Y2, tr.X0, tr.Y0, tr.z0, tr.z1, tr.z2, tr.z0, tr.inv_area, 0.0f,
 		                          id1, slot, tr.bx & 0xFFFF, tr.by & 0xFFFF, bw, bh);
-		push_small(D, small, q, lane);
+		push_small(D, Q, small, q, lane);
 	}
 	if (mb == 0) return;
 	RadBigTri r;
@@ -263,17 +280,17 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, pre, d); if (lane >= d) pre += o; }
 	const int total = __shfl_sync(FULL, pre, 31);
 	uint32_t tbase = 0, ebase = 0;
-	if (lane == 0) { tbase = atomicAdd(&D.qc->q_tris, (uint32_t)__popc(mb)); ebase = atomicAdd(&D.qc->q_entries, (uint32_t)total); }
+	if (lane == 0) { tbase = atomicAdd(&Q.qc->q_tris, (uint32_t)__popc(mb)); ebase = atomicAdd(&Q.qc->q_entries, (uint32_t)total); }
 	tbase = __shfl_sync(FULL, tbase, 0); ebase = __shfl_sync(FULL, ebase, 0);
 	if (!big) return;
 	const uint32_t ti = tbase + __popc(mb & ((1u << lane) - 1u));
 	uint32_t e = ebase + (uint32_t)(pre - nent);
-	if (ti >= D.q_tri_cap || e + nent > D.q_ent_cap) { D.ctl->q_overflow = 1; return; }
-	D.q_tri[ti] = r;
+	if (ti >= Q.q_tri_cap || e + nent > Q.q_ent_cap) { D.ctl->q_overflow = 1; return; }
+	Q.q_tri[ti] = r;
 	for (int cy = 0; cy < ncy; cy++)
 		for (int cx = 0; cx < ncx; cx++) {
 			RadQueueEntry q; q.tri = ti; q.tx = (uint16_t)cx; q.ty = (uint16_t)cy;
-			D.q_ent[e++] = q;
+			Q.q_ent[e++] = q;
 		}
 }
 
@@ -287,7 +304,9 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const Tri& tr, int are
 // The frusta are evaluated in the shooter's orthonormal frame (s = n x u, t = u, f = n; Camera.cpp:19-52): FRONT looks
 // along +f, UP/DOWN along +-t, LEFT/RIGHT along +-s, and the scissored half of every side face is the f >= 0 half.
 // grid: x = patch chunk, z = local hemicube slot
-__global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D) {
+// SL (ring path): the pairs of every slot go to the slot's own list (RadControl::slot[z].n_pairs, z-th share of D.pairs)
+template <bool SL>
+__global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D, RadRing R) {
 	const uint32_t slot = D.h0 + blockIdx.z;
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (D.stop_gate && p == 0 && blockIdx.z == 0 && D.ctl->stopped) D.ctl->gate = 1;   // first raster kernel of a batch: latch the stop test (k == 1 has no camera kernel)
@@ -340,12 +359,13 @@ __global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D) {
 	for (int f = 0; f < RAD_NFACES; f++) { mf[f] = __ballot_sync(FULL, (faces >> f) & 1u); total += __popc(mf[f]); }
 	if (total == 0) return;
 	uint32_t base = 0;
-	if (lane == 0) base = atomicAdd(&D.qc->n_pairs, (uint32_t)total);
+	if (lane == 0) base = atomicAdd(SL ? &D.rc->slot[blockIdx.z].n_pairs : &D.qc->n_pairs, (uint32_t)total);
 	base = __shfl_sync(FULL, base, 0);
-	if (base + total > D.pairs_cap) { if (lane == 0) D.ctl->q_overflow = 1; return; }
+	if (base + total > (SL ? R.cap_pairs : D.pairs_cap)) { if (lane == 0) D.ctl->q_overflow = 1; return; }
+	uint32_t* __restrict__ list = SL ? D.pairs + (size_t)blockIdx.z * R.cap_pairs : D.pairs;
 	#pragma unroll
 	for (int f = 0; f < RAD_NFACES; f++) {
-		if ((faces >> f) & 1u) D.pairs[base + __popc(mf[f] & ((1u << lane) - 1u))] = p | ((uint32_t)f << 23) | ((slot - D.h0) << 26);
+		if ((faces >> f) & 1u) list[base + __popc(mf[f] & ((1u << lane) - 1u))] = p | ((uint32_t)f << 23) | ((slot - D.h0) << 26);
 		base += __popc(mf[f]);
 	}
 }
@@ -403,17 +423,11 @@ __device__ __noinline__ int clip_tri(const float4* __restrict__ v0, const float4
 	return setup_tri(a, b, cc, fw.scx, fw.scy, fw.scw, fw.sch, *out);
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
-	const uint32_t npairs = min(D.qc->n_pairs, D.pairs_cap);
-	const int lane = threadIdx.x & 31;
+// one warp step of the exact stage: pair e per lane (live: the lane has one), records appended to the lists Q
+__device__ __forceinline__ void setup_pairs(const RadDev& D, const QV& Q, uint32_t e, bool live, int lane) {
 	const int N = (int)D.N;
 	const float hw = (float)N * 0.5f;
-	const uint32_t stride = gridDim.x * blockDim.x;
-	for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < npairs; i0 += stride) {
-		const uint32_t i = i0 + lane;
-		const bool live = i < npairs;
-		const uint32_t e = live ? D.pairs[i] : 0u;
+	{
 		const uint32_t p = e & 0x7FFFFFu, slot = D.h0 + (e >> 26);
 		const int f = (int)((e >> 23) & 7u);
 		const FaceWin fw = face_window(f, N);
@@ -437,7 +451,7 @@ __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 				for (int k = 0; k < 4; k++) pv[k] = project(c[k], hw, fw.ox, fw.oy);
 			}
 		}
-		if (!__any_sync(FULL, nin > 0)) continue;
+		if (!__any_sync(FULL, nin > 0)) return;
 		unsigned long long* __restrict__ keys = D.keys + (size_t)(slot - D.kbase) * D.RES;
 		const uint32_t id1 = p + 1;
 		const bool clipped = nin > 0 && nin < 4;
@@ -447,15 +461,57 @@ __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D) {
 			areaA = setup_tri(pv[0], pv[1], pv[2], fw.scx, fw.scy, fw.scw, fw.sch, trA);
 			areaB = setup_tri(pv[0], pv[2], pv[3], fw.scx, fw.scy, fw.scw, fw.sch, trB);
 		}
-		if (emit_quad(D, trA, trB, areaA, areaB, pv[3].X, pv[3].Y, pv[3].Z, id1, slot, lane)) { areaA = 0; areaB = 0; }
+		if (emit_quad(D, Q, trA, trB, areaA, areaB, pv[3].X, pv[3].Y, pv[3].Z, id1, slot, lane)) { areaA = 0; areaB = 0; }
 		// triangles (0,1,2) and (0,2,3) (ModelContainer.cpp:112-117) on their own, then — rare — the clipped fans
 		const int nt = __any_sync(FULL, clipped) ? 6 : 2;
 		#pragma unroll 1
 		for (int t = 0; t < nt; t++) {
 			Tri tr = t ? trB : trA; int area = t == 0 ? areaA : (t == 1 ? areaB : 0);
 			if (t >= 2 && clipped) { Tri ct; area = clip_tri(D.v0, D.v1, D.v2, D.mvp, D.h0, N, e, (t - 2) >> 1, (t - 2) & 1, &ct); if (area > 0) tr = ct; }
-			if (__any_sync(FULL, area > 0)) emit_tri(D, tr, area, id1, slot, lane, keys);
+			if (__any_sync(FULL, area > 0)) emit_tri(D, Q, tr, area, id1, slot, lane, keys);
 		}
+	}
+}
+
+// SL (ring path): the pair lists are per slot; a warp step takes 32 consecutive pairs of ONE slot and appends to that slot's
+// work lists.  s_wbase = first warp step of every slot (running sum of ceil(pairs / 32)).
+template <int MINB, bool SL>
+__global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D, RadRing R) {
+	const int lane = threadIdx.x & 31;
+	if (!SL) {
+		const uint32_t npairs = min(D.qc->n_pairs, D.pairs_cap);
+		const uint32_t stride = gridDim.x * blockDim.x;
+		const QV Q = qv_lane(D);
+		for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < npairs; i0 += stride) {
+			const uint32_t i = i0 + lane;
+			const bool live = i < npairs;
+			setup_pairs(D, Q, live ? D.pairs[i] : 0u, live, lane);
+		}
+		return;
+	}
+	__shared__ uint32_t s_wbase[RAD_RING_SLOTS + 1];
+	if (threadIdx.x < 32) {                        // warp 0: scan of the slots' warp-step counts (two slots per lane)
+		const uint32_t a = 2u * lane, b = a + 1u;
+		const uint32_t na = a < R.nslots ? (min(D.rc->slot[a].n_pairs, R.cap_pairs) + 31u) >> 5 : 0u;
+		const uint32_t nb = b < R.nslots ? (min(D.rc->slot[b].n_pairs, R.cap_pairs) + 31u) >> 5 : 0u;
+		uint32_t incl = na + nb;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+		s_wbase[a] = incl - na - nb; s_wbase[b] = incl - nb;
+		if (lane == 31) s_wbase[RAD_RING_SLOTS] = incl;
+	}
+	__syncthreads();
+	const uint32_t total = s_wbase[RAD_RING_SLOTS];
+	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t w = gw; w < total; w += nw) {
+		uint32_t sl = 0;                           // last slot whose first warp step is <= w
+		#pragma unroll
+		for (uint32_t d = RAD_RING_SLOTS / 2; d > 0; d >>= 1) if (sl + d < R.nslots && s_wbase[sl + d] <= w) sl += d;
+		const uint32_t npairs = min(D.rc->slot[sl].n_pairs, R.cap_pairs);
+		const uint32_t i = ((w - s_wbase[sl]) << 5) + lane;
+		const bool live = i < npairs;
+		const QV Q = qv_slot(D, R, sl);
+		setup_pairs(D, Q, live ? D.pairs[(size_t)sl * R.cap_pairs + i] : 0u, live, lane);
 	}
 }
 
@@ -468,161 +524,276 @@ __device__ __forceinline__ void edge_origin(int ax, int ay, int bx, int by, int&
 	sx = -dy * 256; sy = dx * 256;
 }
 
-// persistent warps drain both queues.
-//  1. small-quad queue: FOUR records per warp step, one quarter warp (8 lanes) each.  A record holds both triangles of a
+// The two walks of the parked records, shared by raster_queue_kernel (whole-batch key buffers) and raster_ring_kernel (ring).
+//  1. small quads: FOUR records per warp step, one quarter warp (8 lanes) each.  A record holds both triangles of a
 //     patch, A = (0,1,2) and B = (0,2,3); the common bbox is walked ONCE as one linear run of w * ceil(h/2) two-row
 //     columns, 8 per step (16 pixels per quarter warp and step),
 //     with the five distinct int32 edge functions (the diagonal is shared: B's edge (0->2) is minus A's edge (2->0)).
 //     A pixel belongs to A or to B (never both: they lie on opposite sides of the diagonal and the top-left rule gives
 //     the diagonal itself to exactly one) and takes its depth from that triangle's plane — the same integers and the
 //     same float operations as two separate triangle walks, in about half the pixel visits;
-//  2. chunk queue: one warp per (triangle, chunk) of at most tile x tile pixels, 8x4 pixels per step.
-// PF (opt-in, RAD_QUEUE_PREFETCH=1): the four records of a warp's NEXT step are fetched into shared memory with cp.async
-// while the current ones are walked (no registers held across the walk), for the ~20 % of the stall samples that wait for
-// the record load.  Not measured yet.
-template <bool PF>
+//  2. chunks: one warp per (triangle, chunk) of at most tile x tile pixels, 8x4 pixels per step.
+// RING: every record of the list belongs to the slot whose key buffer is `ring_keys`; otherwise the record names its slot.
+// (Measured and dropped: the next step's records fetched into shared memory with cp.async during the walk — the walk got
+// slower, 0.371 against 0.331 ms per batch.)
+template <bool RING>
+__device__ __forceinline__ void walk_small4(const RadDev& D, const uint4* __restrict__ qsm, uint32_t base, uint32_t nsm,
+                                            unsigned long long* __restrict__ ring_keys, uint32_t tagsh, int lane) {
+	const int sub = lane >> 3, l8 = lane & 7;
+	const int W = (int)D.W;
+	const uint32_t i = base + sub;
+	int npx = 0, w8 = 1, hh = 0, q8 = 0, r8 = 0, x = 0, y = 0;
+	int a0y2 = 0, a1y2 = 0, a2y2 = 0, b0y2 = 0, b1y2 = 0;
+	int a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0;                         // biased edge values at the bbox origin
+	int a0x = 0, a1x = 0, a2x = 0, b0x = 0, b1x = 0, a0y = 0, a1y = 0, a2y = 0, b0y = 0, b1y = 0;
+	int bA1 = 0, bA2 = 0, bB1 = 0, bB2 = 0;
+	float Z0 = 0, dA1 = 0, dA2 = 0, dB2 = 0, invA = 0, invB = 0;
+	uint32_t id1 = 0; unsigned long long* kp = nullptr;
+	if (i < nsm) {
+		const uint4 r0 = __ldg(qsm + 4 * (size_t)i), r1 = __ldg(qsm + 4 * (size_t)i + 1), r2 = __ldg(qsm + 4 * (size_t)i + 2);
+		const uint2 r3 = __ldg(reinterpret_cast<const uint2*>(qsm + 4 * (size_t)i + 3));
+		const int x0 = (int)(r0.x << 16) >> 16, y0 = (int)r0.x >> 16, x1 = (int)(r0.y << 16) >> 16, y1 = (int)r0.y >> 16;
+		const int x2 = (int)(r0.z << 16) >> 16, y2 = (int)r0.z >> 16, x3 = (int)(r0.w << 16) >> 16, y3 = (int)r0.w >> 16;
+		int bA0, bB0;
+		edge_origin(x1, y1, x2, y2, a0, a0x, a0y, bA0);      // A: edges (1->2), (2->0), (0->1)
+		edge_origin(x2, y2, x0, y0, a1, a1x, a1y, bA1);
+		edge_origin(x0, y0, x1, y1, a2, a2x, a2y, bA2);
+		edge_origin(x2, y2, x3, y3, b0, b0x, b0y, bB0);      // B: edges (2->3), (3->0), (0->2)
+		edge_origin(x3, y3, x0, y0, b1, b1x, b1y, bB1);
+		{ const int dx = x2 - x0, dy = y2 - y0; bB2 = (dy < 0 || (dy == 0 && dx < 0)) ? 0 : -1; }
+		Z0 = __uint_as_float(r1.x);
+		dA1 = __uint_as_float(r1.y) - Z0; dA2 = __uint_as_float(r1.z) - Z0; dB2 = __uint_as_float(r1.w) - Z0;
+		invA = __uint_as_float(r2.x); invB = __uint_as_float(r2.y);
+		id1 = r2.z;
+		const uint32_t slot = r2.w & 0xFFFFu, rcpw = r2.w >> 16;
+		const int px0 = (int)(r3.x & 0xFFFFu), py0 = (int)(r3.x >> 16);
+		w8 = (int)(r3.y & 0xFFu);
+		hh = (int)((r3.y >> 8) & 0xFFu);
+		npx = w8 * ((hh + 1) >> 1);                               // positions of the walk: every one is a column of TWO rows
+		q8 = (int)((8u * rcpw) >> 15); r8 = 8 - q8 * w8;          // 8 / w, 8 % w
+		y = (int)(((uint32_t)l8 * rcpw) >> 15); x = l8 - y * w8;   // this lane's first position (y counts row pairs)
+		kp = (RING ? ring_keys : D.keys + (size_t)(slot - D.kbase) * D.RES) + (size_t)py0 * D.W + px0;
+		a0y2 = 2 * a0y; a1y2 = 2 * a1y; a2y2 = 2 * a2y; b0y2 = 2 * b0y; b1y2 = 2 * b1y;
+	}
+	int msteps = (npx + 7) >> 3;
+	msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 8)); msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 16));
+	int idx = l8;
+	// one covered-pixel test + depth + RED; the unbiased A edge (2->0) is minus B's edge (0->2)
+	auto pixel = [&](int e0, int e1, int e2, int f0, int f1, int off) {
+		const int e1u = e1 - bA1;
+		const int f2 = bB2 - e1u;
+		const bool inA = (e0 | e1 | e2) >= 0, inB = (f0 | f1 | f2) >= 0;
+		if (inA || inB) {
+			const float inv = inA ? invA : invB;
+			const float l1 = (float)(inA ? e1u : f1 - bB1) * inv, l2 = (float)(inA ? e2 - bA2 : -e1u) * inv;
+			float z = (Z0 + l1 * (inA ? dA1 : dA2)) + l2 * (inA ? dA2 : dB2);
+			z = fminf(fmaxf(z, 0.0f), 1.0f);
+			const uint32_t dq = __float2uint_rn(z * 16777215.0f);
+			if (dq < 0xFFFFFFu) atomicMin(kp + off, ((unsigned long long)(tagsh | dq) << 32) | id1);
+		}
+	};
+	for (int s = 0; s < msteps; s++) {
+		if (idx < npx) {
+			// rows 2y and 2y + 1 of column x: the second row's edge values are one add away from the first's
+			const int e0 = a0 + x * a0x + y * a0y2, e1 = a1 + x * a1x + y * a1y2, e2 = a2 + x * a2x + y * a2y2;
+			const int f0 = b0 + x * b0x + y * b0y2, f1 = b1 + x * b1x + y * b1y2;
+			const int off = 2 * y * W + x;
+			pixel(e0, e1, e2, f0, f1, off);
+			if (2 * y + 1 < hh) pixel(e0 + a0y, e1 + a1y, e2 + a2y, f0 + b0y, f1 + b1y, off + W);
+		}
+		idx += 8; x += r8; y += q8;
+		if (x >= w8) { x -= w8; y++; }
+	}
+}
+
+template <bool RING>
+__device__ __forceinline__ void walk_chunk(const RadDev& D, const RadQueueEntry e, const RadBigTri* __restrict__ q_tri, uint32_t q_tri_cap,
+                                           unsigned long long* __restrict__ ring_keys, uint32_t tagsh, int lane) {
+	if (e.tri >= q_tri_cap) return;
+	const RadBigTri r = q_tri[e.tri];
+	Tri w;
+	w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
+	w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
+	const int T = (int)D.tile;
+	const int px0 = r.px0 + (int)e.tx * T, px1 = min(r.px1, px0 + T - 1);
+	const int py0 = r.py0 + (int)e.ty * T, py1 = min(r.py1, py0 + T - 1);
+	unsigned long long* __restrict__ keys = RING ? ring_keys : D.keys + (size_t)(r.slot - D.kbase) * D.RES;
+	// this lane's first pixel; steps of 8 pixels in x and 4 in y
+	const int lx = px0 + (lane & 7), ly = py0 + (lane >> 3);
+	if (fits32(w, px0, py0, T)) {          // warp-uniform: small triangle around this chunk -> int32 walk
+		EdgeSet32 E; edges_at32(w, lx, ly, E);
+		for (int py = ly; py <= py1; py += 4, E.e0 += 4 * E.sy0, E.e1 += 4 * E.sy1, E.e2 += 4 * E.sy2) {
+			int e0 = E.e0, e1 = E.e1, e2 = E.e2;
+			unsigned long long* row = keys + (size_t)py * D.W;
+			for (int px = lx; px <= px1; px += 8, e0 += 8 * E.sx0, e1 += 8 * E.sx1, e2 += 8 * E.sx2)
+				if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, r.id1, row + px, tagsh);
+		}
+		return;
+	}
+	EdgeSet E; edges_at(w, lx, ly, E);
+	// a triangle spread over several chunks: skip the chunk when one edge has all four corner pixels outside
+	if (r.px1 - r.px0 >= T || r.py1 - r.py0 >= T) {
+		// corner values from lane 0's origin value: e(px0,py0) + dx*sx + dy*sy
+		const long long dx = px1 - px0, dy = py1 - py0;
+		const long long c0 = __shfl_sync(FULL, E.e0, 0), c1 = __shfl_sync(FULL, E.e1, 0), c2 = __shfl_sync(FULL, E.e2, 0);
+		const bool out = (c0 < 0 && c0 + dx * E.sx0 < 0 && c0 + dy * E.sy0 < 0 && c0 + dx * E.sx0 + dy * E.sy0 < 0) ||
+		                 (c1 < 0 && c1 + dx * E.sx1 < 0 && c1 + dy * E.sy1 < 0 && c1 + dx * E.sx1 + dy * E.sy1 < 0) ||
+		                 (c2 < 0 && c2 + dx * E.sx2 < 0 && c2 + dy * E.sy2 < 0 && c2 + dx * E.sx2 + dy * E.sy2 < 0);
+		if (out) return;
+	}
+	for (int py = ly; py <= py1; py += 4, E.e0 += 4 * E.sy0, E.e1 += 4 * E.sy1, E.e2 += 4 * E.sy2) {
+		long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
+		unsigned long long* row = keys + (size_t)py * D.W;
+		for (int px = lx; px <= px1; px += 8, e0 += 8 * E.sx0, e1 += 8 * E.sx1, e2 += 8 * E.sx2)
+			if ((e0 | e1 | e2) >= 0) shade_covered(w, e1 - E.b1, e2 - E.b2, r.id1, row + px, tagsh);
+	}
+}
+
+// persistent warps drain both queues of the launch (whole-batch key buffers: staged API, RAD_RING=0, micro-triangle scenes)
 __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
 	const uint32_t tagsh = D.tag << 24;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-	{
-		const uint32_t nsm = min(D.qc->q_small, D.q_sm_cap);
-		const uint4* __restrict__ qsm = reinterpret_cast<const uint4*>(D.q_sm);
-		const int sub = lane >> 3, l8 = lane & 7;
-		const int W = (int)D.W;
-		__shared__ __align__(16) uint4 s_rec[PF ? 4 : 1][2][16];      // [warp][buffer][4 records x 4 words]
-		const int wib = threadIdx.x >> 5;
-		// lanes 0..15 copy one 16-byte word each of the records base .. base + 3
-		auto prefetch = [&](uint32_t b, int buf) {
-			const uint32_t rec = b + (uint32_t)(lane >> 2);
-			if (lane < 16 && rec < nsm) {
-				const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_rec[wib][buf][lane]);
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(qsm + 4 * (size_t)rec + (lane & 3)) : "memory");
-			}
-			asm volatile("cp.async.commit_group;" ::: "memory");
-		};
-		uint32_t it = 0;
-		if (PF && gw * 4 < nsm) prefetch(gw * 4, 0);
-		for (uint32_t base = gw * 4; base < nsm; base += nw * 4, it++) {
-			if (PF) {
-				__syncwarp();                                         // every lane has read the buffer that is refilled now
-				prefetch(base + nw * 4, (int)((it + 1) & 1));         // (an empty group past the end of the queue)
-				asm volatile("cp.async.wait_group 1;" ::: "memory");
-				__syncwarp();
-			}
-			const uint32_t i = base + sub;
-			int npx = 0, w8 = 1, hh = 0, q8 = 0, r8 = 0, x = 0, y = 0;
-			int a0y2 = 0, a1y2 = 0, a2y2 = 0, b0y2 = 0, b1y2 = 0;
-			int a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0;                         // biased edge values at the bbox origin
-			int a0x = 0, a1x = 0, a2x = 0, b0x = 0, b1x = 0, a0y = 0, a1y = 0, a2y = 0, b0y = 0, b1y = 0;
-			int bA1 = 0, bA2 = 0, bB1 = 0, bB2 = 0;
-			float Z0 = 0, dA1 = 0, dA2 = 0, dB2 = 0, invA = 0, invB = 0;
-			uint32_t id1 = 0; unsigned long long* kp = nullptr;
-			if (i < nsm) {
-				uint4 r0, r1, r2; uint2 r3;
-				if (PF) {
-					const uint4* sr = &s_rec[wib][it & 1][4 * sub];
-					r0 = sr[0]; r1 = sr[1]; r2 = sr[2]; r3 = *reinterpret_cast<const uint2*>(sr + 3);
-				} else {
-					r0 = __ldg(qsm + 4 * (size_t)i); r1 = __ldg(qsm + 4 * (size_t)i + 1); r2 = __ldg(qsm + 4 * (size_t)i + 2);
-					r3 = __ldg(reinterpret_cast<const uint2*>(qsm + 4 * (size_t)i + 3));
-				}
-				const int x0 = (int)(r0.x << 16) >> 16, y0 = (int)r0.x >> 16, x1 = (int)(r0.y << 16) >> 16, y1 = (int)r0.y >> 16;
-				const int x2 = (int)(r0.z << 16) >> 16, y2 = (int)r0.z >> 16, x3 = (int)(r0.w << 16) >> 16, y3 = (int)r0.w >> 16;
-				int bA0, bB0;
-				edge_origin(x1, y1, x2, y2, a0, a0x, a0y, bA0);      // A: edges (1->2), (2->0), (0->1)
-				edge_origin(x2, y2, x0, y0, a1, a1x, a1y, bA1);
-				edge_origin(x0, y0, x1, y1, a2, a2x, a2y, bA2);
-				edge_origin(x2, y2, x3, y3, b0, b0x, b0y, bB0);      // B: edges (2->3), (3->0), (0->2)
-				edge_origin(x3, y3, x0, y0, b1, b1x, b1y, bB1);
-				{ const int dx = x2 - x0, dy = y2 - y0; bB2 = (dy < 0 || (dy == 0 && dx < 0)) ? 0 : -1; }
-				Z0 = __uint_as_float(r1.x);
-				dA1 = __uint_as_float(r1.y) - Z0; dA2 = __uint_as_float(r1.z) - Z0; dB2 = __uint_as_float(r1.w) - Z0;
-				invA = __uint_as_float(r2.x); invB = __uint_as_float(r2.y);
-				id1 = r2.z;
-				const uint32_t slot = r2.w & 0xFFFFu, rcpw = r2.w >> 16;
-				const int px0 = (int)(r3.x & 0xFFFFu), py0 = (int)(r3.x >> 16);
-				w8 = (int)(r3.y & 0xFFu);
-				hh = (int)((r3.y >> 8) & 0xFFu);
-				npx = w8 * ((hh + 1) >> 1);                               // positions of the walk: every one is a column of TWO rows
-				q8 = (int)((8u * rcpw) >> 15); r8 = 8 - q8 * w8;          // 8 / w, 8 % w
-				y = (int)(((uint32_t)l8 * rcpw) >> 15); x = l8 - y * w8;   // this lane's first position (y counts row pairs)
-				kp = D.keys + (size_t)(slot - D.kbase) * D.RES + (size_t)py0 * D.W + px0;
-				a0y2 = 2 * a0y; a1y2 = 2 * a1y; a2y2 = 2 * a2y; b0y2 = 2 * b0y; b1y2 = 2 * b1y;
-			}
-			int msteps = (npx + 7) >> 3;
-			msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 8)); msteps = max(msteps, __shfl_xor_sync(FULL, msteps, 16));
-			int idx = l8;
-			// one covered-pixel test + depth + RED; the unbiased A edge (2->0) is minus B's edge (0->2)
-			auto pixel = [&](int e0, int e1, int e2, int f0, int f1, int off) {
-				const int e1u = e1 - bA1;
-				const int f2 = bB2 - e1u;
-				const bool inA = (e0 | e1 | e2) >= 0, inB = (f0 | f1 | f2) >= 0;
-				if (inA || inB) {
-					const float inv = inA ? invA : invB;
-					const float l1 = (float)(inA ? e1u : f1 - bB1) * inv, l2 = (float)(inA ? e2 - bA2 : -e1u) * inv;
-					float z = (Z0 + l1 * (inA ? dA1 : dA2)) + l2 * (inA ? dA2 : dB2);
-					z = fminf(fmaxf(z, 0.0f), 1.0f);
-					const uint32_t dq = __float2uint_rn(z * 16777215.0f);
-					if (dq < 0xFFFFFFu) atomicMin(kp + off, ((unsigned long long)(tagsh | dq) << 32) | id1);
-				}
-			};
-			for (int s = 0; s < msteps; s++) {
-				if (idx < npx) {
-					// rows 2y and 2y + 1 of column x: the second row's edge values are one add away from the first's
-					const int e0 = a0 + x * a0x + y * a0y2, e1 = a1 + x * a1x + y * a1y2, e2 = a2 + x * a2x + y * a2y2;
-					const int f0 = b0 + x * b0x + y * b0y2, f1 = b1 + x * b1x + y * b1y2;
-					const int off = 2 * y * W + x;
-					pixel(e0, e1, e2, f0, f1, off);
-					if (2 * y + 1 < hh) pixel(e0 + a0y, e1 + a1y, e2 + a2y, f0 + b0y, f1 + b1y, off + W);
-				}
-				idx += 8; x += r8; y += q8;
-				if (x >= w8) { x -= w8; y++; }
-			}
-		}
-	}
+	const uint32_t nsm = min(D.qc->q_small, D.q_sm_cap);
+	const uint4* __restrict__ qsm = reinterpret_cast<const uint4*>(D.q_sm);
+	for (uint32_t base = gw * 4; base < nsm; base += nw * 4) walk_small4<false>(D, qsm, base, nsm, nullptr, tagsh, lane);
 	const uint32_t nent = min(D.qc->q_entries, D.q_ent_cap);
-	for (uint32_t i = gw; i < nent; i += nw) {
-		const RadQueueEntry e = D.q_ent[i];
-		if (e.tri >= D.q_tri_cap) continue;
-		const RadBigTri r = D.q_tri[e.tri];
-		Tri w;
-		w.X0 = r.X0; w.Y0 = r.Y0; w.X1 = r.X1; w.Y1 = r.Y1; w.X2 = r.X2; w.Y2 = r.Y2;
-		w.z0 = r.z0; w.dz1 = r.dz1; w.dz2 = r.dz2; w.inv_area = r.inv_area;
-		const int T = (int)D.tile;
-		const int px0 = r.px0 + (int)e.tx * T, px1 = min(r.px1, px0 + T - 1);
-		const int py0 = r.py0 + (int)e.ty * T, py1 = min(r.py1, py0 + T - 1);
-		unsigned long long* __restrict__ keys = D.keys + (size_t)(r.slot - D.kbase) * D.RES;
-		// this lane's first pixel; steps of 8 pixels in x and 4 in y
-		const int lx = px0 + (lane & 7), ly = py0 + (lane >> 3);
-		if (fits32(w, px0, py0, T)) {          // warp-uniform: small triangle around this chunk -> int32 walk
-			EdgeSet32 E; edges_at32(w, lx, ly, E);
-			for (int py = ly; py <= py1; py += 4, E.e0 += 4 * E.sy0, E.e1 += 4 * E.sy1, E.e2 += 4 * E.sy2) {
-				int e0 = E.e0, e1 = E.e1, e2 = E.e2;
-				unsigned long long* row = keys + (size_t)py * D.W;
-				for (int px = lx; px <= px1; px += 8, e0 += 8 * E.sx0, e1 += 8 * E.sx1, e2 += 8 * E.sx2)
-					if ((e0 | e1 | e2) >= 0) shade_covered32(w, e1 - E.b1, e2 - E.b2, r.id1, row + px, tagsh);
+	for (uint32_t i = gw; i < nent; i += nw) walk_chunk<false>(D, D.q_ent[i], D.q_tri, D.q_tri_cap, nullptr, tagsh, lane);
+}
+
+// ---- ring path: walk + ProcessHemicube in one persistent kernel, stage by stage through L2-resident key buffers ---------
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+	uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// The warp waits until stage `st` is ready (flag set by the last CTA that finished it).  s_seen caches, per CTA, how many
+// stages are known to be ready.  false: the watchdog fired — somebody waited for two seconds — give up.
+__device__ __forceinline__ bool ring_wait(const uint32_t* flag, uint32_t st, uint32_t* s_seen, uint32_t* abort_flag, int lane) {
+	int ok = 1;
+	if (lane == 0 && *reinterpret_cast<volatile uint32_t*>(s_seen) <= st) {
+		uint32_t spins = 0, ns = 200; unsigned long long t0 = 0;
+		while (ld_acquire_u32(flag) == 0u) {
+			if (*reinterpret_cast<volatile uint32_t*>(s_seen) > st) break;      // a warp of this CTA has seen it
+			__nanosleep(ns); if (ns < 1600) ns += ns;
+			if ((++spins & 63u) == 0u) {
+				if (*reinterpret_cast<volatile uint32_t*>(abort_flag)) { ok = 0; break; }
+				const unsigned long long t = global_ns();
+				if (t0 == 0) t0 = t; else if (t - t0 > 2000000000ull) { *reinterpret_cast<volatile uint32_t*>(abort_flag) = 1u; ok = 0; break; }
 			}
-			continue;
 		}
-		EdgeSet E; edges_at(w, lx, ly, E);
-		// a triangle spread over several chunks: skip the chunk when one edge has all four corner pixels outside
-		if (r.px1 - r.px0 >= T || r.py1 - r.py0 >= T) {
-			// corner values from lane 0's origin value: e(px0,py0) + dx*sx + dy*sy
-			const long long dx = px1 - px0, dy = py1 - py0;
-			const long long c0 = __shfl_sync(FULL, E.e0, 0), c1 = __shfl_sync(FULL, E.e1, 0), c2 = __shfl_sync(FULL, E.e2, 0);
-			const bool out = (c0 < 0 && c0 + dx * E.sx0 < 0 && c0 + dy * E.sy0 < 0 && c0 + dx * E.sx0 + dy * E.sy0 < 0) ||
-			                 (c1 < 0 && c1 + dx * E.sx1 < 0 && c1 + dy * E.sy1 < 0 && c1 + dx * E.sx1 + dy * E.sy1 < 0) ||
-			                 (c2 < 0 && c2 + dx * E.sx2 < 0 && c2 + dy * E.sy2 < 0 && c2 + dx * E.sx2 + dy * E.sy2 < 0);
-			if (out) continue;
-		}
-		for (int py = ly; py <= py1; py += 4, E.e0 += 4 * E.sy0, E.e1 += 4 * E.sy1, E.e2 += 4 * E.sy2) {
-			long long e0 = E.e0, e1 = E.e1, e2 = E.e2;
-			unsigned long long* row = keys + (size_t)py * D.W;
-			for (int px = lx; px <= px1; px += 8, e0 += 8 * E.sx0, e1 += 8 * E.sx1, e2 += 8 * E.sx2)
-				if ((e0 | e1 | e2) >= 0) shade_covered(w, e1 - E.b1, e2 - E.b2, r.id1, row + px, tagsh);
+		if (ok) { __threadfence_block(); atomicMax(s_seen, st + 1u); }
+	}
+	__threadfence_block();
+	return __shfl_sync(FULL, ok, 0) != 0;
+}
+// This warp has finished the stage (all its REDs / key reads are done).  The last warp of the CTA counts the CTA in; the
+// last CTA raises the stage's ready flag.  fence.acq_rel, not the sequentially consistent __threadfence(): every hop is a
+// release (writes before it) / acquire (the counter it has just read) pair.
+__device__ __forceinline__ void fence_ar_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void ring_signal(uint32_t* s_cnt, uint32_t* cnt, uint32_t* flag, uint32_t nctas, int lane) {
+	__syncwarp();
+	if (lane == 0) {
+		fence_ar_gpu();
+		if (atomicAdd(s_cnt, 1u) == (blockDim.x >> 5) - 1u) {
+			fence_ar_gpu();
+			if (atomicAdd(cnt, 1u) == nctas - 1u) { fence_ar_gpu(); *reinterpret_cast<volatile uint32_t*>(flag) = 1u; }
 		}
 	}
+}
+
+// CTAs [0, R.walk_ctas) walk, the others process.  Stage st = slots [st * sg, (st + 1) * sg) of the launch, key buffers
+// (st % rs) * sg ... of the ring, epoch tag tag0 - st / rs.  Work inside a stage is dealt out statically: item g (counted
+// over the whole launch, so that the remainders do not always hit the same warps) belongs to warp g % nw.
+//   walk:    wait until the process warps have finished stage st - rs (the buffers' previous user), walk, signal walk_done[st]
+//   process: wait until all walk warps have signalled walk_done[st], resolve + ProcessHemicube, signal proc_done[st]
+// Every warp of the grid must be resident for this to make progress: the launch is cooperative (co-residency checked by
+// the driver) and every wait has a watchdog.  Keys are read with ld.global.cg: the ring re-uses addresses inside one
+// launch, L1 must not serve a line of the previous round.
+template <bool KEEP>
+__global__ void __launch_bounds__(128, 8) raster_ring_kernel(RadDev D, RadRing R) {
+	__shared__ uint32_t s_nsm[RAD_RING_SLOTS], s_nent[RAD_RING_SLOTS], s_valid[RAD_RING_SLOTS], s_cnt[RAD_RING_SLOTS], s_seen;
+	if (D.stop_gate && D.ctl->gate) return;                           // the stop test fired in an earlier batch of this replay
+	if (threadIdx.x == 0) s_seen = 0;
+	for (uint32_t t = threadIdx.x; t < RAD_RING_SLOTS; t += blockDim.x) s_cnt[t] = 0;
+	for (uint32_t t = threadIdx.x; t < R.nslots; t += blockDim.x) {
+		s_nsm[t] = min(D.rc->slot[t].q_small, R.cap_sm); s_nent[t] = min(D.rc->slot[t].q_entries, R.cap_ent);
+		s_valid[t] = D.em[D.h0 + t].valid;
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const bool walker = blockIdx.x < R.walk_ctas;
+	const uint32_t nw = walker ? R.nw_walk : R.nw_proc;
+	const uint32_t gw = (walker ? blockIdx.x : blockIdx.x - R.walk_ctas) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	uint32_t rot = 0;                                                   // items dealt so far, mod nw
+	const bool stamp = (R.debug & 16u) && threadIdx.x == 0;
+	if (stamp) atomicMin(&D.rc->t_start, global_ns());
+	unsigned long long waited = 0;
+	if (walker) {
+		for (uint32_t st = 0; st < R.nst; st++) {
+			const unsigned long long tw0 = stamp ? global_ns() : 0ull;
+			if (st >= R.rs && !(R.debug & 1u) && !ring_wait(&D.rc->proc_ready[st - R.rs][0], st - R.rs, &s_seen, &D.ctl->ring_abort, lane)) return;
+			if (stamp) waited += global_ns() - tw0;
+			const uint32_t tagsh = (R.tag0 - st / R.rs) << 24;
+			const uint32_t s1 = min((st + 1) * R.sg, R.nslots);
+			for (uint32_t sl = st * R.sg; sl < s1; sl++) {
+				unsigned long long* __restrict__ keys = D.keys + (size_t)((st % R.rs) * R.sg + (sl - st * R.sg)) * D.RES;
+				const uint32_t nsm = s_nsm[sl], ws = (nsm + 3u) >> 2;
+				const uint4* __restrict__ qsm = reinterpret_cast<const uint4*>(D.q_sm + (size_t)sl * R.cap_sm);
+				for (uint32_t j = gw >= rot ? gw - rot : gw + nw - rot; j < ws; j += nw) walk_small4<true>(D, qsm, 4u * j, nsm, keys, tagsh, lane);
+				rot = (rot + ws) % nw;
+				const uint32_t nent = s_nent[sl];
+				const RadQueueEntry* __restrict__ qe = D.q_ent + (size_t)sl * R.cap_ent;
+				for (uint32_t j = gw >= rot ? gw - rot : gw + nw - rot; j < nent; j += nw)
+					walk_chunk<true>(D, qe[j], D.q_tri + (size_t)sl * R.cap_tri, R.cap_tri, keys, tagsh, lane);
+				rot = (rot + nent) % nw;
+			}
+			ring_signal(&s_cnt[st], &D.rc->walk_cnt[st][0], &D.rc->walk_ready[st][0], R.walk_ctas, lane);
+		}
+		if (stamp) { atomicMax(&D.rc->t_walk_end, global_ns()); atomicAdd(&D.rc->t_walk_wait, waited); }
+		return;
+	}
+	const uint32_t nsteps = D.RES >> 7;                                 // 128 pixels per warp step
+	const float4* __restrict__ ff4 = reinterpret_cast<const float4*>(D.ff);
+	for (uint32_t st = 0; st < R.nst; st++) {
+		const unsigned long long tw0 = stamp ? global_ns() : 0ull;
+		if (!ring_wait(&D.rc->walk_ready[st][0], st, &s_seen, &D.ctl->ring_abort, lane)) return;
+		if (stamp) waited += global_ns() - tw0;
+		const uint32_t tag_end = (R.tag0 - st / R.rs + 1u) << 24;      // tags only decrease and a minimum survives: mine iff high word < (tag + 1) << 24
+		const uint32_t s1 = min((st + 1) * R.sg, R.nslots);
+		for (uint32_t sl = st * R.sg; sl < s1; sl++) {
+			if (!s_valid[sl]) continue;                                 // NULL emitters render nothing (Main.cpp:1253)
+			const uint32_t slot = D.h0 + sl;
+			const uint4* __restrict__ keys4 = reinterpret_cast<const uint4*>(D.keys + (size_t)((st % R.rs) * R.sg + (sl - st * R.sg)) * D.RES);
+			float* __restrict__ F = D.F + (size_t)slot * D.P;
+			uint4* __restrict__ items4 = reinterpret_cast<uint4*>(D.items + (size_t)slot * D.RES);
+			const uint32_t pairs = (nsteps + 1u) >> 1;                   // two warp steps per item: their loads are in flight together
+			for (uint32_t j = gw >= rot ? gw - rot : gw + nw - rot; j < pairs; j += nw) {
+				uint4 id[2]; float4 v[2];
+				#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					const uint32_t g = 2u * j + u;
+					id[u] = make_uint4(0u, 0u, 0u, 0u); v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+					if (g < nsteps) {
+						const uint32_t q = (g << 5) + lane;               // this lane's group of four pixels
+						const uint4 k0 = __ldcg(keys4 + 2 * (size_t)q), k1 = __ldcg(keys4 + 2 * (size_t)q + 1);
+						id[u] = make_uint4(k0.y < tag_end ? k0.x : 0u, k0.w < tag_end ? k0.z : 0u, k1.y < tag_end ? k1.x : 0u, k1.w < tag_end ? k1.z : 0u);
+						v[u] = __ldg(ff4 + q);
+					}
+				}
+				#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					const uint32_t g = 2u * j + u;
+					if (g < nsteps) {
+						if (KEEP) items4[(g << 5) + lane] = id[u];
+						process4(id[u], v[u], lane, F, D.P);
+					}
+				}
+			}
+			rot = (rot + pairs) % nw;
+		}
+		ring_signal(&s_cnt[st], &D.rc->proc_cnt[st][0], &D.rc->proc_ready[st][0], gridDim.x - R.walk_ctas, lane);
+	}
+	if (stamp) { atomicMax(&D.rc->t_proc_end, global_ns()); atomicAdd(&D.rc->t_proc_wait, waited); }
 }
 
 // recycles the chunk queue between hemicube groups of one batch (see rad_launch_raster)
@@ -709,6 +880,18 @@ static RadDev lane_view(const rad_ctx* c, uint32_t lane, uint32_t L) {
 	return D;
 }
 
+// exact stage: persistent grid over the surviving pairs (their number is only known on the device)
+template <bool SL>
+static void launch_setup_kernel(const RadDev& D, const RadRing& R, uint32_t n, cudaStream_t st) {
+	uint64_t want = ((uint64_t)D.P * n * 2 + 127) / 128;      // typically ~1 of 5 (patch, face) pairs survives
+	static const int sctas = [] { const char* e = getenv("RAD_SETUP_CTAS"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 16 ? 16 : v); }();   // tuning knob: CTAs per SM of the set-up grid (3 = what fits; more only queue up behind the other lanes)
+	const uint32_t blocks = (uint32_t)(want < 148 ? 148 : (want > 148u * sctas ? 148u * sctas : want));
+	static const int minb = [] { const char* e = getenv("RAD_SETUP_MINB"); const int v = e ? atoi(e) : 3; return v < 3 ? 3 : (v > 5 ? 5 : v); }();   // tuning knob: resident CTAs per SM the set-up kernel is compiled for
+	if (minb == 3) raster_setup_kernel<3, SL><<<blocks, 128, 0, st>>>(D, R);
+	else if (minb == 4) raster_setup_kernel<4, SL><<<blocks, 128, 0, st>>>(D, R);
+	else raster_setup_kernel<5, SL><<<blocks, 128, 0, st>>>(D, R);
+}
+
 // slots [D.h0 + s0, +n) of the view V on stream st
 static void launch_setup(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n, uint32_t kbase, bool tiles = false) {
 	RadDev D = V;
@@ -720,24 +903,17 @@ static void launch_setup(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t 
 	// tile-binned form (raster_tiles.cu): every triangle is parked (nothing touches the global key buffer), a large
 	// triangle gets one chunk entry (unused there: the bins cut it by atlas tile)
 	if (tiles) { D.inline_area = 0u; D.tile = 1u << 15; }
-	raster_cull_kernel<<<dim3((D.P + 255) / 256, 1, n), 256, 0, st>>>(D);
+	const RadRing R0 = {};
+	raster_cull_kernel<false><<<dim3((D.P + 255) / 256, 1, n), 256, 0, st>>>(D, R0);
 	// exact stage: persistent grid over the surviving pairs (their number is only known on the device)
-	uint64_t want = ((uint64_t)D.P * n * 2 + 127) / 128;      // typically ~1 of 5 (patch, face) pairs survives
-	static const int sctas = [] { const char* e = getenv("RAD_SETUP_CTAS"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 16 ? 16 : v); }();   // tuning knob: CTAs per SM of the set-up grid (3 = what fits; more only queue up behind the other lanes)
-	const uint32_t blocks = (uint32_t)(want < 148 ? 148 : (want > 148u * sctas ? 148u * sctas : want));
-	static const int minb = [] { const char* e = getenv("RAD_SETUP_MINB"); const int v = e ? atoi(e) : 3; return v < 3 ? 3 : (v > 5 ? 5 : v); }();   // tuning knob: resident CTAs per SM the set-up kernel is compiled for
-	if (minb == 3) raster_setup_kernel<3><<<blocks, 128, 0, st>>>(D);
-	else if (minb == 4) raster_setup_kernel<4><<<blocks, 128, 0, st>>>(D);
-	else raster_setup_kernel<5><<<blocks, 128, 0, st>>>(D);
+	launch_setup_kernel<false>(D, R0, n, st);
 	c->launches += 2;
 }
 static void launch_chunks(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t kbase) {
 	RadDev D = V;
 	D.kbase = kbase;
 	static const int ctas = [] { const char* e = getenv("RAD_QUEUE_CTAS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();   // tuning knob: persistent CTAs per SM
-	static const bool pf = [] { const char* e = getenv("RAD_QUEUE_PREFETCH"); return e && atoi(e) != 0; }();   // tuning knob (not measured yet)
-	if (pf) raster_queue_kernel<true><<<148 * ctas, 128, 0, st>>>(D);
-	else raster_queue_kernel<false><<<148 * ctas, 128, 0, st>>>(D);
+	raster_queue_kernel<<<148 * ctas, 128, 0, st>>>(D);
 	c->launches++;
 }
 
@@ -774,9 +950,89 @@ void rad_launch_process_view(rad_ctx* c, const RadDev& V, cudaStream_t st, uint3
 // HBM — and overlap when they run side by side (+28 % shots/s measured at 4 lanes on the 16 k-patch scene).
 // Within a lane the slots are rendered in groups only if its share of the work lists cannot hold the worst case (or a
 // key-buffer cap is set, RAD_L2_GROUP_MB); a group's key buffers are then recycled by the next one under a new tag.
+// ---- ring path (RadRing, raster_ring_kernel) -------------------------------------------------------------------------------
+// Worth it when the walks dominate (a handful of pixels per patch or more; micro-triangle scenes keep the inline tier of the
+// lane path, which needs every slot's key buffer at set-up time) and there are enough slots to pipeline.
+static bool ring_eligible(const rad_ctx* c, uint32_t nslots) {
+	const RadDev& D = c->d;
+	return c->ring_mode && !c->tile_mode && nslots >= 4 && D.k >= 4 && D.P > 0 && D.RES / D.P >= 8u && (D.RES & 127u) == 0;
+}
+template <bool KEEP>
+static cudaError_t launch_ring_kernel(rad_ctx* c, const RadDev& D, RadRing& R) {
+	if (c->ring_ctas_per_sm == 0) {
+		int a = 0, b = 0;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, raster_ring_kernel<false>, 128, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, raster_ring_kernel<true>, 128, 0);
+		c->ring_ctas_per_sm = a < b ? a : b;
+		if (c->ring_ctas_per_sm < 2) c->ring_ctas_per_sm = 2;
+		if (c->ring_ctas_per_sm > 8) c->ring_ctas_per_sm = 8;
+	}
+	int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->cfg.device);
+	const uint32_t layers = (uint32_t)c->ring_ctas_per_sm;
+	uint32_t pl = c->ring_proc_layers ? c->ring_proc_layers : (layers >= 6 ? 2u : 1u);      // process CTAs per SM
+	if (pl >= layers) pl = layers - 1;
+	R.walk_ctas = (uint32_t)nsm * (layers - pl);
+	R.nw_walk = R.walk_ctas * 4u; R.nw_proc = (uint32_t)nsm * pl * 4u;
+	R.keep_items = KEEP ? 1u : 0u;
+	static const uint32_t dbg = [] { const char* e = getenv("RAD_RING_DEBUG"); return e ? (uint32_t)atoi(e) : 0u; }();   // measurement knob: 1 walk CTAs do not wait for the ring (wrong results), 16 role time stamps
+	R.debug = dbg;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((uint32_t)nsm * layers); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // all CTAs resident at once, or the launch fails
+	cfg.attrs = at; cfg.numAttrs = 1;
+	void* args[2] = { (void*)&D, (void*)&R };
+	return cudaLaunchKernelExC(&cfg, (const void*)raster_ring_kernel<KEEP>, args);
+}
+static void launch_ring(rad_ctx* c, bool keep_items, const std::function<void(int)>& mark) {
+	const RadDev& D0 = c->d;
+	const uint32_t nslots = D0.h1 - D0.h0;
+	const uint64_t slot_bytes = (uint64_t)D0.RES * 8ull;
+	// stage = about 16 MB of keys, ring = what stays L2-resident next to the records and F (<= ~80 MB)
+	uint32_t sg = c->ring_sg ? c->ring_sg : (uint32_t)((16ull << 20) / slot_bytes);
+	if (sg < 1) sg = 1;
+	if (sg > 8) sg = 8;
+	uint32_t rs = c->ring_rs ? c->ring_rs : (slot_bytes * sg * 4ull <= (80ull << 20) ? 4u : (slot_bytes * sg * 3ull <= (80ull << 20) ? 3u : 2u));
+	if (rs < 2) rs = 2;
+	while (sg > 1 && sg * rs > D0.k) sg--;
+	while (rs > 2 && sg * rs > D0.k) rs--;
+	for (uint32_t g0 = 0; g0 < nslots; g0 += RAD_RING_SLOTS) {
+		const uint32_t n = nslots - g0 < RAD_RING_SLOTS ? nslots - g0 : RAD_RING_SLOTS;
+		RadDev D = D0;
+		D.h0 = D0.h0 + g0; D.h1 = D.h0 + n; D.kbase = D.h0;
+		D.inline_area = 0u;                                    // every triangle is parked: no key buffer exists at set-up time
+		RadRing R = {};
+		R.nslots = n; R.sg = sg; R.rs = rs; R.nst = (n + sg - 1) / sg;
+		const uint32_t rounds = (R.nst + rs - 1) / rs;         // one epoch tag per trip round the ring
+		if (c->epoch < rounds) rad_launch_clear_keys(c);
+		R.tag0 = c->epoch; c->epoch -= rounds; c->d.tag = R.tag0 - (rounds - 1);
+		R.cap_pairs = D.pairs_cap / n; R.cap_sm = D.q_sm_cap / n; R.cap_tri = D.q_tri_cap / n; R.cap_ent = D.q_ent_cap / n;
+		cudaMemsetAsync(D.rc, 0, sizeof(RadRingCtl), c->stream);
+		cudaMemsetAsync(&D.rc->t_start, 0xFF, 8, c->stream);
+		raster_cull_kernel<true><<<dim3((D.P + 255) / 256, 1, n), 256, 0, c->stream>>>(D, R);
+		launch_setup_kernel<true>(D, R, n, c->stream);
+		c->launches += 2;
+		if (mark) mark(1);
+		const cudaError_t e = keep_items ? launch_ring_kernel<true>(c, D, R) : launch_ring_kernel<false>(c, D, R);
+		if (e != cudaSuccess) { c->err = std::string("raster_ring_kernel launch: ") + cudaGetErrorString(e); c->ring_failed = true; }
+		c->launches++;
+		if (mark) mark(2);
+		if (mark && getenv("RAD_RING_DEBUG") && (atoi(getenv("RAD_RING_DEBUG")) & 16)) {
+			RadRingCtl* h = new RadRingCtl;
+			cudaMemcpyAsync(h, D.rc, sizeof(RadRingCtl), cudaMemcpyDeviceToHost, c->stream); cudaStreamSynchronize(c->stream);
+			uint32_t nrec = 0, nent = 0; for (uint32_t i = 0; i < n; i++) { nrec += h->slot[i].q_small; nent += h->slot[i].q_entries; }
+			fprintf(stderr, "ring: walk %.1f us (first CTA start -> last walk CTA end), process end %.1f us, mean wait per CTA: walk %.1f us, process %.1f us; %u records, %u chunk entries, sg %u rs %u nst %u, %u walk CTAs\n",
+			        (h->t_walk_end - h->t_start) * 1e-3, (h->t_proc_end - h->t_start) * 1e-3, h->t_walk_wait * 1e-3 / R.walk_ctas, h->t_proc_wait * 1e-3 / ((R.nw_proc / 4) ? (R.nw_proc / 4) : 1), nrec, nent, R.sg, R.rs, R.nst, R.walk_ctas);
+			delete h;
+		}
+	}
+	c->keys_dirty = false;
+}
+
 void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::function<void(int)>& mark) {
 	const uint32_t nslots = c->d.h1 - c->d.h0;
 	if (nslots == 0) return;
+	if (ring_eligible(c, nslots)) { launch_ring(c, keep_items, mark); return; }
 	uint32_t L = mark ? 1u : c->lanes;        // the per-stage profile wants the stages back to back
 	if (L > nslots) L = nslots;
 	if (L < 1) L = 1;

@@ -7,8 +7,8 @@ import json,sys
 t=sys.argv[1]
 try:
     d=json.load(open(f"gpurun_out/q_{t}.json"))
-    r=d["kernels"]["raster (K1: raster_setup + raster_queue)"]
-    print(t, round(d["value"],1), "shots/s e2e", round(d["e2e"]["value"],1), {k.split(" ")[0]:round(v["ms_per_batch"],4) for k,v in d["kernels"].items()}, "setup/queue", round(r["setup_ms"],4), round(r["queue_ms"],4),
+    r=[v for k,v in d["kernels"].items() if k.startswith("raster")][0]
+    print(t, round(d["value"],1), "shots/s e2e", round(d["e2e"]["value"],1), {k.split(" ")[0]:round(v["ms_per_batch"],4) for k,v in d["kernels"].items()}, "setup/queue", round(r["setup_ms"],4), round(r.get("queue_ms", r.get("ring_ms", 0)),4),
           "K2", round(d["process_hemicube"]["gpix_per_s"],1), "Gpix/s", round(d["process_hemicube"]["ms_per_launch"],4), "ms")
 except Exception as e: print(t,"ERR",e)
 PY
