@@ -400,6 +400,8 @@ def strong_scaling(B, name, steps=4, warmup=2):
         one = B.context(arrays, N, k, sharded=False)
         v1, ms1, _, _ = B.timed(one, batches, steps, warmup, collective=False, runs=runs)
         res.update(v1=v1, ms_per_step_1gpu=ms1, e2e_1gpu=B.e2e(one, r, il, batches, 2, 1, collective=False, runs=runs))
+        one.restore_state(); one.shoot(batches - 1)
+        r_less, _, _ = B.state_digest(one)              # (sanity of the comparison below: one batch less must NOT agree)
         one.restore_state(); one.shoot(batches)
         r1, i1, _ = B.state_digest(one)
         one.close()
@@ -411,9 +413,11 @@ def strong_scaling(B, name, steps=4, warmup=2):
     rad, illum, dig = B.state_digest(ctx)
     same = B.replicas_identical(dig)
     B.close(ctx, True)
-    res.update(vN=vN, ms_per_step_sharded=msN, n_gpus=B.world, replicas_bit_identical=bool(same), e2e_sharded=e2eN)
+    res.update(vN=vN, ms_per_step_sharded=msN, n_gpus=B.world, replicas_bit_identical=bool(same), e2e_sharded=e2eN,
+               rel_l2_radiosity_vs_fresh_scene=rel_l2(rad, r))      # (sanity: the compared state is not the start state)
     if B.rank == 0:
-        res.update(efficiency=vN / (B.world * v1), speedup=vN / v1, rel_l2_radiosity_vs_one_gpu=rel_l2(rad, r1), rel_l2_illumination_vs_one_gpu=rel_l2(illum, i1))
+        res.update(efficiency=vN / (B.world * v1), speedup=vN / v1, rel_l2_radiosity_vs_one_gpu=rel_l2(rad, r1), rel_l2_illumination_vs_one_gpu=rel_l2(illum, i1),
+                   values_differing_from_one_gpu=int(np.count_nonzero(rad != r1)), rel_l2_radiosity_vs_one_batch_less=rel_l2(rad, r_less))
         res["ok"] = bool(same and res["rel_l2_radiosity_vs_one_gpu"] < 1e-3 and res["rel_l2_illumination_vs_one_gpu"] < 1e-3)
     return res
 

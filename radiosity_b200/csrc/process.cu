@@ -20,8 +20,11 @@
 // by rad_shoot: it reads the rasteriser's 64-bit keys directly  (a key counts iff its top byte is the render's
 // epoch tag, so nothing is cleared) and only materialises the item buffer when asked to.
 #include "rad_internal.cuh"
+#include "segadd.cuh"
 
+#ifndef FULL
 #define FULL 0xFFFFFFFFu
+#endif
 
 namespace {
 
@@ -42,7 +45,7 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
 }
 
 // (id+1, sum) of one run into F: predicated red, no branch
-__device__ __forceinline__ void flush_run(uint32_t id, float v, float* __restrict__ F, uint32_t P, bool on = true) {
+__device__ __forceinline__ void flush_run_pred(uint32_t id, float v, float* __restrict__ F, uint32_t P, bool on = true) {
 	asm volatile("{\n.reg .pred q, o;\n.reg .u32 c;\n.reg .u64 a;\n"
 	             "sub.u32 c, %0, 1;\n"
 	             "setp.ne.u32 o, %4, 0;\n"
@@ -161,20 +164,62 @@ __global__ void __launch_bounds__(kWarps * 32, FROM_KEYS ? 6 : 8) process_kernel
 			if (__all_sync(FULL, live && wr == s_runs && cur == first)) {   // the whole chunk is one run
 				#pragma unroll
 				for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
-				flush_run(cur, acc, F, P, lane == 0);
+				flush_run_pred(cur, acc, F, P, lane == 0);
 			} else {
-				flush_run(cur, acc, F, P);
+				flush_run_pred(cur, acc, F, P);
 				const uint32_t wmax = __reduce_max_sync(FULL, wr);
 				for (uint32_t a = s_runs; a < wmax; a += 512u) {       // two parked runs per step (the loads overlap)
 					uint32_t rid0 = 0u, rv0 = 0u, rid1 = 0u, rv1 = 0u;
 					asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %2, %3;\n@p ld.shared.v2.b32 {%0, %1}, [%2];\n}" : "+r"(rid0), "+r"(rv0) : "r"(a), "r"(wr));
 					asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %2, %3;\n@p ld.shared.v2.b32 {%0, %1}, [%2];\n}" : "+r"(rid1), "+r"(rv1) : "r"(a + 256u), "r"(wr));
-					flush_run(rid0, __uint_as_float(rv0), F, P);
-					flush_run(rid1, __uint_as_float(rv1), F, P);
+					flush_run_pred(rid0, __uint_as_float(rv0), F, P);
+					flush_run_pred(rid1, __uint_as_float(rv1), F, P);
 				}
 			}
 		}
 		__syncthreads();                                               // every warp holds its dFF entries: the next task may overwrite the chunk
+	}
+}
+
+// Fused form for launches of fewer slots than a CTA has warps (k = 1: ONE hemicube per launch, a latency chain): the task
+// kernel above would leave three of four warps idle and pay a bulk-copy round trip per chunk, so every warp takes 128-pixel
+// steps of the slot directly — two steps' loads in flight, four pixels per lane, runs merged by the segmented shuffle of
+// segadd.cuh.  grid: x = warps over the atlas, y = slot.
+template <bool KEEP>
+__global__ void __launch_bounds__(256) process_few_kernel(RadDev D) {
+	const uint32_t slot = D.h0 + blockIdx.y;
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.qc->q_tris | D.qc->q_small | D.qc->n_pairs)) { D.qc->parked = D.qc->q_tris + D.qc->q_small; D.qc->q_tris = 0; D.qc->q_entries = 0; D.qc->q_small = 0; D.qc->n_pairs = 0; }
+	if (D.stop_gate && D.ctl->gate) return;
+	if (!D.em[slot].valid) return;
+	const int lane = threadIdx.x & 31;
+	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t nsteps = D.RES >> 7;               // 128 pixels per warp step (RES = 3 N^2, N a multiple of 8)
+	const uint32_t tag_end = (D.tag + 1u) << 24;
+	float* __restrict__ F = D.F + (size_t)slot * D.P;
+	const float4* __restrict__ ff4 = reinterpret_cast<const float4*>(D.ff);
+	const uint4* __restrict__ keys4 = reinterpret_cast<const uint4*>(D.keys + (size_t)(slot - D.kbase) * D.RES);
+	uint4* __restrict__ items4 = reinterpret_cast<uint4*>(D.items + (size_t)slot * D.RES);
+	for (uint32_t g0 = gw * 2; g0 < nsteps; g0 += nw * 2) {
+		uint4 id[2]; float4 v[2];
+		#pragma unroll
+		for (int u = 0; u < 2; u++) {
+			const uint32_t g = g0 + u;
+			id[u] = make_uint4(0u, 0u, 0u, 0u); v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (g < nsteps) {
+				const uint32_t q = (g << 5) + lane;   // this lane's group of four pixels
+				const uint4 k0 = __ldcs(keys4 + 2 * (size_t)q), k1 = __ldcs(keys4 + 2 * (size_t)q + 1);
+				id[u] = make_uint4(k0.y < tag_end ? k0.x : 0u, k0.w < tag_end ? k0.z : 0u, k1.y < tag_end ? k1.x : 0u, k1.w < tag_end ? k1.z : 0u);
+				v[u] = __ldg(ff4 + q);
+			}
+		}
+		#pragma unroll
+		for (int u = 0; u < 2; u++) {
+			const uint32_t g = g0 + u;
+			if (g < nsteps) {
+				if (KEEP) items4[(g << 5) + lane] = id[u];
+				process4(id[u], v[u], lane, F, D.P);
+			}
+		}
 	}
 }
 
@@ -211,7 +256,11 @@ void rad_launch_process(rad_ctx* c) {
 void rad_launch_process_view(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n, uint32_t kbase, bool keep_items) {
 	RadDev D = V;
 	D.h0 = V.h0 + s0; D.h1 = D.h0 + n; D.kbase = kbase;
-	if (keep_items) launch_process<true, true>(D, st); else launch_process<true, false>(D, st);
+	if (n < (uint32_t)kWarps && (D.RES & 127u) == 0) {         // k = 1 and other tiny launches
+		uint32_t bx = ((D.RES >> 7) + 15) / 16;                    // two steps per warp, eight warps per CTA
+		if (bx > 148u * 8u) bx = 148u * 8u;
+		if (keep_items) process_few_kernel<true><<<dim3(bx, n), 256, 0, st>>>(D); else process_few_kernel<false><<<dim3(bx, n), 256, 0, st>>>(D);
+	} else if (keep_items) launch_process<true, true>(D, st); else launch_process<true, false>(D, st);
 	c->launches++;
 	c->keys_dirty = false;
 }

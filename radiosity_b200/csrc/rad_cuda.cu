@@ -82,7 +82,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->ev_fork = nullptr; for (int l = 0; l < RAD_MAX_LANES; l++) { c->lane_stream[l] = nullptr; c->ev_lane[l] = nullptr; }
 	c->inline_area_forced = false; c->l2_group_mb = 1u << 20;   // default: the whole batch in one group (measured faster than L2-sized groups)
 	if (const char* e = getenv("RAD_L2_GROUP_MB")) { const int v = atoi(e); if (v >= 1) c->l2_group_mb = (uint32_t)v; }   // tuning knob
-	c->ring_failed = false;
+	c->ring_failed = false; c->lane_delta_done = false;
 	c->ring_mode = false; c->ring_sg = c->ring_rs = c->ring_proc_layers = 0; c->ring_ctas_per_sm = 0;
 	if (const char* e = getenv("RAD_RING")) c->ring_mode = atoi(e) != 0;      // opt-in: L2-resident key ring (raster_ring_kernel; measured slower than the raster lanes)
 	if (const char* e = getenv("RAD_RING_SG")) { const int v = atoi(e); if (v >= 1 && v <= 16) c->ring_sg = (uint32_t)v; }     // tuning knobs
@@ -410,8 +410,9 @@ static void enqueue_batch(rad_ctx* c, bool keep_items) {
 
 static int enqueue_batch_multi(rad_ctx* c, bool keep_items) {
 	rad_launch_select(c);
+	c->lane_delta_done = false;
 	rad_launch_raster_process(c, keep_items);
-	rad_launch_delta(c);
+	if (!c->lane_delta_done) rad_launch_delta(c);             // (paths without raster lanes: one kernel for the rank's slots)
 	if (c->peer_mode && c->d.xtwo) rad_launch_xreduce(c);
 	if (c->nccl_comm && !c->peer_mode) {
 		int rc = g_nccl.AllReduce(c->d.dB, c->d.dB, (size_t)3 * c->d.P, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream);
@@ -622,12 +623,13 @@ int rad_profile_batch(rad_ctx* c, float* ms6) {
 	auto mark = [&](int st) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); ev.push_back(e); stage.push_back(st); };
 	mark(-1);
 	rad_launch_select(c); mark(0);
+	c->lane_delta_done = false;
 	rad_launch_raster_process_marked(c, keep, [&](int st) { mark(st); });
 	const bool fuse = c->d.k == 1;
 	if (c->world > 1 && (c->nccl_comm || c->peer_mode)) {
 		// sharded batch (collective: every rank profiles the same batch): [3] = local dB (+ the reduce-scatter kernel of the
 		// two-shot exchange / ncclAllReduce), [5] = the update kernel including its wait for the peers
-		rad_launch_delta(c);
+		if (!c->lane_delta_done) rad_launch_delta(c);
 		if (c->peer_mode && c->d.xtwo) rad_launch_xreduce(c);
 		if (c->nccl_comm && !c->peer_mode) g_nccl.AllReduce(c->d.dB, c->d.dB, (size_t)3 * c->d.P, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream);
 		mark(3);
@@ -774,8 +776,9 @@ int rad_batch_partial(rad_ctx* c) {
 	if (c->peer_mode) { c->err = "rad_batch_partial: the host-mediated exchange is not available after rad_peer_init (dB lives in the exchange buffer)"; return RAD_E_STATE; }
 	const bool keep = (c->cfg.flags & RAD_FLAG_KEEP_ITEMBUFFER) != 0;
 	rad_launch_select(c);
+	c->lane_delta_done = false;
 	rad_launch_raster_process(c, keep);
-	rad_launch_delta(c);
+	if (!c->lane_delta_done) rad_launch_delta(c);
 	return sync_check(c);
 }
 int rad_read_delta(rad_ctx* c, float* dB3) {

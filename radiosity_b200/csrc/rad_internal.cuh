@@ -199,6 +199,7 @@ struct rad_ctx {
 	bool inline_area_forced;      // RAD_INLINE_AREA set: do not auto-tune the inline tier
 	bool ring_mode;               // RAD_RING=1 (opt-in): steady state through the L2-resident key ring instead of raster lanes + whole-batch key buffers
 	uint32_t ring_sg, ring_rs, ring_proc_layers;   // tuning knobs (0 = automatic): RAD_RING_SG, RAD_RING_RS, RAD_RING_PROC
+	bool lane_delta_done;         // multi-GPU: the raster lanes of the batch being enqueued have added their dB themselves (no whole-rank kernel needed)
 	bool ring_failed;             // a raster_ring_kernel launch was refused since the last check
 	int ring_ctas_per_sm;         // resident CTAs per SM of raster_ring_kernel (occupancy query, once)
 	uint32_t l2_group_mb;         // key-buffer footprint (MB) of one hemicube group of the fused path
@@ -219,7 +220,8 @@ void rad_launch_resolve_process(rad_ctx* c, bool keep_items);   // fused (all sl
 void rad_launch_raster_process(rad_ctx* c, bool keep_items);    // steady state: per L2-sized hemicube group raster -> fused process
 void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::function<void(int)>& mark);   // same, mark(stage) after each launch (1 set-up, 2 chunks, 4 process)
 void rad_launch_apply(rad_ctx* c, bool fuse_select); // S4..S6 (+ argmax of the new B for k==1)
-void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB
+void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB (whole rank, one kernel)
+void rad_launch_lane_delta(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n);   // multi-GPU: local dB of one raster lane's slots, added into the rank's planes
 void rad_launch_xreduce(rad_ctx* c);                // multi-GPU, fused two-shot exchange: this rank's slice of the summed dB
 void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update
 void rad_launch_argmax(rad_ctx* c);                 // k==1: prime selkey[parity] from the current B

@@ -326,11 +326,13 @@ __global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D, RadRing R) {
 		const float m1 = 0.01f * (n1.x * n1.x + n1.y * n1.y + n1.z * n1.z) * d2, m2 = 0.01f * (n2.x * n2.x + n2.y * n2.y + n2.z * n2.z) * d2;
 		const bool back = (s1 < 0.0f && s1 * s1 > m1 || m1 == 0.0f) && (s2 < 0.0f && s2 * s2 > m2 || m2 == 0.0f) && (m1 > 0.0f || m2 > 0.0f);
 		if (!back) {
-			// out[k]: bit v set if vertex v is clearly outside plane k.  planes: 0 c>=0 | 1..4 FRONT c-a,c+a,c-b,c+b |
-			// 5..7 UP b-a,b+a,b-c | 8..10 DOWN -b-a,-b+a,-b-c | 11..13 LEFT a-b,a+b,a-c | 14..16 RIGHT -a-b,-a+b,-a-c
-			unsigned out[17];
+			// g[k] = largest (h_k(v) + margin(v)) over the four vertices: negative <=> all of them are clearly outside plane k
+			// (h < -margin; margin(v) = sqrt(ctol) |r_v|, a hair wider than the squared form h^2 > ctol |r|^2 it replaces).
+			// planes: 0 c>=0 | 1..4 FRONT c-a,c+a,c-b,c+b | 5..7 UP b-a,b+a,b-c | 8..10 DOWN -b-a,-b+a,-b-c |
+			// 11..13 LEFT a-b,a+b,a-c | 14..16 RIGHT -a-b,-a+b,-a-c  (a+b = b+a, -a-b = -b-a, -a+b = b-a: 14 distinct values)
+			float g[14];
 			#pragma unroll
-			for (int k = 0; k < 17; k++) out[k] = 0;
+			for (int k = 0; k < 14; k++) g[k] = -3.0e38f;
 			const V3* vv[4] = { &q.a, &q.b, &q.c, &q.d };
 			#pragma unroll
 			for (int v = 0; v < 4; v++) {
@@ -338,18 +340,19 @@ __global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D, RadRing R) {
 				const float a = r.x * em.ax[0] + r.y * em.ax[1] + r.z * em.ax[2];
 				const float b = r.x * em.ax[3] + r.y * em.ax[4] + r.z * em.ax[5];
 				const float c = r.x * em.ax[6] + r.y * em.ax[7] + r.z * em.ax[8];
-				const float tol = em.ctol * (r.x * r.x + r.y * r.y + r.z * r.z);     // ((2e-3 + 3 dev) |r|)^2, see camera_emitter
-				const float h[17] = { c, c - a, c + a, c - b, c + b, b - a, b + a, b - c, -b - a, -b + a, -b - c, a - b, a + b, a - c, -a - b, -a + b, -a - c };
+				const float mr = sqrtf(em.ctol * (r.x * r.x + r.y * r.y + r.z * r.z)) * 1.0001f;     // ((2e-3 + 3 dev) |r|), see camera_emitter
+				const float am = a + mr, bm = b + mr, cm = c + mr, na = mr - a, nb = mr - b;
+				const float h[14] = { cm, cm - a, cm + a, cm - b, cm + b, bm - a, bm + a, bm - c, nb - a, nb + a, nb - c, am - b, am - c, na - c };
 				#pragma unroll
-				for (int k = 0; k < 17; k++) if (h[k] < 0.0f && h[k] * h[k] > tol) out[k] |= 1u << v;
+				for (int k = 0; k < 14; k++) g[k] = fmaxf(g[k], h[k]);
 			}
-			const bool below = out[0] == 15u;
+			const bool below = g[0] < 0.0f;
 			if (!below) {
-				if (!(out[5] == 15u || out[6] == 15u || out[7] == 15u)) faces |= 1u;          // UP
-				if (!(out[8] == 15u || out[9] == 15u || out[10] == 15u)) faces |= 2u;         // DOWN
-				if (!(out[11] == 15u || out[12] == 15u || out[13] == 15u)) faces |= 4u;       // LEFT
-				if (!(out[14] == 15u || out[15] == 15u || out[16] == 15u)) faces |= 8u;       // RIGHT
-				if (!(out[1] == 15u || out[2] == 15u || out[3] == 15u || out[4] == 15u)) faces |= 16u;   // FRONT
+				if (!(g[5] < 0.0f || g[6] < 0.0f || g[7] < 0.0f)) faces |= 1u;                     // UP: b-a, b+a, b-c
+				if (!(g[8] < 0.0f || g[9] < 0.0f || g[10] < 0.0f)) faces |= 2u;                    // DOWN: -b-a, -b+a, -b-c
+				if (!(g[11] < 0.0f || g[6] < 0.0f || g[12] < 0.0f)) faces |= 4u;                   // LEFT: a-b, a+b, a-c
+				if (!(g[8] < 0.0f || g[5] < 0.0f || g[13] < 0.0f)) faces |= 8u;                    // RIGHT: -a-b, -a+b, -a-c
+				if (!(g[1] < 0.0f || g[2] < 0.0f || g[3] < 0.0f || g[4] < 0.0f)) faces |= 16u;     // FRONT: c-a, c+a, c-b, c+b
 			}
 		}
 	}
@@ -955,7 +958,7 @@ void rad_launch_process_view(rad_ctx* c, const RadDev& V, cudaStream_t st, uint3
 // lane path, which needs every slot's key buffer at set-up time) and there are enough slots to pipeline.
 static bool ring_eligible(const rad_ctx* c, uint32_t nslots) {
 	const RadDev& D = c->d;
-	return c->ring_mode && !c->tile_mode && nslots >= 4 && D.k >= 4 && D.P > 0 && D.RES / D.P >= 8u && (D.RES & 127u) == 0;
+	return c->ring_mode && !c->tile_mode && c->world == 1 && nslots >= 4 && D.k >= 4 && D.P > 0 && D.RES / D.P >= 8u && (D.RES & 127u) == 0;
 }
 template <bool KEEP>
 static cudaError_t launch_ring_kernel(rad_ctx* c, const RadDev& D, RadRing& R) {

@@ -39,16 +39,29 @@ __device__ __forceinline__ void xb_wait(const RadDev& D, uint32_t row_off, uint3
 	}
 	__syncthreads();
 }
-// the block that finishes last publishes `seq` into this rank's slot of flag row `row_off` on every peer
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// Sequence protocol of the fused exchange: s = the sequence number in this rank's buffer = batches exchanged so far.  The
+// batch in flight writes plane set (s + 1) & 1 (local dB: the raster lanes' lane_delta_kernel, or the whole-rank apply_kernel<1>),
+// the FIRST kernel after that (xreduce_kernel, or apply_kernel<2> in the one-shot form) publishes s + 1 to every peer right
+// at its start — everything the stream ran before it is in this GPU's L2 — and xb_bump_kernel, right behind the update kernel, bumps s.
+__device__ __forceinline__ void xb_publish_now(const RadDev& D, uint32_t row_off, uint32_t seq) {
+	if (blockIdx.x == 0 && threadIdx.x < D.xworld) {
+		fence_acq_rel_sys();
+		st_release_sys(reinterpret_cast<uint32_t*>(D.xb[threadIdx.x] + row_off + 128 * D.xrank), seq);
+	}
+}
+// the block that finishes last publishes `seq` into this rank's slot of flag row `row_off` on every peer (row_off != 0)
+// and / or stores it as the new sequence number (bump_seq).  Release / acquire fences: the sequentially consistent
+// __threadfence_system() of every block serialises (tens of microseconds for a few hundred blocks).
 __device__ __forceinline__ void xb_publish_last(const RadDev& D, uint32_t row_off, uint32_t seq, bool bump_seq) {
 	__shared__ bool s_lastblk;
 	__syncthreads();
-	if (threadIdx.x == 0) { __threadfence_system(); const uint32_t done = atomicAdd(&D.ctl->ticket, 1u); s_lastblk = done == gridDim.x - 1; if (s_lastblk) D.ctl->ticket = 0; }
+	if (threadIdx.x == 0) { fence_acq_rel(); const uint32_t done = atomicAdd(&D.ctl->ticket, 1u); s_lastblk = done == gridDim.x - 1; if (s_lastblk) D.ctl->ticket = 0; }
 	__syncthreads();
 	if (!s_lastblk) return;
-	if (threadIdx.x == 0) { __threadfence_system(); if (bump_seq) *reinterpret_cast<volatile uint32_t*>(D.xb[D.xrank]) = seq; }
+	if (threadIdx.x == 0) { fence_acq_rel_sys(); if (bump_seq) *reinterpret_cast<volatile uint32_t*>(D.xb[D.xrank]) = seq; }
 	__syncthreads();
-	if (threadIdx.x < D.xworld) st_release_sys(reinterpret_cast<uint32_t*>(D.xb[threadIdx.x] + row_off + 128 * D.xrank), seq);
+	if (row_off && threadIdx.x < D.xworld) st_release_sys(reinterpret_cast<uint32_t*>(D.xb[threadIdx.x] + row_off + 128 * D.xrank), seq);
 }
 __device__ __forceinline__ uint32_t xb_slice(const RadDev& D) { return (D.P + D.xworld - 1) / D.xworld; }   // patches per rank slice
 
@@ -372,9 +385,12 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	uint32_t xseq = 0;
 	float* dB_out = D.dB;
 	if (fused) {
-		xseq = *reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]);
-		if (MODE == 1) dB_out = xb_planes(D, D.xrank, (xseq + 1) & 1u);
-		if (MODE == 2) xb_wait(D, D.xtwo ? RAD_XB_FLAG2 : 128, xseq);
+		xseq = *reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]) + 1u;     // the batch in flight (see xb_publish_now)
+		if (MODE == 1) dB_out = xb_planes(D, D.xrank, xseq & 1u);
+		if (MODE == 2) {
+			if (!D.xtwo) xb_publish_now(D, 128, xseq);
+			xb_wait(D, D.xtwo ? RAD_XB_FLAG2 : 128, xseq);
+		}
 	}
 	for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < P; i0 += gridDim.x * blockDim.x) {
 		const uint32_t i = i0 + threadIdx.x;
@@ -396,17 +412,32 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 		}
 		float bx = D.rad[i], by = D.rad[P + i], bz = D.rad[2 * (size_t)P + i];
 		if (MODE == 0) gather_transfer(D, s_em, 0, k, P, i, rho, bx, by, bz);
-		else if (!fused) { bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i]; }
-		else if (D.xtwo) {                                    // two-shot: the slice owner has already summed the ranks' planes
+		else if (!fused) {                                    // (dB is left zeroed: the raster lanes of the next batch add into it)
+			bx += D.dB[i]; by += D.dB[P + i]; bz += D.dB[2 * (size_t)P + i];
+			D.dB[i] = 0.0f; D.dB[P + i] = 0.0f; D.dB[2 * (size_t)P + i] = 0.0f;
+		} else if (D.xtwo) {                                  // two-shot: the slice owner has already summed the ranks' planes
 			const float* red = xb_reduced(D, i / xb_slice(D));
 			bx += __ldcg(red + i); by += __ldcg(red + D.xPmax + i); bz += __ldcg(red + 2 * (size_t)D.xPmax + i);
 		} else {
-			float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-			for (uint32_t r = 0; r < D.xworld; r++) {         // peer loads over NVLink, L1 bypassed
-				const float* pl = xb_planes(D, r, xseq & 1u);
-				sx += __ldcg(pl + i); sy += __ldcg(pl + D.xPmax + i); sz += __ldcg(pl + 2 * (size_t)D.xPmax + i);
+			// peer loads over NVLink, L1 bypassed: ALL ranks' values are requested before the first one is used (a warp is
+			// in-order: summing inside the load loop costs one NVLink round trip per rank, 44 us for 8 ranks at 16 k patches)
+			float vx[RAD_MAX_PEERS], vy[RAD_MAX_PEERS], vz[RAD_MAX_PEERS];
+			#pragma unroll
+			for (uint32_t r = 0; r < RAD_MAX_PEERS; r++) {
+				vx[r] = vy[r] = vz[r] = 0.0f;
+				if (r < D.xworld) {
+					const float* pl = xb_planes(D, r, xseq & 1u);
+					vx[r] = __ldcg(pl + i); vy[r] = __ldcg(pl + D.xPmax + i); vz[r] = __ldcg(pl + 2 * (size_t)D.xPmax + i);
+				}
 			}
+			float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+			#pragma unroll
+			for (uint32_t r = 0; r < RAD_MAX_PEERS; r++) if (r < D.xworld) { sx += vx[r]; sy += vy[r]; sz += vz[r]; }   // rank order
 			bx += sx; by += sy; bz += sz;
+		}
+		if (MODE == 2 && fused) {      // the plane set of the NEXT batch: every peer is done with it (it published this batch after its last update); the raster lanes add into it
+			float* nx = xb_planes(D, D.xrank, (xseq + 1u) & 1u);
+			nx[i] = 0.0f; nx[D.xPmax + i] = 0.0f; nx[2 * (size_t)D.xPmax + i] = 0.0f;
 		}
 		const int h = s_slot[threadIdx.x];
 		if (h != 0x7FFFFFFF) {
@@ -420,13 +451,9 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 		D.rad[i] = bx; D.rad[P + i] = by; D.rad[2 * (size_t)P + i] = bz;
 		if (fuse_select) best = max(best, energy_key_last(len2(bx, by, bz), i));
 	}
-	if (MODE == 1) {
-		if (!fused) return;
-		// the last block to finish publishes the planes: seq + 1 into this rank's flag slot on every peer
-		xb_publish_last(D, 128, xseq + 1, true);
-		return;
-	}
+	if (MODE == 1) return;                      // (published by the next kernel of the stream, see xb_publish_now)
 	if (blockIdx.x == 0 && threadIdx.x == 0) { D.ctl->batches_done += 1; D.ctl->shots_done += s_nvalid; }
+	// (the sequence number is bumped by xb_bump_kernel, the next launch: a "last block" ticket here costs every block a fence)
 	if (fuse_select) {
 		best = block_max(best);
 		if (threadIdx.x == 0 && best) atomicMax(&D.ctl->selkey[parity ^ 1], best);
@@ -445,19 +472,63 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 // (2 (G-1)/G P values cross NVLink per rank instead of (G-1) P).
 __global__ void __launch_bounds__(256) xreduce_kernel(RadDev D) {
 	if (D.stop_gate && D.ctl->gate) return;
-	const uint32_t xseq = *reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]);
+	const uint32_t xseq = *reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]) + 1u;
+	xb_publish_now(D, 128, xseq);
 	xb_wait(D, 128, xseq);
 	const uint32_t sz = xb_slice(D), lo = D.xrank * sz, hi = min(D.P, lo + sz);
 	float* red = xb_reduced(D, D.xrank);
 	for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
-		float sx = 0.0f, sy = 0.0f, sz3 = 0.0f;
-		for (uint32_t r = 0; r < D.xworld; r++) {
-			const float* pl = xb_planes(D, r, xseq & 1u);
-			sx += __ldcg(pl + i); sy += __ldcg(pl + D.xPmax + i); sz3 += __ldcg(pl + 2 * (size_t)D.xPmax + i);
+		float vx[RAD_MAX_PEERS], vy[RAD_MAX_PEERS], vz[RAD_MAX_PEERS];      // all requests first, then the sum in rank order
+		#pragma unroll
+		for (uint32_t r = 0; r < RAD_MAX_PEERS; r++) {
+			vx[r] = vy[r] = vz[r] = 0.0f;
+			if (r < D.xworld) {
+				const float* pl = xb_planes(D, r, xseq & 1u);
+				vx[r] = __ldcg(pl + i); vy[r] = __ldcg(pl + D.xPmax + i); vz[r] = __ldcg(pl + 2 * (size_t)D.xPmax + i);
+			}
 		}
+		float sx = 0.0f, sy = 0.0f, sz3 = 0.0f;
+		#pragma unroll
+		for (uint32_t r = 0; r < RAD_MAX_PEERS; r++) if (r < D.xworld) { sx += vx[r]; sy += vy[r]; sz3 += vz[r]; }
 		red[i] = sx; red[D.xPmax + i] = sy; red[2 * (size_t)D.xPmax + i] = sz3;
 	}
 	xb_publish_last(D, RAD_XB_FLAG2, xseq, false);
+}
+
+// the batch is exchanged: bump the sequence number (a launch of its own: every block of the update kernel reads it)
+__global__ void xb_bump_kernel(RadDev D) {
+	if (D.stop_gate && D.ctl->gate) return;
+	if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(D.xb[D.xrank]) += 1u;
+}
+
+// Multi-GPU, raster-lane form of the local dB: the slots [D.h0, D.h1) of ONE raster lane, right behind the lane's
+// ProcessHemicube on the lane's stream, so that the transfer of a finished lane overlaps the other lanes' rasterisation.
+// The lanes of a rank add into the same planes (red.global.add.f32; the planes start out zeroed, see apply_kernel<2>): the
+// sum's association differs from run to run like F's own, every replica reads the same published values.
+__global__ void __launch_bounds__(256) lane_delta_kernel(RadDev D) {
+	__shared__ EmLite s_loc[RAD_RING_SLOTS];
+	if (D.stop_gate && D.ctl->gate) return;
+	const uint32_t P = D.P, n = D.h1 - D.h0;
+	for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+		const uint32_t h = D.h0 + j;
+		const float4 a = D.emlite[2 * h], b = D.emlite[2 * h + 1];
+		const uint32_t vo = __float_as_uint(a.w), id = __float_as_uint(b.w);
+		EmLite l; l.S0 = a.x; l.S1 = a.y; l.S2 = a.z; l.valid = (vo && id < P) ? 1u : 0u; l.c0 = b.x; l.c1 = b.y; l.c2 = b.z; l.id = id;
+		s_loc[j] = l;
+	}
+	__syncthreads();
+	const EmLite* s_em = s_loc - D.h0;          // indexed by slot
+	const bool fused = D.xworld > 0;
+	float* out = fused ? xb_planes(D, D.xrank, (*reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]) + 1u) & 1u) : D.dB;
+	const size_t pl = fused ? D.xPmax : P;
+	const float rho = D.reflectivity;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+		float dx = 0.0f, dy = 0.0f, dz = 0.0f;
+		gather_transfer(D, s_em, D.h0, D.h1, P, i, rho, dx, dy, dz);
+		if (dx != 0.0f) atomicAdd(out + i, dx);
+		if (dy != 0.0f) atomicAdd(out + pl + i, dy);
+		if (dz != 0.0f) atomicAdd(out + 2 * pl + i, dz);
+	}
 }
 
 } // namespace
@@ -525,6 +596,14 @@ void rad_launch_delta(rad_ctx* c) {
 	apply_kernel<1><<<patch_grid(D.P, T), T, D.k * sizeof(EmLite), c->stream>>>(D, 0, 0);
 	c->launches++;
 }
+void rad_launch_lane_delta(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n) {
+	RadDev D = V;
+	D.h0 = V.h0 + s0; D.h1 = D.h0 + n;
+	const uint32_t T = apply_threads(D.P);
+	lane_delta_kernel<<<patch_grid(D.P, T), T, 0, st>>>(D);
+	c->launches++;
+	c->lane_delta_done = true;
+}
 void rad_launch_xreduce(rad_ctx* c) {
 	const RadDev& D = c->d;
 	const uint32_t slice = (D.P + D.xworld - 1) / D.xworld;
@@ -536,4 +615,5 @@ void rad_launch_finish(rad_ctx* c, bool fuse_select) {
 	const uint32_t T = apply_threads(D.P);
 	apply_kernel<2><<<patch_grid(D.P, T), T, D.k * sizeof(EmLite), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
 	c->launches++;
+	if (D.xworld > 0) { xb_bump_kernel<<<1, 32, 0, c->stream>>>(D); c->launches++; }
 }

@@ -175,3 +175,43 @@ def test_neighbours_dropped_when_the_scene_changes_size(api, orc, box):
     with pytest.raises(api.RadError):
         ctx.shade_vertices()
     ctx.close()
+
+
+def test_ring_path_is_bit_identical_to_the_lane_path(api, orc):
+    """RAD_RING=1 (opt-in): per-slot work lists + raster_ring_kernel (walk and ProcessHemicube in one cooperative kernel through
+    an L2-resident ring of key buffers, re-used under decreasing epoch tags).  Same item buffers as the oracle, and the same
+    state as the default path within float-atomic rounding — also when the ring is as small as it gets (2 stages of 1 slot)
+    and when a batch is larger than one launch group (k > 64).  The knob is read at context creation: child processes."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from radiosity_b200 import api
+        from oracle import orc
+        v, c, r, il = orc.scene_cornell(0.05)
+        N, k = 128, int(sys.argv[2])
+        ctx = api.Context(N, k, v.shape[0], select_mode=api.SELECT_TOPK, flags=api.FLAG_KEEP_ITEMBUFFER)
+        ctx.set_formfactors(api.formfactors(N)); ctx.upload_scene(v, c, r, il)
+        ids, valid = ctx.select()
+        st = ctx.shoot(1)
+        for h in range(0, k, max(1, k // 6)):
+            if valid[h]:
+                assert (ctx.read_itembuffer(h) == orc.render_hemicube(v, int(ids[h]), N)).all(), (h, ids[h])
+        ctx.upload_state(r, il)
+        st = ctx.shoot(20)
+        assert st.batches_done == 20 and st.queue_overflow == 0
+        rad, illum = ctx.download_state()
+        np.save(sys.argv[1], np.concatenate([rad.ravel(), illum.ravel()]))
+        print("ok")
+    """ % (root, os.path.join(root, "tests")))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    for k in (8, 96):
+        out = []
+        for env_extra in ({"RAD_RING": "0"}, {"RAD_RING": "1"}, {"RAD_RING": "1", "RAD_RING_SG": "1", "RAD_RING_RS": "2"}):
+            env = dict(os.environ, **env_extra)
+            path = os.path.join(root, "gpurun_out", "ring_%d_%s.npy" % (k, "_".join(env_extra.values())))
+            p = subprocess.run([sys.executable, "-c", code, path, str(k)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+            assert p.returncode == 0 and "ok" in p.stdout, p.stdout[-2000:]
+            out.append(np.load(path))
+        assert rel_l2(out[1], out[0]) < 1e-5 and rel_l2(out[2], out[0]) < 1e-5
