@@ -537,8 +537,9 @@ __device__ __forceinline__ void edge_origin(int ax, int ay, int bx, int by, int&
 //     same float operations as two separate triangle walks, in about half the pixel visits;
 //  2. chunks: one warp per (triangle, chunk) of at most tile x tile pixels, 8x4 pixels per step.
 // RING: every record of the list belongs to the slot whose key buffer is `ring_keys`; otherwise the record names its slot.
-// (Measured and dropped: the next step's records fetched into shared memory with cp.async during the walk — the walk got
-// slower, 0.371 against 0.331 ms per batch.)
+// (Measured and dropped: the next step's records fetched into shared memory with cp.async during the walk — 0.371 against
+// 0.331 ms per batch; both rows' keys computed first and the two REDs issued back to back from one asm block, against the
+// write-after-read waits on the REDs' operand registers — 0.342 against 0.333 ms.)
 template <bool RING>
 __device__ __forceinline__ void walk_small4(const RadDev& D, const uint4* __restrict__ qsm, uint32_t base, uint32_t nsm,
                                             unsigned long long* __restrict__ ring_keys, uint32_t tagsh, int lane) {
@@ -652,7 +653,7 @@ __device__ __forceinline__ void walk_chunk(const RadDev& D, const RadQueueEntry 
 	}
 }
 
-// persistent warps drain both queues of the launch (whole-batch key buffers: staged API, RAD_RING=0, micro-triangle scenes)
+// persistent warps drain both queues of the launch (whole-batch key buffers)
 __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
 	const int lane = threadIdx.x & 31;
 	const uint32_t tagsh = D.tag << 24;

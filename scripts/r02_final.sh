@@ -6,6 +6,7 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python bench.py > gpurun_out/r02_bench_config2.json 2> gpurun_out/r02_bench_config2.err; echo bench rc=$?; tail -2 gpurun_out/r02_bench_config2.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2>/dev/null
 RAD_RING=1 timeout 300 python bench.py --steps 5 --no-cpu-baseline --no-extras > gpurun_out/r02_bench_config2_ring.json 2>/dev/null
+timeout 120 python scripts/fuzz_parity.py --seconds 18 > gpurun_out/r02_fuzz_parity.json 2>/dev/null; tail -c 400 gpurun_out/r02_fuzz_parity.json; echo
 timeout 300 python scripts/sweep_config5.py > gpurun_out/r02_config5_resolution_sweep.json 2>/dev/null
 RAD_LANES=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_config2.csv python scripts/prof_batches.py --workload config2 --batches 2 --process-reps 2 2>&1 | tail -1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_config2_lanes.csv python scripts/prof_batches.py --workload config2 --batches 2 2>&1 | tail -1
