@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(kWarps * 32, FROM_KEYS ? 6 : 8) process_kernel
 // segadd.cuh.  grid: x = warps over the atlas, y = slot.
 template <bool KEEP>
 __global__ void __launch_bounds__(256) process_few_kernel(RadDev D) {
+	pdl_enter();
 	const uint32_t slot = D.h0 + blockIdx.y;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (D.qc->q_tris | D.qc->q_small | D.qc->n_pairs)) { D.qc->parked = D.qc->q_tris + D.qc->q_small; D.qc->q_tris = 0; D.qc->q_entries = 0; D.qc->q_small = 0; D.qc->n_pairs = 0; }
 	if (D.stop_gate && D.ctl->gate) return;
@@ -259,7 +260,8 @@ void rad_launch_process_view(rad_ctx* c, const RadDev& V, cudaStream_t st, uint3
 	if (n < (uint32_t)kWarps && (D.RES & 127u) == 0) {         // k = 1 and other tiny launches
 		uint32_t bx = ((D.RES >> 7) + 15) / 16;                    // two steps per warp, eight warps per CTA
 		if (bx > 148u * 8u) bx = 148u * 8u;
-		if (keep_items) process_few_kernel<true><<<dim3(bx, n), 256, 0, st>>>(D); else process_few_kernel<false><<<dim3(bx, n), 256, 0, st>>>(D);
+		if (keep_items) rad_launch_pdl(c->pdl, process_few_kernel<true>, dim3(bx, n), dim3(256), 0, st, D);
+		else rad_launch_pdl(c->pdl, process_few_kernel<false>, dim3(bx, n), dim3(256), 0, st, D);
 	} else if (keep_items) launch_process<true, true>(D, st); else launch_process<true, false>(D, st);
 	c->launches++;
 	c->keys_dirty = false;

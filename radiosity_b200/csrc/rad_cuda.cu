@@ -83,6 +83,8 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->inline_area_forced = false; c->l2_group_mb = 1u << 20;   // default: the whole batch in one group (measured faster than L2-sized groups)
 	if (const char* e = getenv("RAD_L2_GROUP_MB")) { const int v = atoi(e); if (v >= 1) c->l2_group_mb = (uint32_t)v; }   // tuning knob
 	c->ring_failed = false; c->lane_delta_done = false;
+	c->pdl = false;               // opt-in (RAD_PDL=1, k == 1 only): measured slower, 28.1 k against 30.1 k shots/s — the early CTAs of the next kernels take SM slots from the running one
+	if (const char* e = getenv("RAD_PDL")) c->pdl = cfg->hemicubes == 1 && atoi(e) != 0;
 	c->ring_mode = false; c->ring_sg = c->ring_rs = c->ring_proc_layers = 0; c->ring_ctas_per_sm = 0;
 	if (const char* e = getenv("RAD_RING")) c->ring_mode = atoi(e) != 0;      // opt-in: L2-resident key ring (raster_ring_kernel; measured slower than the raster lanes)
 	if (const char* e = getenv("RAD_RING_SG")) { const int v = atoi(e); if (v >= 1 && v <= 16) c->ring_sg = (uint32_t)v; }     // tuning knobs

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <string>
 #include <functional>
+#include <utility>
 #include "../../include/rad_cuda.h"
 
 #define RAD_NFACES 5
@@ -199,6 +200,7 @@ struct rad_ctx {
 	bool inline_area_forced;      // RAD_INLINE_AREA set: do not auto-tune the inline tier
 	bool ring_mode;               // RAD_RING=1 (opt-in): steady state through the L2-resident key ring instead of raster lanes + whole-batch key buffers
 	uint32_t ring_sg, ring_rs, ring_proc_layers;   // tuning knobs (0 = automatic): RAD_RING_SG, RAD_RING_RS, RAD_RING_PROC
+	bool pdl;                     // RAD_PDL=1 (opt-in, k == 1): the kernels of a shot are chained by programmatic dependent launches
 	bool lane_delta_done;         // multi-GPU: the raster lanes of the batch being enqueued have added their dB themselves (no whole-rank kernel needed)
 	bool ring_failed;             // a raster_ring_kernel launch was refused since the last check
 	int ring_ctas_per_sm;         // resident CTAs per SM of raster_ring_kernel (occupancy query, once)
@@ -234,6 +236,24 @@ void rad_launch_planes_to_aos3(rad_ctx* c, const float* planes, float* aos, uint
 void rad_launch_split_quads(rad_ctx* c, const float* verts12, uint32_t P);
 void rad_launch_nb_to_planes(rad_ctx* c, const int32_t* nb8, uint32_t P);
 void rad_launch_shade(rad_ctx* c, float* out12);   // shade.cu
+
+// Programmatic dependent launch (opt-in, RAD_PDL=1; k == 1: one hemicube per launch, the shot is a chain of five latency-bound kernels).  A
+// kernel launched through rad_launch_pdl with pdl = true may START while its predecessor in the stream is still running —
+// its CTAs get resident and run up to pdl_enter(), which returns once the predecessor has completed and its writes are
+// visible — so the launch latency of every link of the chain overlaps the previous kernel.  pdl_enter() must be the first
+// statement of such a kernel (it also lets the NEXT kernel start early); it is a no-op in a normal launch.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() { asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rad_launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+	return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 #define RAD_CUDA_TRY(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
 	(c)->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return RAD_E_CUDA; } } while (0)

@@ -34,6 +34,7 @@ namespace {
 // one block per hemicube slot: lanes 0..4 build the face matrices, lane 0 takes the snapshot (camera.cuh)
 __global__ void camera_kernel(RadDev D, int sel_parity) {
 	__shared__ RadEmitter s_e;
+	pdl_enter();
 	if (D.stop_gate && blockIdx.x == 0 && threadIdx.x == 0 && D.ctl->stopped) D.ctl->gate = 1;   // the previous batch was the last one (Main.cpp:1137,1298)
 	camera_block(D, blockIdx.x, sel_parity, &s_e);
 }
@@ -307,6 +308,7 @@ __device__ __forceinline__ void emit_tri(const RadDev& D, const QV& Q, const Tri
 // SL (ring path): the pairs of every slot go to the slot's own list (RadControl::slot[z].n_pairs, z-th share of D.pairs)
 template <bool SL>
 __global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D, RadRing R) {
+	pdl_enter();
 	const uint32_t slot = D.h0 + blockIdx.z;
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (D.stop_gate && p == 0 && blockIdx.z == 0 && D.ctl->stopped) D.ctl->gate = 1;   // first raster kernel of a batch: latch the stop test (k == 1 has no camera kernel)
@@ -480,6 +482,7 @@ __device__ __forceinline__ void setup_pairs(const RadDev& D, const QV& Q, uint32
 // work lists.  s_wbase = first warp step of every slot (running sum of ceil(pairs / 32)).
 template <int MINB, bool SL>
 __global__ void __launch_bounds__(128, MINB) raster_setup_kernel(RadDev D, RadRing R) {
+	pdl_enter();
 	const int lane = threadIdx.x & 31;
 	if (!SL) {
 		const uint32_t npairs = min(D.qc->n_pairs, D.pairs_cap);
@@ -655,6 +658,7 @@ __device__ __forceinline__ void walk_chunk(const RadDev& D, const RadQueueEntry 
 
 // persistent warps drain both queues of the launch (whole-batch key buffers)
 __global__ void __launch_bounds__(128) raster_queue_kernel(RadDev D) {
+	pdl_enter();
 	const int lane = threadIdx.x & 31;
 	const uint32_t tagsh = D.tag << 24;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -856,7 +860,7 @@ void rad_launch_atomic_bench(rad_ctx* c, uint32_t pattern, uint32_t steps, uint3
 }
 
 void rad_launch_camera(rad_ctx* c, int sel_parity) {
-	camera_kernel<<<c->d.k, 32, 0, c->stream>>>(c->d, sel_parity);
+	rad_launch_pdl(c->pdl, camera_kernel, dim3(c->d.k), dim3(32), 0, c->stream, c->d, sel_parity);
 	c->launches++;
 }
 
@@ -886,14 +890,14 @@ static RadDev lane_view(const rad_ctx* c, uint32_t lane, uint32_t L) {
 
 // exact stage: persistent grid over the surviving pairs (their number is only known on the device)
 template <bool SL>
-static void launch_setup_kernel(const RadDev& D, const RadRing& R, uint32_t n, cudaStream_t st) {
+static void launch_setup_kernel(const RadDev& D, const RadRing& R, uint32_t n, cudaStream_t st, bool pdl = false) {
 	uint64_t want = ((uint64_t)D.P * n * 2 + 127) / 128;      // typically ~1 of 5 (patch, face) pairs survives
 	static const int sctas = [] { const char* e = getenv("RAD_SETUP_CTAS"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 16 ? 16 : v); }();   // tuning knob: CTAs per SM of the set-up grid (3 = what fits; more only queue up behind the other lanes)
 	const uint32_t blocks = (uint32_t)(want < 148 ? 148 : (want > 148u * sctas ? 148u * sctas : want));
 	static const int minb = [] { const char* e = getenv("RAD_SETUP_MINB"); const int v = e ? atoi(e) : 3; return v < 3 ? 3 : (v > 5 ? 5 : v); }();   // tuning knob: resident CTAs per SM the set-up kernel is compiled for
-	if (minb == 3) raster_setup_kernel<3, SL><<<blocks, 128, 0, st>>>(D, R);
-	else if (minb == 4) raster_setup_kernel<4, SL><<<blocks, 128, 0, st>>>(D, R);
-	else raster_setup_kernel<5, SL><<<blocks, 128, 0, st>>>(D, R);
+	if (minb == 3) rad_launch_pdl(pdl, raster_setup_kernel<3, SL>, dim3(blocks), dim3(128), 0, st, D, R);
+	else if (minb == 4) rad_launch_pdl(pdl, raster_setup_kernel<4, SL>, dim3(blocks), dim3(128), 0, st, D, R);
+	else rad_launch_pdl(pdl, raster_setup_kernel<5, SL>, dim3(blocks), dim3(128), 0, st, D, R);
 }
 
 // slots [D.h0 + s0, +n) of the view V on stream st
@@ -908,16 +912,16 @@ static void launch_setup(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t 
 	// triangle gets one chunk entry (unused there: the bins cut it by atlas tile)
 	if (tiles) { D.inline_area = 0u; D.tile = 1u << 15; }
 	const RadRing R0 = {};
-	raster_cull_kernel<false><<<dim3((D.P + 255) / 256, 1, n), 256, 0, st>>>(D, R0);
+	rad_launch_pdl(c->pdl, raster_cull_kernel<false>, dim3((D.P + 255) / 256, 1, n), dim3(256), 0, st, D, R0);
 	// exact stage: persistent grid over the surviving pairs (their number is only known on the device)
-	launch_setup_kernel<false>(D, R0, n, st);
+	launch_setup_kernel<false>(D, R0, n, st, c->pdl);
 	c->launches += 2;
 }
 static void launch_chunks(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t kbase) {
 	RadDev D = V;
 	D.kbase = kbase;
 	static const int ctas = [] { const char* e = getenv("RAD_QUEUE_CTAS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();   // tuning knob: persistent CTAs per SM
-	raster_queue_kernel<<<148 * ctas, 128, 0, st>>>(D);
+	rad_launch_pdl(c->pdl, raster_queue_kernel, dim3(148 * ctas), dim3(128), 0, st, D);
 	c->launches++;
 }
 

@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(256) apply_kernel(RadDev D, int fuse_select, i
 	__shared__ int s_slot[256];            // first emitter slot of each patch of the current chunk (INT_MAX: none)
 	__shared__ int s_last_h, s_dups; __shared__ uint32_t s_nvalid;
 	const uint32_t P = D.P, k = D.k;
+	pdl_enter();
 	if (D.stop_gate && D.ctl->gate) return;     // the stop test fired in an earlier batch of this replay: the loop has ended (Main.cpp:1137)
 	if (threadIdx.x == 0) { s_last_h = -1; s_dups = 0; s_nvalid = 0; }
 	__syncthreads();
@@ -587,7 +588,7 @@ static uint32_t apply_threads(uint32_t P) { return P <= 148u * 8u * 64u ? 64u : 
 void rad_launch_apply(rad_ctx* c, bool fuse_select) {
 	const RadDev& D = c->d;
 	const uint32_t T = apply_threads(D.P);
-	apply_kernel<0><<<patch_grid(D.P, T), T, D.k * sizeof(EmLite), c->stream>>>(D, fuse_select ? 1 : 0, (int)c->parity);
+	rad_launch_pdl(c->pdl, apply_kernel<0>, dim3(patch_grid(D.P, T)), dim3(T), D.k * sizeof(EmLite), c->stream, D, fuse_select ? 1 : 0, (int)c->parity);
 	c->launches++;
 }
 void rad_launch_delta(rad_ctx* c) {
