@@ -400,6 +400,13 @@ def strong_scaling(B, name, steps=4, warmup=2):
         one = B.context(arrays, N, k, sharded=False)
         v1, ms1, _, _ = B.timed(one, batches, steps, warmup, collective=False, runs=runs)
         res.update(v1=v1, ms_per_step_1gpu=ms1, e2e_1gpu=B.e2e(one, r, il, batches, 2, 1, collective=False, runs=runs))
+        one.restore_state()
+        stage1 = np.zeros(6, np.float64)
+        for _ in range(4):
+            stage1 += one.profile_batch()
+        stage1 /= 4
+        res["stages_1gpu_ms_per_batch"] = {"select+camera": float(stage1[0]), "raster_setup": float(stage1[1]), "raster_queue": float(stage1[2]),
+                                           "process_hemicube": float(stage1[4]), "update": float(stage1[5])}
         one.restore_state(); one.shoot(batches - 1)
         r_less, _, _ = B.state_digest(one)              # (sanity of the comparison below: one batch less must NOT agree)
         one.restore_state(); one.shoot(batches)
@@ -409,6 +416,14 @@ def strong_scaling(B, name, steps=4, warmup=2):
     ctx = B.context(arrays, N, k, sharded=True)
     vN, msN, _, _ = B.timed(ctx, batches, steps, warmup, runs=runs)
     e2eN = B.e2e(ctx, r, il, batches, 2, 1, runs=runs)
+    # where the sharded batch goes: the stages of one batch un-graphed, back to back (collective: every rank profiles the same batches)
+    ctx.restore_state()
+    stage = np.zeros(6, np.float64)
+    for _ in range(4):
+        stage += ctx.profile_batch()
+    stage /= 4
+    res["stages_sharded_ms_per_batch"] = {"select+camera": float(stage[0]), "raster_setup": float(stage[1]), "raster_queue": float(stage[2]), "local_dB+exchange": float(stage[3]),
+                                          "process_hemicube": float(stage[4]), "update(incl. wait for peers)": float(stage[5])}
     ctx.restore_state(); ctx.shoot(batches)
     rad, illum, dig = B.state_digest(ctx)
     same = B.replicas_identical(dig)
