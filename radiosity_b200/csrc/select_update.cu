@@ -309,11 +309,12 @@ struct EmLite { float S0, S1, S2; uint32_t valid; float c0, c1, c2; uint32_t id;
 // kernel is a latency chain otherwise — then the slots are zeroed for the next batch (fill_n(p_tmp_formfactors, 0),
 // Main.cpp:1278).  Invalid (NULL) emitters are not read.
 constexpr int kFBatch = 16;
-__device__ __forceinline__ void take_F(const RadDev& D, const EmLite* s_em, uint32_t hb, uint32_t hend, uint32_t P, uint32_t i, float* f) {
+// (s_em[h - h_tab] = emitter of slot h: the table starts at slot h_tab)
+__device__ __forceinline__ void take_F(const RadDev& D, const EmLite* s_em, uint32_t h_tab, uint32_t hb, uint32_t hend, uint32_t P, uint32_t i, float* f) {
 	#pragma unroll
 	for (int j = 0; j < kFBatch; j++) {
 		const uint32_t h = hb + j;
-		f[j] = (h < hend && s_em[h].valid) ? __ldcs(D.F + (size_t)h * P + i) : 0.0f;
+		f[j] = (h < hend && s_em[h - h_tab].valid) ? __ldcs(D.F + (size_t)h * P + i) : 0.0f;
 	}
 	#pragma unroll
 	for (int j = 0; j < kFBatch; j++)
@@ -321,15 +322,15 @@ __device__ __forceinline__ void take_F(const RadDev& D, const EmLite* s_em, uint
 }
 // B += sum over slots [hb0, hend) of ((S_h * F_h[i]) * rho) (.) c_h, in slot order   (Main.cpp:1274)
 __device__ __forceinline__ void gather_transfer(const RadDev& D, const EmLite* s_em, uint32_t hb0, uint32_t hend, uint32_t P, uint32_t i, float rho,
-                                                float& bx, float& by, float& bz) {
+                                                float& bx, float& by, float& bz, uint32_t h_tab = 0) {
 	for (uint32_t hb = hb0; hb < hend; hb += kFBatch) {
 		float f[kFBatch];
-		take_F(D, s_em, hb, hend, P, i, f);
+		take_F(D, s_em, h_tab, hb, hend, P, i, f);
 		#pragma unroll
 		for (int j = 0; j < kFBatch; j++) {
 			const uint32_t h = hb + j;
 			if (h < hend) {
-				const EmLite e = s_em[h];
+				const EmLite e = s_em[h - h_tab];
 				if (e.valid) {
 					bx += ((e.S0 * f[j]) * rho) * e.c0;
 					by += ((e.S1 * f[j]) * rho) * e.c1;
@@ -518,14 +519,13 @@ __global__ void __launch_bounds__(256) lane_delta_kernel(RadDev D) {
 		s_loc[j] = l;
 	}
 	__syncthreads();
-	const EmLite* s_em = s_loc - D.h0;          // indexed by slot
 	const bool fused = D.xworld > 0;
 	float* out = fused ? xb_planes(D, D.xrank, (*reinterpret_cast<const volatile uint32_t*>(D.xb[D.xrank]) + 1u) & 1u) : D.dB;
 	const size_t pl = fused ? D.xPmax : P;
 	const float rho = D.reflectivity;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
 		float dx = 0.0f, dy = 0.0f, dz = 0.0f;
-		gather_transfer(D, s_em, D.h0, D.h1, P, i, rho, dx, dy, dz);
+		gather_transfer(D, s_loc, D.h0, D.h1, P, i, rho, dx, dy, dz, D.h0);
 		if (dx != 0.0f) atomicAdd(out + i, dx);
 		if (dy != 0.0f) atomicAdd(out + pl + i, dy);
 		if (dz != 0.0f) atomicAdd(out + 2 * pl + i, dz);
