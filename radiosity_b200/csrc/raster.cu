@@ -542,7 +542,8 @@ __device__ __forceinline__ void edge_origin(int ax, int ay, int bx, int by, int&
 // RING: every record of the list belongs to the slot whose key buffer is `ring_keys`; otherwise the record names its slot.
 // (Measured and dropped: the next step's records fetched into shared memory with cp.async during the walk — 0.371 against
 // 0.331 ms per batch; both rows' keys computed first and the two REDs issued back to back from one asm block, against the
-// write-after-read waits on the REDs' operand registers — 0.342 against 0.333 ms.)
+// write-after-read waits on the REDs' operand registers — 0.342 against 0.333 ms; prefetch.global.L2 of the next step's records
+// — 0.338 against 0.334 ms; every append of the set-up kernel ordered by walk length — no change in the walk, set-up slower.)
 template <bool RING>
 __device__ __forceinline__ void walk_small4(const RadDev& D, const uint4* __restrict__ qsm, uint32_t base, uint32_t nsm,
                                             unsigned long long* __restrict__ ring_keys, uint32_t tagsh, int lane) {
