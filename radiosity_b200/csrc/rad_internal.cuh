@@ -63,6 +63,7 @@ struct RadControl {               // small device-resident control block
 	                              // replay is a no-op (the loop of Main.cpp:1137 ends with the batch that stopped)
 	RadQueueCtl lane[RAD_MAX_LANES];
 	uint32_t ticket;              // blocks finished ("last block merges" pattern of the selection / update kernels)
+	uint32_t ref_fast;            // RAD_SELECT_REFERENCE, k > 1: the tie-free fast path has written the emitter list of this batch
 	uint32_t ring_abort;          // ring path watchdog: a wait inside raster_ring_kernel timed out (never expected; the call fails instead of hanging)
 };
 // Ring path (RadRing): work-list counters per hemicube slot of the launch and the stage hand-over between walk and process

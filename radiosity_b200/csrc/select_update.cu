@@ -119,6 +119,10 @@ __global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
 	__shared__ int s_n; __shared__ float s_min;
 	const uint32_t count = D.k;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	__shared__ uint32_t s_fast;
+	if (threadIdx.x == 0) s_fast = D.ctl->ref_fast;           // the tie-free fast path has written the list (topk_level_kernel, ref_mode)
+	__syncthreads();
+	if (s_fast) return;
 	if (threadIdx.x == 0) { s_n = 0; s_min = 0.0f; }
 	// warp 0: the list.  entry i < 32 in (eA, idA) of lane i, entry i >= 32 in (eB, idB) of lane i - 32
 	float eA = 0.0f, eB = 0.0f; uint32_t idA = 0u, idB = 0u; int n = 0;
@@ -252,21 +256,31 @@ __device__ __forceinline__ void block_topk(unsigned long long& a0, unsigned long
 	}
 }
 
+// ref_mode (RAD_SELECT_REFERENCE, k > 1): the fast path of the reference's list.  The list of ModelContainer.cpp:259-299 only
+// ever rejects a patch whose energy is below the list's last entry, and that entry's energy never decreases (it starts as
+// patch 0's): the final SET is the top-`count` of S = {0} + {i : |B_i|^2 > 0 and >= |B_0|^2}, and the final ORDER is by energy
+// wherever energies differ.  Ties are what makes the list history-dependent (every append reverses every tie group), so:
+// the level kernels select the top-(count + 1) of S (first level filters by |B_0|^2), and if those energies are pairwise
+// different — no tie inside the list, none across its end — the list is written here and select_reference_kernel, launched
+// behind, returns at once (RadControl::ref_fast); otherwise it runs its exact emulation.  14 of the 16 batches of the bench
+// run take the fast path (the fresh scene's 99 equal light patches are the other two).
 template <bool FIRST>
 __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const unsigned long long* __restrict__ in, uint32_t n_in,
-                                                                  unsigned long long* __restrict__ out, int keep, int finish) {
+                                                                  unsigned long long* __restrict__ out, int keep, int finish, int ref_mode) {
 	__shared__ unsigned long long s[kTopChunk];
 	__shared__ bool s_last;
 	const int t = threadIdx.x;
 	unsigned long long a[2];
+	const uint32_t e0b = (FIRST && ref_mode) ? __float_as_uint(len2(D.rad[0], D.rad[D.P], D.rad[2 * (size_t)D.P])) : 0u;
 	#pragma unroll
 	for (int r = 0; r < 2; r++) {
 		const uint32_t i = blockIdx.x * kTopChunk + t + r * 1024;
 		unsigned long long key = 0ull;
 		if (i < n_in) {
-			if (FIRST) {
+			if constexpr (FIRST) {
 				const uint32_t eb = __float_as_uint(len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i]));
-				if (eb != 0 && eb < 0x7F800000u) key = ((unsigned long long)eb << 32) | (0xFFFFFFFFu - i);
+				const bool in_s = !ref_mode || eb >= e0b;                         // (positive floats order like their bits)
+				if (eb != 0 && eb < 0x7F800000u && in_s) key = ((unsigned long long)eb << 32) | (0xFFFFFFFFu - i);
 			} else key = in[i];
 		}
 		a[r] = key;
@@ -288,6 +302,27 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 		int span = keep;
 		while ((uint32_t)span < nc) span <<= 1;
 		block_topk(a[0], a[1], s, t, keep, true, span);
+	}
+	if (ref_mode) {
+		// sorted descending in a[0] of threads [0, keep), keep > count: any two neighbours of equal energy among the first count + 1?
+		const uint32_t count = D.k;
+		__syncthreads();
+		if (t < keep) s[t] = a[0];
+		__syncthreads();
+		const uint32_t hi = (uint32_t)(a[0] >> 32);
+		const int tie = (uint32_t)t < count && hi != 0u && hi == (uint32_t)(s[t + 1] >> 32);
+		const int npos = __syncthreads_count((uint32_t)t < count && a[0] != 0ull);     // list entries with positive energy
+		const int ok = !__syncthreads_or(tie);
+		if (t == 0) D.ctl->ref_fast = ok ? 1u : 0u;
+		if (!ok) return;
+		const bool seed0 = __float_as_uint(len2(D.rad[0], D.rad[D.P], D.rad[2 * (size_t)D.P])) == 0u;   // the seeded patch 0 stays behind the positive ones while there is room
+		if ((uint32_t)t < count) {
+			const bool isseed = seed0 && t == npos;
+			D.em[t].id = a[0] ? 0xFFFFFFFFu - (uint32_t)(a[0] & 0xFFFFFFFFull) : 0u;
+			D.em[t].valid = (a[0] || isseed) ? 1u : 0u;
+			D.em[t].order = (uint32_t)t;
+		}
+		return;
 	}
 	if ((uint32_t)t < D.k) {
 		const uint32_t G = D.deal, slot = G > 1 ? ((uint32_t)t % G) * (D.k / G) + (uint32_t)t / G : (uint32_t)t;
@@ -553,12 +588,10 @@ void rad_launch_select(rad_ctx* c) {
 		if (!c->selkey_valid) { rad_launch_argmax(c); c->cam_valid = false; }
 		if (!c->cam_valid) rad_launch_camera(c, (int)c->parity);      // decodes the fused argmax key, then snapshot + MVPs
 		return;                                                       // (otherwise the previous update's tail already did)
-	} else if (c->cfg.select_mode == RAD_SELECT_REFERENCE) {
-		select_reference_kernel<<<1, 1024, 0, c->stream>>>(D);
-		c->launches++;
 	} else {
+		const bool ref = c->cfg.select_mode == RAD_SELECT_REFERENCE;
 		int keep = 64;
-		while ((uint32_t)keep < D.k) keep <<= 1;
+		while ((uint32_t)keep < D.k + (ref ? 1u : 0u)) keep <<= 1;             // reference list: one entry beyond its end (tie check)
 		uint32_t n = D.P;
 		const unsigned long long* in = nullptr;
 		unsigned long long* out = D.cand0;
@@ -566,11 +599,15 @@ void rad_launch_select(rad_ctx* c) {
 		for (;;) {
 			const uint32_t nb = (n + kTopChunk - 1) / kTopChunk;
 			const int fin = nb * (uint32_t)keep <= (uint32_t)kTopChunk;       // the level's last block can finish the selection
-			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin);
-			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin);
+			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, ref ? 1 : 0);
+			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, ref ? 1 : 0);
 			c->launches++;
 			if (fin) break;
 			n = nb * keep; in = out; out = out == D.cand0 ? D.cand1 : D.cand0; first = false;
+		}
+		if (ref) {                                                            // exact emulation of the list; a no-op after the fast path
+			select_reference_kernel<<<1, 1024, 0, c->stream>>>(D);
+			c->launches++;
 		}
 	}
 	rad_launch_camera(c);

@@ -215,3 +215,38 @@ def test_ring_path_is_bit_identical_to_the_lane_path(api, orc):
             assert p.returncode == 0 and "ok" in p.stdout, p.stdout[-2000:]
             out.append(np.load(path))
         assert rel_l2(out[1], out[0]) < 1e-5 and rel_l2(out[2], out[0]) < 1e-5
+
+
+@pytest.mark.parametrize("area", [0.5, 0.014])
+def test_reference_list_fast_path_and_fallback(api, orc, area):
+    """RAD_SELECT_REFERENCE, k > 1: when the top-(k + 1) energies of {0} + {i : |B_i|^2 > 0 and >= |B_0|^2} are pairwise different
+    the list of ModelContainer.cpp:259-299 is their top-k in energy order and is written by the top-k kernels (ref_mode);
+    any tie inside the list or across its end falls back to the exact emulation.  Both must equal the oracle's list: random
+    tie-free states with a dark / dim / bright patch 0, fewer candidates than slots, and ties planted inside and at the end."""
+    v, c, r, il = orc.scene_cornell(area)
+    P = v.shape[0]
+    rng = np.random.default_rng(11)
+
+    def state(e0, n_pos=None):
+        rad = (rng.random((P, 3), dtype=np.float32) + np.float32(0.05)).astype(np.float32)
+        if n_pos is not None:                       # only n_pos patches (besides patch 0) carry energy
+            keep = rng.choice(np.arange(1, P), n_pos, replace=False)
+            m = np.zeros(P, bool); m[keep] = True
+            rad[~m] = 0
+        rad[0] = np.float32(e0)
+        return rad
+
+    for k in (3, 10, 64):
+        ctx = api.Context(32, k, P, select_mode=api.SELECT_REFERENCE)
+        ctx.set_formfactors(api.formfactors(32)); ctx.upload_scene(v, c, r, il)
+        cases = [state(0.0), state(0.2), state(0.9), state(5.0), state(0.0, n_pos=5), state(0.3, n_pos=k - 1), state(0.0, n_pos=k), state(0.0, n_pos=k + 1)]
+        # ties: inside the list (two of the strongest patches equal), across its end (k-th and (k+1)-th equal), and with patch 0
+        t1 = state(0.0); order = np.argsort(-(t1.astype(np.float32) ** 2).sum(1, dtype=np.float32)); t1[order[1]] = t1[order[0]]; cases.append(t1)
+        t2 = state(0.0); order = np.argsort(-(t2.astype(np.float32) ** 2).sum(1, dtype=np.float32)); t2[order[k]] = t2[order[k - 1]]; cases.append(t2)
+        t3 = state(0.4); order = np.argsort(-(t3.astype(np.float32) ** 2).sum(1, dtype=np.float32)); t3[order[2]] = t3[0]; cases.append(t3)
+        for j, rad in enumerate(cases):
+            ctx.upload_state(rad, il)
+            ids, valid = ctx.select()
+            exp, nul = orc.select(rad, k, 0)
+            assert ids.tolist() == exp.tolist() and valid.tolist() == (1 - nul).tolist(), (k, j)
+        ctx.close()
