@@ -92,6 +92,13 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	if (const char* e = getenv("RAD_RING_PROC")) { const int v = atoi(e); if (v >= 1 && v <= 7) c->ring_proc_layers = (uint32_t)v; }
 	c->tile_mode = false; memset(&c->tl, 0, sizeof(c->tl));
 	if (const char* e = getenv("RAD_RASTER")) c->tile_mode = strcmp(e, "tiles") == 0;   // opt-in: tile-binned rasteriser (raster_tiles.cu)
+	c->spec = cfg->hemicubes == 1 && !(cfg->flags & RAD_FLAG_KEEP_ITEMBUFFER);
+	if (const char* e = getenv("RAD_SPEC")) c->spec = c->spec && atoi(e) != 0;
+	c->spec_slots = c->spec ? RAD_SPEC_SLOTS : 0u;
+	if (const char* e = getenv("RAD_SPEC_SLOTS")) { const int v = atoi(e); if (c->spec && v >= 8 && v <= RAD_SPEC_SLOTS) c->spec_slots = (uint32_t)v; }   // tuning knob
+	c->spec_graph = nullptr; c->spec_graph_batches = 0; c->spec_graph_launches = 0; c->spec_graph_stop = 0; c->spec_graph_epoch_after = 0; c->spec_blocks = 0; c->select_override = 0;
+	const uint32_t kslots = c->spec ? c->spec_slots : cfg->hemicubes;        // hemicube slots the buffers hold
+	c->key_slots = kslots;
 	RadDev& D = c->d;
 	memset(&D, 0, sizeof(D));
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
@@ -102,7 +109,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	// is tens of GB for a 1 M-patch scene: HBM capacity is what a B200 has to spare, and a whole batch per launch group is
 	// worth it.  Bounded by a third of the free memory (the raster then falls back to smaller hemicube groups).
 	{
-		const uint64_t kk = cfg->hemicubes < 64 ? cfg->hemicubes : 64;
+		const uint64_t kk = kslots < 64 ? kslots : 64;
 		size_t free_b = 0, total_b = 0;
 		cudaMemGetInfo(&free_b, &total_b);
 		const uint64_t budget = (uint64_t)free_b / 3;                         // bytes for the four lists
@@ -132,9 +139,10 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(v0, Pm)); A(dalloc(v1, Pm)); A(dalloc(v2, Pm));
 	A(dalloc(color, 3 * Pm)); A(dalloc(D.rad, 3 * Pm)); A(dalloc(D.illum, 3 * Pm));
 	A(dalloc(ff, (size_t)D.RES));
-	A(dalloc(D.keys, (size_t)D.k * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
-	A(dalloc(D.F, (size_t)D.k * Pm)); A(dalloc(D.dB, 3 * Pm));
-	A(dalloc(D.mvp, (size_t)D.k * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)D.k)); A(dalloc(D.emlite, 2 * (size_t)D.k)); A(dalloc(D.ctl, 1)); A(dalloc(D.rc, 1));
+	A(dalloc(D.keys, (size_t)kslots * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
+	A(dalloc(D.F, (size_t)kslots * Pm)); A(dalloc(D.dB, 3 * Pm));
+	A(dalloc(D.mvp, (size_t)kslots * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)kslots)); A(dalloc(D.emlite, 2 * (size_t)kslots)); A(dalloc(D.ctl, 1)); A(dalloc(D.rc, 1));
+	A(dalloc(D.spec_cand, (size_t)3 * 256));
 	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap)); A(dalloc(D.pairs, (size_t)D.pairs_cap)); A(dalloc(D.nb, 8 * Pm)); A(dalloc(D.shade_e, 3 * Pm));
 	A(dalloc(D.ework, Pm < RAD_MAX_HEMICUBES ? (size_t)RAD_MAX_HEMICUBES : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(proj, 16));
 	if (c->tile_mode) {
@@ -155,12 +163,12 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.v0 = v0; D.v1 = v1; D.v2 = v2; D.color = color; D.ff = ff; D.proj = proj;
 	D.qc = &D.ctl->lane[0];
 	cudaMemcpyAsync(proj, cfg->projection, 64, cudaMemcpyHostToDevice, c->stream);
-	cudaMemsetAsync(D.keys, 0xFF, (size_t)D.k * D.RES * 8, c->stream);
+	cudaMemsetAsync(D.keys, 0xFF, (size_t)kslots * D.RES * 8, c->stream);
 	cudaMemsetAsync(D.items, 0, (size_t)D.k * D.RES * 4, c->stream);
-	cudaMemsetAsync(D.F, 0, (size_t)D.k * Pm * 4, c->stream);
+	cudaMemsetAsync(D.F, 0, (size_t)kslots * Pm * 4, c->stream);
 	cudaMemsetAsync(D.dB, 0, 3 * Pm * 4, c->stream);
-	cudaMemsetAsync(D.em, 0, (size_t)D.k * sizeof(RadEmitter), c->stream);
-	cudaMemsetAsync(D.emlite, 0, 2 * (size_t)D.k * sizeof(float4), c->stream);
+	cudaMemsetAsync(D.em, 0, (size_t)kslots * sizeof(RadEmitter), c->stream);
+	cudaMemsetAsync(D.emlite, 0, 2 * (size_t)kslots * sizeof(float4), c->stream);
 	cudaMemsetAsync(D.ctl, 0, sizeof(RadControl), c->stream);
 	cudaMemsetAsync(D.rc, 0, sizeof(RadRingCtl), c->stream);
 	if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete c; return RAD_E_CUDA; }
@@ -170,6 +178,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 
 static void drop_graph(rad_ctx* c) {
 	if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_batches = 0; }
+	if (c->spec_graph) { cudaGraphExecDestroy(c->spec_graph); c->spec_graph = nullptr; c->spec_graph_batches = 0; }
 }
 
 int rad_destroy(rad_ctx* c) {
@@ -183,7 +192,7 @@ int rad_destroy(rad_ctx* c) {
 	RadDev& D = c->d;
 	cudaFree((void*)D.v0); cudaFree((void*)D.v1); cudaFree((void*)D.v2); cudaFree((void*)D.color);
 	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
-	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.emlite); cudaFree(D.ctl); cudaFree(D.rc);
+	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.emlite); cudaFree(D.ctl); cudaFree(D.rc); cudaFree(D.spec_cand);
 	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.pairs); cudaFree(D.nb); cudaFree(D.shade_e); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
 	if (c->tl.cnt) cudaFree(c->tl.cnt);
 	if (c->tl.base) cudaFree(c->tl.base);
@@ -425,6 +434,74 @@ static int enqueue_batch_multi(rad_ctx* c, bool keep_items) {
 	return RAD_OK;
 }
 
+// ---- speculative strict progressive refinement (k == 1; rad_ctx::spec) ------------------------------------------------------
+// One batch: the `nslots` strongest patches are selected with the argmax's tie rule, their hemicubes rendered and processed
+// through the raster lanes like any batch, then spec_apply_kernel replays the one-shot-at-a-time loop over them.  The
+// launchers read c->d: the batch view (k = spec_slots) is swapped in for the duration of the enqueue.
+static int enqueue_spec_batch(rad_ctx* c, uint32_t nslots, int stop_armed) {
+	const RadDev saved = c->d;
+	RadDev& S = c->d;
+	S.k = c->spec_slots; S.h0 = 0; S.h1 = nslots; S.spec = 1u; S.stop_gate = 1u; S.deal = 0u;
+	S.small_steps = RAD_SMALL_STEPS; S.tile = RAD_TILE;
+	c->select_override = 2;
+	cudaMemsetAsync(S.F, 0, (size_t)nslots * S.P * 4, c->stream);                 // the slots a cut-short batch did not use are not zeroed by anybody else
+	cudaMemsetAsync(&S.ctl->spec_key[0], 0, 3 * sizeof(unsigned long long), c->stream);
+	rad_launch_select(c);
+	rad_launch_raster_process(c, false);
+	const int r = rad_launch_spec_apply(c, S, nslots, stop_armed);
+	c->select_override = 0;
+	c->d = saved;
+	return r;
+}
+
+static int shoot_speculative(rad_ctx* c, uint32_t n_shots, int stop_test, const RadControl& ctl0, uint64_t* launches_out, RadControl* ctl_out) {
+	int r;
+	const uint32_t target = ctl0.shots_done + n_shots;
+	RAD_CUDA_TRY(c, cudaMemcpyAsync(&c->d.ctl->spec_target, &target, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	RAD_CUDA_TRY(c, cudaMemsetAsync(&c->d.ctl->spec_done, 0, sizeof(uint32_t), c->stream));
+	RAD_CUDA_TRY(c, cudaMemsetAsync(&c->d.ctl->gate, 0, sizeof(uint32_t), c->stream));
+	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));                            // (target is a stack variable)
+	uint64_t launches = 0;
+	uint32_t done = 0;
+	RadControl t = ctl0;
+	const uint32_t GB = 4, M = c->spec_slots;
+	while (done < n_shots) {
+		const uint32_t remaining = n_shots - done;
+		if (remaining >= GB * M) {
+			// a CUDA graph of GB full batches; batches behind the end of the call are gated on the device
+			if (!c->spec_graph || c->spec_graph_stop != (uint32_t)stop_test) {
+				if (c->spec_graph) { cudaGraphExecDestroy(c->spec_graph); c->spec_graph = nullptr; }
+				cudaGraph_t g = nullptr;
+				const uint32_t l0 = c->launches;
+				RAD_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+				rad_launch_clear_keys(c);
+				for (uint32_t b = 0; b < GB; b++) if ((r = enqueue_spec_batch(c, M, stop_test))) { cudaGraph_t junk; cudaStreamEndCapture(c->stream, &junk); return r; }
+				c->spec_graph_epoch_after = c->epoch;
+				RAD_CUDA_TRY(c, cudaStreamEndCapture(c->stream, &g));
+				RAD_CUDA_TRY(c, cudaGraphInstantiate(&c->spec_graph, g, 0));
+				cudaGraphDestroy(g);
+				c->spec_graph_batches = GB; c->spec_graph_stop = (uint32_t)stop_test;
+				c->spec_graph_launches = c->launches - l0; c->launches = l0;
+			}
+			RAD_CUDA_TRY(c, cudaGraphLaunch(c->spec_graph, c->stream));
+			launches += c->spec_graph_launches;
+			c->epoch = c->spec_graph_epoch_after;
+		} else {
+			uint32_t m = 8; while (m < remaining && m < M) m <<= 1;                 // a short tail renders only what it may need
+			if (m > M) m = M;
+			const uint32_t l0 = c->launches;
+			if ((r = enqueue_spec_batch(c, m, stop_test))) return r;
+			launches += c->launches - l0;
+		}
+		if ((r = read_ctl(c, &t))) return r;
+		done = t.shots_done - ctl0.shots_done;
+		if (t.spec_done) break;
+	}
+	c->selkey_valid = false; c->cam_valid = false;
+	*launches_out = launches; *ctl_out = t;
+	return RAD_OK;
+}
+
 int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 	int r = need_ready(c, "rad_shoot"); if (r) return r;
 	const bool keep = (c->cfg.flags & RAD_FLAG_KEEP_ITEMBUFFER) != 0;
@@ -478,6 +555,10 @@ int rad_shoot(rad_ctx* c, uint32_t n_batches, int stop_test, rad_stats* out) {
 			if (stop_test) { RadControl t; if ((r = read_ctl(c, &t))) return r; stopped = t.stopped != 0; }
 		}
 		launches += c->launches;
+	} else if (c->spec && c->d.k == 1 && !keep) {
+		RadControl t;
+		if ((r = shoot_speculative(c, n_batches, stop_test, ctl0, &launches, &t))) return r;
+		c->launches = 0;
 	} else {
 		if (c->d.k == 1 && !c->selkey_valid) rad_launch_argmax(c);
 		// steady state: a CUDA graph of GB batches (even, so that the k==1 key ping-pong returns to its start)

@@ -43,6 +43,7 @@ struct __align__(16) RadSmallQuad {
 #define RAD_XB_DATA 4096           // byte offset of the dB planes inside an exchange buffer
 #define RAD_XB_FLAG2 2048          // byte offset of the second flag row (two-shot exchange: reduced slices ready)
 #define RAD_MAX_LANES 8            // concurrent raster lanes (streams) a batch can be split into
+#define RAD_SPEC_SLOTS 64          // hemicubes rendered ahead of a strict-progressive (k == 1) run, see rad_ctx::spec
 #define RAD_RING_SLOTS 64          // hemicube slots one launch of the ring path renders (per-slot work lists, see RadRing)
 struct RadQueueCtl {              // work-list counters of one raster lane
 	uint32_t q_tris;              // chunk queue: triangles parked
@@ -54,6 +55,7 @@ struct RadQueueCtl {              // work-list counters of one raster lane
 };
 struct RadControl {               // small device-resident control block
 	unsigned long long selkey[2]; // k==1 selection: (E bits << 32 | id), ping-pong by batch parity
+	unsigned long long spec_key[3];   // speculative k == 1 path: the grid's argmax key of shot s in spec_key[s % 3]
 	uint32_t q_overflow;
 	uint32_t stopped;             // |lastEnergy| < 0.1 seen
 	float last_energy_len;
@@ -63,6 +65,9 @@ struct RadControl {               // small device-resident control block
 	                              // replay is a no-op (the loop of Main.cpp:1137 ends with the batch that stopped)
 	RadQueueCtl lane[RAD_MAX_LANES];
 	uint32_t ticket;              // blocks finished ("last block merges" pattern of the selection / update kernels)
+	uint32_t spec_target;         // speculative k == 1 path: shots_done at which the call ends
+	uint32_t spec_done;           // ... reached (or the stop test fired while armed): the batches still enqueued do nothing
+	uint32_t spec_hits, spec_misses;   // statistics: shots served from a rendered-ahead hemicube / batches cut short by a shooter outside the set
 	uint32_t ref_fast;            // RAD_SELECT_REFERENCE, k > 1: the tie-free fast path has written the emitter list of this batch
 	uint32_t ring_abort;          // ring path watchdog: a wait inside raster_ring_kernel timed out (never expected; the call fails instead of hanging)
 };
@@ -102,6 +107,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	uint32_t tag;                 // epoch tag (top byte of every key written / accepted by this launch)
 	uint32_t inline_area;         // bbox area (px) up to which the owning lane rasterises alone; larger -> chunk queue
 	uint32_t small_steps;         // longest quarter-warp walk (8 px per step) accepted by the small-quad queue
+	uint32_t spec;                // 1 in the view the speculative k == 1 path launches its batches with: the batch gate follows RadControl::spec_done
 	uint32_t stop_gate;           // rad_shoot(stop_test): batches enqueued after the one whose stop test fired do nothing (RadControl::gate)
 	uint32_t tile;                // chunk edge (px) of the chunk queue.  k == 1 is latency-bound (one hemicube cannot fill the
 	                              // GPU): shorter walks and smaller chunks there, longer ones for batches
@@ -127,6 +133,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	RadEmitter* em;               // [k]
 	float4* emlite;               // [k][2] what the update kernel needs of an emitter: (S, valid | order << 1), (colour, id)
 	RadControl* ctl;
+	float4* spec_cand;            // [3][blocks] (argmax key, B of that patch) of every block of spec_apply_kernel, by shot % 3
 	RadRingCtl* rc;               // ring path: per-slot work-list counters + stage hand-over (see RadRingCtl)
 	RadQueueCtl* qc;              // this launch's lane counters (= &ctl->lane[lane])
 	RadBigTri* q_tri; RadQueueEntry* q_ent;
@@ -201,6 +208,14 @@ struct rad_ctx {
 	bool inline_area_forced;      // RAD_INLINE_AREA set: do not auto-tune the inline tier
 	bool ring_mode;               // RAD_RING=1 (opt-in): steady state through the L2-resident key ring instead of raster lanes + whole-batch key buffers
 	uint32_t ring_sg, ring_rs, ring_proc_layers;   // tuning knobs (0 = automatic): RAD_RING_SG, RAD_RING_RS, RAD_RING_PROC
+	// Speculative strict progressive refinement (k == 1, default; RAD_SPEC=0: one hemicube per launch).  F_h depends on the
+	// geometry only, so the hemicubes of the RAD_SPEC_SLOTS currently strongest patches are rendered and processed as ONE
+	// batch (raster lanes, full GPU), and spec_apply_kernel then replays the reference's one-shot-at-a-time loop over them:
+	// argmax of the CURRENT B, transfer with the S of that moment, emitter update, stop test — exactly the k == 1 semantics.
+	// A shot whose shooter is not among the rendered ones ends the batch; the next batch is selected from the state reached.
+	uint32_t key_slots;           // hemicube slots the key / F / emitter buffers hold (hemicubes, or RAD_SPEC_SLOTS for a speculative k == 1 context)
+	bool spec; uint32_t spec_slots; cudaGraphExec_t spec_graph; uint32_t spec_graph_batches, spec_graph_launches, spec_graph_stop, spec_graph_epoch_after; int spec_blocks;
+	int select_override;          // 0: cfg.select_mode; 2: top-k with the argmax's tie rule (higher id first) — the speculative path's candidate set
 	bool pdl;                     // RAD_PDL=1 (opt-in, k == 1): the kernels of a shot are chained by programmatic dependent launches
 	bool lane_delta_done;         // multi-GPU: the raster lanes of the batch being enqueued have added their dB themselves (no whole-rank kernel needed)
 	bool ring_failed;             // a raster_ring_kernel launch was refused since the last check
@@ -227,6 +242,7 @@ void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB (whol
 void rad_launch_lane_delta(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n);   // multi-GPU: local dB of one raster lane's slots, added into the rank's planes
 void rad_launch_xreduce(rad_ctx* c);                // multi-GPU, fused two-shot exchange: this rank's slice of the summed dB
 void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update
+int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t nslots, int stop_armed);   // speculative k == 1 path: the sequential part (cooperative launch)
 void rad_launch_argmax(rad_ctx* c);                 // k==1: prime selkey[parity] from the current B
 void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out);
 void rad_launch_tiles_view(rad_ctx* c, const RadDev& V, const RadTiles& T, cudaStream_t st, uint32_t s0, uint32_t n, bool keep_items,

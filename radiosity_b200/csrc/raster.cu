@@ -35,7 +35,7 @@ namespace {
 __global__ void camera_kernel(RadDev D, int sel_parity) {
 	__shared__ RadEmitter s_e;
 	pdl_enter();
-	if (D.stop_gate && blockIdx.x == 0 && threadIdx.x == 0 && D.ctl->stopped) D.ctl->gate = 1;   // the previous batch was the last one (Main.cpp:1137,1298)
+	if (D.stop_gate && blockIdx.x == 0 && threadIdx.x == 0 && (D.spec ? D.ctl->spec_done : D.ctl->stopped)) D.ctl->gate = 1;   // the previous batch was the last one (Main.cpp:1137,1298)
 	camera_block(D, blockIdx.x, sel_parity, &s_e);
 }
 
@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(256) raster_cull_kernel(RadDev D, RadRing R) {
 	pdl_enter();
 	const uint32_t slot = D.h0 + blockIdx.z;
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (D.stop_gate && p == 0 && blockIdx.z == 0 && D.ctl->stopped) D.ctl->gate = 1;   // first raster kernel of a batch: latch the stop test (k == 1 has no camera kernel)
+	if (D.stop_gate && p == 0 && blockIdx.z == 0 && (D.spec ? D.ctl->spec_done : D.ctl->stopped)) D.ctl->gate = 1;   // first raster kernel of a batch: latch the stop test (k == 1 has no camera kernel)
+	if (D.spec && D.ctl->gate) return;            // speculative path: batches behind the end of the call render nothing (the camera kernel has latched the gate)
 	const bool live = p < D.P;
 	Quad q;
 	if (live) q = load_quad(D, p);
@@ -1103,7 +1104,7 @@ void rad_launch_resolve(rad_ctx* c, bool) {
 
 void rad_launch_clear_keys(rad_ctx* c) {
 	const RadDev& D = c->d;
-	clear_keys_kernel<<<148 * 8, 256, 0, c->stream>>>(D.keys, (size_t)D.k * D.RES);
+	clear_keys_kernel<<<148 * 8, 256, 0, c->stream>>>(D.keys, (size_t)c->key_slots * D.RES);   // every buffer: the epoch is shared by all of them
 	c->launches++;
 	c->keys_dirty = false;
 	c->epoch = 254;

@@ -15,6 +15,7 @@
 // reject-below-minimum while not full, tie groups reversed by every insertion); RAD_SELECT_TOPK runs a
 // tournament of block-wide bitonic sorts over keys (bits << 32 | ~id): energy desc, id asc.
 #include "rad_internal.cuh"
+#include <cooperative_groups.h>
 #include "camera.cuh"
 
 namespace {
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 	__shared__ bool s_last;
 	const int t = threadIdx.x;
 	unsigned long long a[2];
-	const uint32_t e0b = (FIRST && ref_mode) ? __float_as_uint(len2(D.rad[0], D.rad[D.P], D.rad[2 * (size_t)D.P])) : 0u;
+	const uint32_t e0b = (FIRST && ref_mode == 1) ? __float_as_uint(len2(D.rad[0], D.rad[D.P], D.rad[2 * (size_t)D.P])) : 0u;
 	#pragma unroll
 	for (int r = 0; r < 2; r++) {
 		const uint32_t i = blockIdx.x * kTopChunk + t + r * 1024;
@@ -279,8 +280,8 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 		if (i < n_in) {
 			if constexpr (FIRST) {
 				const uint32_t eb = __float_as_uint(len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i]));
-				const bool in_s = !ref_mode || eb >= e0b;                         // (positive floats order like their bits)
-				if (eb != 0 && eb < 0x7F800000u && in_s) key = ((unsigned long long)eb << 32) | (0xFFFFFFFFu - i);
+				const bool in_s = ref_mode != 1 || eb >= e0b;                         // (positive floats order like their bits)
+				if (eb != 0 && eb < 0x7F800000u && in_s) key = ((unsigned long long)eb << 32) | (ref_mode == 2 ? i : 0xFFFFFFFFu - i);   // 2: ties -> higher id first, the argmax's rule
 			} else key = in[i];
 		}
 		a[r] = key;
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 		while ((uint32_t)span < nc) span <<= 1;
 		block_topk(a[0], a[1], s, t, keep, true, span);
 	}
-	if (ref_mode) {
+	if (ref_mode == 1) {
 		// sorted descending in a[0] of threads [0, keep), keep > count: any two neighbours of equal energy among the first count + 1?
 		const uint32_t count = D.k;
 		__syncthreads();
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 	}
 	if ((uint32_t)t < D.k) {
 		const uint32_t G = D.deal, slot = G > 1 ? ((uint32_t)t % G) * (D.k / G) + (uint32_t)t / G : (uint32_t)t;
-		D.em[slot].id = a[0] ? 0xFFFFFFFFu - (uint32_t)(a[0] & 0xFFFFFFFFull) : 0u;
+		D.em[slot].id = a[0] ? (ref_mode == 2 ? (uint32_t)(a[0] & 0xFFFFFFFFull) : 0xFFFFFFFFu - (uint32_t)(a[0] & 0xFFFFFFFFull)) : 0u;
 		D.em[slot].valid = a[0] ? 1u : 0u;
 		D.em[slot].order = (uint32_t)t;
 	}
@@ -567,6 +568,112 @@ __global__ void __launch_bounds__(256) lane_delta_kernel(RadDev D) {
 	}
 }
 
+// ---- speculative strict progressive refinement (k == 1), the sequential part -------------------------------------------
+// The hemicubes of the `nslots` strongest patches (D.em[0 .. nslots), chosen by the top-k kernels with the argmax's own tie
+// rule) have been rendered and processed: F[s] is complete for every slot.  This kernel replays the reference's loop over
+// them, one shot at a time (Main.cpp:1137-1309 with HEMICUBES_CNT = 1): shooter = argmax of the CURRENT |B|^2 (largest energy,
+// last index among equals, nothing to do when everything is dark), S = B of that patch at this moment, B_i += ((S F[i]) rho) c,
+// emitter update, stop test — the arithmetic of apply_kernel<0>, shot by shot.  The radiosities stay in registers (PPT patches
+// per thread, the grid covers all patches); per shot the blocks agree on the argmax through one 64-bit atomicMax and ONE grid
+// barrier (three keys in rotation: the key of shot s + 1 is reset before the barrier of shot s, read last in shot s - 2), and
+// every block publishes the B of its own candidate next to its key, so the winner's S needs no second barrier.  A shooter that
+// is not among the rendered slots ends the batch (the caller selects the next batch from the state reached); the first shot
+// of a batch always hits, its shooter is slot 0 by construction.
+template <int PPT>
+__global__ void __launch_bounds__(1024, 1) spec_apply_kernel(RadDev D, uint32_t nslots, int stop_armed) {
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	__shared__ uint32_t s_id[RAD_SPEC_SLOTS], s_used[RAD_SPEC_SLOTS];
+	__shared__ unsigned long long s_key;
+	__shared__ int s_slot;
+	if (D.ctl->gate) return;                    // (grid-uniform: latched by the camera kernel of this batch)
+	const uint32_t P = D.P, tid = threadIdx.x, stride = gridDim.x * 1024u, i0 = blockIdx.x * 1024u + tid;
+	if (tid < RAD_SPEC_SLOTS) { s_id[tid] = (tid < nslots && D.em[tid].valid) ? D.em[tid].id : 0xFFFFFFFFu; s_used[tid] = 0u; }
+	float bx[PPT], by[PPT], bz[PPT];
+	#pragma unroll
+	for (int j = 0; j < PPT; j++) {
+		const uint32_t i = i0 + (uint32_t)j * stride;
+		bx[j] = by[j] = bz[j] = 0.0f;
+		if (i < P) { bx[j] = D.rad[i]; by[j] = D.rad[P + i]; bz[j] = D.rad[2 * (size_t)P + i]; }
+	}
+	const uint32_t target = D.ctl->spec_target, done0 = D.ctl->shots_done;
+	const float rho = D.reflectivity;
+	uint32_t count = 0; int ended = 0, missed = 0;      // ended: the call is over (target reached, stop test, everything dark)
+	__syncthreads();
+	for (uint32_t shot = 0; done0 + count < target; shot++) {
+		unsigned long long mine = 0ull;
+		#pragma unroll
+		for (int j = 0; j < PPT; j++) {
+			const uint32_t i = i0 + (uint32_t)j * stride;
+			if (i < P) { const unsigned long long kk = energy_key_last(len2(bx[j], by[j], bz[j]), i); mine = kk > mine ? kk : mine; }
+		}
+		const unsigned long long blockbest = block_max(mine);
+		const uint32_t rk = shot % 3u;
+		if (tid == 0) {
+			s_key = blockbest;
+			if (blockbest) atomicMax(&D.ctl->spec_key[rk], blockbest);
+			if (blockIdx.x == 0) D.ctl->spec_key[(shot + 1u) % 3u] = 0ull;
+		}
+		__syncthreads();
+		if (mine != 0ull && mine == s_key) {        // this thread owns the block's candidate: its B rides along with the key
+			#pragma unroll
+			for (int j = 0; j < PPT; j++) {
+				const uint32_t i = i0 + (uint32_t)j * stride;
+				if (i == (uint32_t)(mine & 0xFFFFFFFFull)) D.spec_cand[rk * 256u + blockIdx.x] = make_float4(bx[j], by[j], bz[j], 0.0f);
+			}
+		}
+		__threadfence();
+		grid.sync();
+		const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&D.ctl->spec_key[rk]);
+		if (key == 0ull) {                          // everything is dark: the remaining shots shoot patch 0 with S = 0 (Main.cpp:1161: no-ops that still count)
+			count = target - done0; ended = 1;
+			if (blockIdx.x == 0 && tid == 0) { D.ctl->last_energy_len = 0.0f; D.ctl->stopped = 1; }
+			break;
+		}
+		const uint32_t shooter = (uint32_t)(key & 0xFFFFFFFFull);
+		if (tid == 0) s_slot = -1;
+		__syncthreads();
+		if (tid < nslots && s_id[tid] == shooter && !s_used[tid]) s_slot = (int)tid;
+		__syncthreads();
+		const int slot = s_slot;
+		if (slot < 0) { missed = 1; break; }        // not rendered ahead: the batch ends here
+		const float4 Sv = __ldcg(D.spec_cand + rk * 256u + (shooter >> 10) % gridDim.x);     // the owner block's candidate IS the winner
+		const float c0 = __ldg(D.color + shooter), c1 = __ldg(D.color + P + shooter), c2 = __ldg(D.color + 2 * (size_t)P + shooter);
+		const float* __restrict__ F = D.F + (size_t)slot * P;
+		#pragma unroll
+		for (int j = 0; j < PPT; j++) {
+			const uint32_t i = i0 + (uint32_t)j * stride;
+			if (i < P) {
+				const float f = __ldcg(F + i);
+				bx[j] += ((Sv.x * f) * rho) * c0; by[j] += ((Sv.y * f) * rho) * c1; bz[j] += ((Sv.z * f) * rho) * c2;
+				if (i == shooter) {                  // emitter update (Main.cpp:1286-1295): lastEnergy before the subtraction
+					D.illum[i] += Sv.x; D.illum[P + i] += Sv.y; D.illum[2 * (size_t)P + i] += Sv.z;
+					bx[j] -= Sv.x; by[j] -= Sv.y; bz[j] -= Sv.z;
+				}
+			}
+		}
+		// the stop test on the emitter's energy after the transfer, before the subtraction — every block evaluates the same floats
+		const float fs = __ldcg(F + shooter);
+		const float ex = Sv.x + ((Sv.x * fs) * rho) * c0, ey = Sv.y + ((Sv.y * fs) * rho) * c1, ez = Sv.z + ((Sv.z * fs) * rho) * c2;
+		const float l = sqrtf(len2(ex, ey, ez));
+		const bool stop_now = (double)l < 0.1;       // Main.cpp:1298
+		if (blockIdx.x == 0 && tid == 0) { D.ctl->last_energy_len = l; if (stop_now) D.ctl->stopped = 1; }
+		if (tid == 0) s_used[slot] = 1u;
+		count++;
+		if (stop_armed && stop_now) { ended = 1; break; }
+		__syncthreads();
+	}
+	#pragma unroll
+	for (int j = 0; j < PPT; j++) {
+		const uint32_t i = i0 + (uint32_t)j * stride;
+		if (i < P) { D.rad[i] = bx[j]; D.rad[P + i] = by[j]; D.rad[2 * (size_t)P + i] = bz[j]; }
+	}
+	if (blockIdx.x == 0 && tid == 0) {
+		D.ctl->shots_done = done0 + count; D.ctl->batches_done += count;
+		D.ctl->spec_hits += count; D.ctl->spec_misses += (uint32_t)missed;
+		if (ended || done0 + count >= target) D.ctl->spec_done = 1;
+	}
+}
+
 } // namespace
 
 static uint32_t patch_grid(uint32_t P, uint32_t threads) {
@@ -589,7 +696,8 @@ void rad_launch_select(rad_ctx* c) {
 		if (!c->cam_valid) rad_launch_camera(c, (int)c->parity);      // decodes the fused argmax key, then snapshot + MVPs
 		return;                                                       // (otherwise the previous update's tail already did)
 	} else {
-		const bool ref = c->cfg.select_mode == RAD_SELECT_REFERENCE;
+		const bool ref = c->cfg.select_mode == RAD_SELECT_REFERENCE && c->select_override == 0;
+		const int mode = c->select_override ? c->select_override : (ref ? 1 : 0);
 		int keep = 64;
 		while ((uint32_t)keep < D.k + (ref ? 1u : 0u)) keep <<= 1;             // reference list: one entry beyond its end (tie check)
 		uint32_t n = D.P;
@@ -599,8 +707,8 @@ void rad_launch_select(rad_ctx* c) {
 		for (;;) {
 			const uint32_t nb = (n + kTopChunk - 1) / kTopChunk;
 			const int fin = nb * (uint32_t)keep <= (uint32_t)kTopChunk;       // the level's last block can finish the selection
-			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, ref ? 1 : 0);
-			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, ref ? 1 : 0);
+			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, mode);
+			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, mode);
 			c->launches++;
 			if (fin) break;
 			n = nb * keep; in = out; out = out == D.cand0 ? D.cand1 : D.cand0; first = false;
@@ -641,6 +749,30 @@ void rad_launch_lane_delta(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_
 	lane_delta_kernel<<<patch_grid(D.P, T), T, 0, st>>>(D);
 	c->launches++;
 	c->lane_delta_done = true;
+}
+// the grid covers every patch: blocks of 1024 threads, one per SM at most (co-resident: the kernel has a grid barrier per shot)
+int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t nslots, int stop_armed) {
+	int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->cfg.device);
+	uint32_t nb = (S.P + 1023u) / 1024u;
+	if (nb > (uint32_t)nsm) nb = (uint32_t)nsm;
+	if (nb > 256u) nb = 256u;
+	if (nb < 1u) nb = 1u;
+	const uint32_t ppt = (S.P + nb * 1024u - 1u) / (nb * 1024u);
+	const void* fn = nullptr;
+	if (ppt <= 1) fn = (const void*)spec_apply_kernel<1>; else if (ppt <= 2) fn = (const void*)spec_apply_kernel<2>; else if (ppt <= 4) fn = (const void*)spec_apply_kernel<4>;
+	else if (ppt <= 8) fn = (const void*)spec_apply_kernel<8>; else if (ppt <= 16) fn = (const void*)spec_apply_kernel<16>;
+	else { c->err = "speculative k = 1 path: too many patches per SM (set RAD_SPEC=0)"; return RAD_E_ARG; }
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(nb); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+	cfg.attrs = at; cfg.numAttrs = 1;
+	RadDev D = S;
+	void* args[3] = { (void*)&D, (void*)&nslots, (void*)&stop_armed };
+	const cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+	c->launches++;
+	if (e != cudaSuccess) { c->err = std::string("spec_apply_kernel launch: ") + cudaGetErrorString(e); return RAD_E_CUDA; }
+	return RAD_OK;
 }
 void rad_launch_xreduce(rad_ctx* c) {
 	const RadDev& D = c->d;

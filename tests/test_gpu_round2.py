@@ -250,3 +250,53 @@ def test_reference_list_fast_path_and_fallback(api, orc, area):
             exp, nul = orc.select(rad, k, 0)
             assert ids.tolist() == exp.tolist() and valid.tolist() == (1 - nul).tolist(), (k, j)
         ctx.close()
+
+
+def test_speculative_strict_progressive_equals_the_one_shot_loop(api, orc):
+    """k = 1 (default path): the hemicubes of the 64 strongest patches are rendered as one batch and spec_apply_kernel replays
+    the reference's one-shot-at-a-time loop over them (argmax of the current B, S of that moment, emitter update, stop test).
+    Same shots, same state as the oracle's strict loop and as the one-hemicube-per-launch path (RAD_SPEC=0) — on the
+    direct-launch path (short runs, odd counts), on the CUDA-graph path (>= 256 shots) and across calls."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    v, c, r, il = orc.scene_cornell(0.5)
+    N = 64
+    # against the oracle, in-process (default = speculative)
+    ctx = api.Context(N, 1, v.shape[0])
+    ctx.set_formfactors(api.formfactors(N)); ctx.upload_scene(v, c, r, il)
+    total = 0
+    for n in (1, 37, 300, 2):
+        st = ctx.shoot(n)
+        assert st.batches_done == n and st.shots_done == n and st.queue_overflow == 0
+        total += n
+    rad, illum = ctx.download_state()
+    orad, oillum, sched, *_ = orc.shoot(v, c, r, il, N, 1, total)
+    assert rel_l2(rad, orad) < 1e-3 and rel_l2(illum, oillum) < 1e-3
+    # a converged scene: every further shot is the reference's no-op shot of patch 0 and still counts
+    ctx.upload_state(np.zeros_like(r), il)
+    st = ctx.shoot(500)
+    assert st.batches_done == 500 and st.stopped == 1
+    ctx.close()
+    # against the one-hemicube-per-launch path (the knob is read at context creation: child processes)
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        from radiosity_b200 import api
+        from oracle import orc
+        v, c, r, il = orc.scene_cornell(0.05)
+        ctx = api.Context(128, 1, v.shape[0])
+        ctx.set_formfactors(api.formfactors(128)); ctx.upload_scene(v, c, r, il)
+        st = ctx.shoot(700)
+        assert st.batches_done == 700 and st.shots_done == 700
+        rad, illum = ctx.download_state()
+        np.save(sys.argv[1], np.concatenate([rad.ravel(), illum.ravel()]))
+        print("ok")
+    """ % root)
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    out = []
+    for spec in ("1", "0"):
+        path = os.path.join(root, "gpurun_out", "spec_%s.npy" % spec)
+        p = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, RAD_SPEC=spec), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0 and "ok" in p.stdout, p.stdout[-2000:]
+        out.append(np.load(path))
+    assert rel_l2(out[0], out[1]) < 1e-5
