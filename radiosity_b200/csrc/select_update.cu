@@ -14,6 +14,7 @@
 // For k > 1: RAD_SELECT_REFERENCE runs a one-block emulation of the reference's list (seeded patch 0,
 // reject-below-minimum while not full, tie groups reversed by every insertion); RAD_SELECT_TOPK runs a
 // tournament of block-wide bitonic sorts over keys (bits << 32 | ~id): energy desc, id asc.
+#include <stdlib.h>
 #include "rad_internal.cuh"
 #include <cooperative_groups.h>
 #include "camera.cuh"
@@ -621,8 +622,7 @@ __global__ void __launch_bounds__(1024, 1) spec_apply_kernel(RadDev D, uint32_t 
 				if (i == (uint32_t)(mine & 0xFFFFFFFFull)) D.spec_cand[rk * 256u + blockIdx.x] = make_float4(bx[j], by[j], bz[j], 0.0f);
 			}
 		}
-		__threadfence();
-		grid.sync();
+		grid.sync();                                // (orders the candidates and the key for every thread of the grid; no fence of our own: a fence in every thread serialises)
 		const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&D.ctl->spec_key[rk]);
 		if (key == 0ull) {                          // everything is dark: the remaining shots shoot patch 0 with S = 0 (Main.cpp:1161: no-ops that still count)
 			count = target - done0; ended = 1;
@@ -757,7 +757,10 @@ int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t nslots, int stop
 	if (nb > (uint32_t)nsm) nb = (uint32_t)nsm;
 	if (nb > 256u) nb = 256u;
 	if (nb < 1u) nb = 1u;
-	const uint32_t ppt = (S.P + nb * 1024u - 1u) / (nb * 1024u);
+	uint32_t ppt = (S.P + nb * 1024u - 1u) / (nb * 1024u);
+	// (fewer, fuller blocks do not pay: the per-thread work of a shot, not the grid barrier, is what a shot waits for)
+	static const uint32_t min_ppt = [] { const char* e = getenv("RAD_SPEC_PPT"); const int v = e ? atoi(e) : 1; return (uint32_t)(v < 1 ? 1 : (v > 16 ? 16 : v)); }();   // tuning knob (measured: 1 is best — 86 k shots/s against 76 k at 4 and 54 k at 16 on config 2)
+	if (ppt < min_ppt) { ppt = min_ppt; nb = (S.P + ppt * 1024u - 1u) / (ppt * 1024u); if (nb < 1u) nb = 1u; }
 	const void* fn = nullptr;
 	if (ppt <= 1) fn = (const void*)spec_apply_kernel<1>; else if (ppt <= 2) fn = (const void*)spec_apply_kernel<2>; else if (ppt <= 4) fn = (const void*)spec_apply_kernel<4>;
 	else if (ppt <= 8) fn = (const void*)spec_apply_kernel<8>; else if (ppt <= 16) fn = (const void*)spec_apply_kernel<16>;
