@@ -674,6 +674,111 @@ __global__ void __launch_bounds__(1024, 1) spec_apply_kernel(RadDev D, uint32_t 
 	}
 }
 
+// Cluster form of the same loop for scenes that fit ONE thread-block cluster (P <= 16 x 1024 x PPT patches): the 16 CTAs
+// exchange their argmax candidates (key + B of that patch) through distributed shared memory — every CTA stores its candidate
+// into all 16 CTAs' tables, double-buffered by shot parity — and meet at the hardware cluster barrier instead of a grid
+// barrier through global memory.  Everything else is spec_apply_kernel.
+template <int PPT>
+__global__ void __launch_bounds__(1024, 1) spec_apply_cluster_kernel(RadDev D, uint32_t nslots, int stop_armed) {
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster();
+	__shared__ uint32_t s_id[RAD_SPEC_SLOTS], s_used[RAD_SPEC_SLOTS];
+	__shared__ unsigned long long s_key;
+	__shared__ float4 s_cand;
+	__shared__ int s_slot;
+	__shared__ unsigned long long c_key[2][16];
+	__shared__ float4 c_S[2][16];
+	if (D.ctl->gate) return;                    // (uniform over the cluster)
+	const uint32_t P = D.P, tid = threadIdx.x, NB = cluster.num_blocks(), rank = cluster.block_rank(), stride = NB * 1024u, i0 = rank * 1024u + tid;
+	if (tid < RAD_SPEC_SLOTS) { s_id[tid] = (tid < nslots && D.em[tid].valid) ? D.em[tid].id : 0xFFFFFFFFu; s_used[tid] = 0u; }
+	float bx[PPT], by[PPT], bz[PPT];
+	#pragma unroll
+	for (int j = 0; j < PPT; j++) {
+		const uint32_t i = i0 + (uint32_t)j * stride;
+		bx[j] = by[j] = bz[j] = 0.0f;
+		if (i < P) { bx[j] = D.rad[i]; by[j] = D.rad[P + i]; bz[j] = D.rad[2 * (size_t)P + i]; }
+	}
+	const uint32_t target = D.ctl->spec_target, done0 = D.ctl->shots_done;
+	const float rho = D.reflectivity;
+	uint32_t count = 0; int ended = 0, missed = 0;
+	cluster.sync();                              // every CTA of the cluster is running: its shared memory may be written
+	for (uint32_t shot = 0; done0 + count < target; shot++) {
+		unsigned long long mine = 0ull;
+		#pragma unroll
+		for (int j = 0; j < PPT; j++) {
+			const uint32_t i = i0 + (uint32_t)j * stride;
+			if (i < P) { const unsigned long long kk = energy_key_last(len2(bx[j], by[j], bz[j]), i); mine = kk > mine ? kk : mine; }
+		}
+		const unsigned long long blockbest = block_max(mine);
+		const uint32_t par = shot & 1u;
+		if (tid == 0) s_key = blockbest;
+		__syncthreads();
+		if (mine != 0ull && mine == s_key) {
+			#pragma unroll
+			for (int j = 0; j < PPT; j++) {
+				const uint32_t i = i0 + (uint32_t)j * stride;
+				if (i == (uint32_t)(mine & 0xFFFFFFFFull)) s_cand = make_float4(bx[j], by[j], bz[j], 0.0f);
+			}
+		}
+		__syncthreads();
+		if (tid < NB) {                              // this CTA's candidate into CTA tid's table
+			*cluster.map_shared_rank(&c_key[par][rank], tid) = s_key;
+			*cluster.map_shared_rank(&c_S[par][rank], tid) = s_cand;
+		}
+		cluster.sync();
+		unsigned long long key = 0ull; uint32_t owner = 0;
+		#pragma unroll
+		for (uint32_t r = 0; r < 16u; r++) if (r < NB) { const unsigned long long kk = c_key[par][r]; if (kk > key) { key = kk; owner = r; } }
+		if (key == 0ull) {
+			count = target - done0; ended = 1;
+			if (rank == 0 && tid == 0) { D.ctl->last_energy_len = 0.0f; D.ctl->stopped = 1; }
+			break;
+		}
+		const uint32_t shooter = (uint32_t)(key & 0xFFFFFFFFull);
+		if (tid == 0) s_slot = -1;
+		__syncthreads();
+		if (tid < nslots && s_id[tid] == shooter && !s_used[tid]) s_slot = (int)tid;
+		__syncthreads();
+		const int slot = s_slot;
+		if (slot < 0) { missed = 1; break; }
+		const float4 Sv = c_S[par][owner];
+		const float c0 = __ldg(D.color + shooter), c1 = __ldg(D.color + P + shooter), c2 = __ldg(D.color + 2 * (size_t)P + shooter);
+		const float* __restrict__ F = D.F + (size_t)slot * P;
+		#pragma unroll
+		for (int j = 0; j < PPT; j++) {
+			const uint32_t i = i0 + (uint32_t)j * stride;
+			if (i < P) {
+				const float f = __ldcg(F + i);
+				bx[j] += ((Sv.x * f) * rho) * c0; by[j] += ((Sv.y * f) * rho) * c1; bz[j] += ((Sv.z * f) * rho) * c2;
+				if (i == shooter) {
+					D.illum[i] += Sv.x; D.illum[P + i] += Sv.y; D.illum[2 * (size_t)P + i] += Sv.z;
+					bx[j] -= Sv.x; by[j] -= Sv.y; bz[j] -= Sv.z;
+				}
+			}
+		}
+		const float fs = __ldcg(F + shooter);
+		const float ex = Sv.x + ((Sv.x * fs) * rho) * c0, ey = Sv.y + ((Sv.y * fs) * rho) * c1, ez = Sv.z + ((Sv.z * fs) * rho) * c2;
+		const float l = sqrtf(len2(ex, ey, ez));
+		const bool stop_now = (double)l < 0.1;
+		if (rank == 0 && tid == 0) { D.ctl->last_energy_len = l; if (stop_now) D.ctl->stopped = 1; }
+		if (tid == 0) s_used[slot] = 1u;
+		count++;
+		if (stop_armed && stop_now) { ended = 1; break; }
+		__syncthreads();
+	}
+	#pragma unroll
+	for (int j = 0; j < PPT; j++) {
+		const uint32_t i = i0 + (uint32_t)j * stride;
+		if (i < P) { D.rad[i] = bx[j]; D.rad[P + i] = by[j]; D.rad[2 * (size_t)P + i] = bz[j]; }
+	}
+	if (rank == 0 && tid == 0) {
+		D.ctl->shots_done = done0 + count; D.ctl->batches_done += count;
+		D.ctl->spec_hits += count; D.ctl->spec_misses += (uint32_t)missed;
+		if (ended || done0 + count >= target) D.ctl->spec_done = 1;
+	}
+	cluster.sync();                              // nobody leaves while a peer may still store into its tables
+}
+
 } // namespace
 
 static uint32_t patch_grid(uint32_t P, uint32_t threads) {
@@ -761,6 +866,30 @@ int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t nslots, int stop
 	// (fewer, fuller blocks do not pay: the per-thread work of a shot, not the grid barrier, is what a shot waits for)
 	static const uint32_t min_ppt = [] { const char* e = getenv("RAD_SPEC_PPT"); const int v = e ? atoi(e) : 1; return (uint32_t)(v < 1 ? 1 : (v > 16 ? 16 : v)); }();   // tuning knob (measured: 1 is best — 86 k shots/s against 76 k at 4 and 54 k at 16 on config 2)
 	if (ppt < min_ppt) { ppt = min_ppt; nb = (S.P + ppt * 1024u - 1u) / (ppt * 1024u); if (nb < 1u) nb = 1u; }
+	// one thread-block cluster of 16 CTAs when the scene fits it (hardware cluster barrier + distributed shared memory per shot)
+	// (opt-in, RAD_SPEC_CLUSTER=1: parity-green and no faster, 88.1 k against 89.0 k shots/s on config 2 — a shot is not waiting for its barrier)
+	static const bool use_cluster = [] { const char* e = getenv("RAD_SPEC_CLUSTER"); return e && atoi(e) != 0; }();
+	if (use_cluster && S.P <= 16u * 1024u * 4u) {
+		const uint32_t cppt = (S.P + 16u * 1024u - 1u) / (16u * 1024u);
+		const void* cfn = cppt <= 1 ? (const void*)spec_apply_cluster_kernel<1> : (cppt <= 2 ? (const void*)spec_apply_cluster_kernel<2> : (const void*)spec_apply_cluster_kernel<4>);
+		static bool attr_done = false;
+		if (!attr_done) {
+			cudaFuncSetAttribute(spec_apply_cluster_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+			cudaFuncSetAttribute(spec_apply_cluster_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+			cudaFuncSetAttribute(spec_apply_cluster_kernel<4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+			attr_done = true;
+		}
+		cudaLaunchConfig_t ccfg = {};
+		ccfg.gridDim = dim3(16); ccfg.blockDim = dim3(1024); ccfg.dynamicSmemBytes = 0; ccfg.stream = c->stream;
+		cudaLaunchAttribute cat[1];
+		cat[0].id = cudaLaunchAttributeClusterDimension; cat[0].val.clusterDim.x = 16; cat[0].val.clusterDim.y = 1; cat[0].val.clusterDim.z = 1;
+		ccfg.attrs = cat; ccfg.numAttrs = 1;
+		RadDev Dc = S;
+		void* cargs[3] = { (void*)&Dc, (void*)&nslots, (void*)&stop_armed };
+		const cudaError_t ce = cudaLaunchKernelExC(&ccfg, cfn, cargs);
+		if (ce == cudaSuccess) { c->launches++; return RAD_OK; }
+		cudaGetLastError();                      // (a device that cannot place the cluster: the grid form below)
+	}
 	const void* fn = nullptr;
 	if (ppt <= 1) fn = (const void*)spec_apply_kernel<1>; else if (ppt <= 2) fn = (const void*)spec_apply_kernel<2>; else if (ppt <= 4) fn = (const void*)spec_apply_kernel<4>;
 	else if (ppt <= 8) fn = (const void*)spec_apply_kernel<8>; else if (ppt <= 16) fn = (const void*)spec_apply_kernel<16>;
