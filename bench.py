@@ -50,7 +50,7 @@ WORKLOADS = {
 }
 # runs per step: a step repeats the workload's run (restore the fresh state, shoot) so that the timed region of the default
 # K = 20 steps is well over a second (the state restore is a 400 KB device copy outside the device-timed rad_shoot)
-RUNS_PER_STEP = {"config1": 50, "config2": 10, "config3": 2, "config4": 2, "config2_k1": 2}
+RUNS_PER_STEP = {"config1": 50, "config2": 10, "config3": 2, "config4": 2, "config2_k1": 10}
 
 
 def measured_peak():
