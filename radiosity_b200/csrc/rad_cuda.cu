@@ -95,10 +95,15 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	c->spec = cfg->hemicubes == 1 && !(cfg->flags & RAD_FLAG_KEEP_ITEMBUFFER);
 	if (const char* e = getenv("RAD_SPEC")) c->spec = c->spec && atoi(e) != 0;
 	c->spec_slots = c->spec ? RAD_SPEC_SLOTS : 0u;
+	c->spec_overlap = false;      // opt-in (RAD_SPEC_OVERLAP=1): the sequential kernel running beside the raster lanes is starved — 14.5 k against 88.4 k shots/s
+	c->sel_base = c->sel_count = c->sel_excl = c->sel_excl_n = c->cam_base = c->cam_count = c->last_lanes = 0; c->defer_join = false;
+	if (const char* e = getenv("RAD_SPEC_OVERLAP")) c->spec_overlap = c->spec && atoi(e) != 0;
 	if (const char* e = getenv("RAD_SPEC_SLOTS")) { const int v = atoi(e); if (c->spec && v >= 8 && v <= RAD_SPEC_SLOTS) c->spec_slots = (uint32_t)v; }   // tuning knob
 	c->spec_graph = nullptr; c->spec_graph_batches = 0; c->spec_graph_launches = 0; c->spec_graph_stop = 0; c->spec_graph_epoch_after = 0; c->spec_blocks = 0; c->select_override = 0;
-	const uint32_t kslots = c->spec ? c->spec_slots : cfg->hemicubes;        // hemicube slots the buffers hold
+	const uint32_t kslots = c->spec ? (c->spec_overlap ? (uint32_t)RAD_SPEC_POOL : c->spec_slots) : cfg->hemicubes;        // hemicube slots the buffers hold
 	c->key_slots = kslots;
+	const uint32_t kbufs = kslots > 64u && c->spec ? 64u : kslots;             // key buffers: a speculative context renders 64 slots at a time into buffers 0 .. 63
+	c->key_bufs = kbufs;
 	RadDev& D = c->d;
 	memset(&D, 0, sizeof(D));
 	D.N = cfg->hemicube_side; D.W = 2 * D.N; D.H = D.N + D.N / 2; D.RES = D.W * D.H; D.k = cfg->hemicubes;
@@ -139,7 +144,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(v0, Pm)); A(dalloc(v1, Pm)); A(dalloc(v2, Pm));
 	A(dalloc(color, 3 * Pm)); A(dalloc(D.rad, 3 * Pm)); A(dalloc(D.illum, 3 * Pm));
 	A(dalloc(ff, (size_t)D.RES));
-	A(dalloc(D.keys, (size_t)kslots * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
+	A(dalloc(D.keys, (size_t)kbufs * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
 	A(dalloc(D.F, (size_t)kslots * Pm)); A(dalloc(D.dB, 3 * Pm));
 	A(dalloc(D.mvp, (size_t)kslots * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)kslots)); A(dalloc(D.emlite, 2 * (size_t)kslots)); A(dalloc(D.ctl, 1)); A(dalloc(D.rc, 1));
 	A(dalloc(D.spec_cand, (size_t)3 * 256));
@@ -163,7 +168,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	D.v0 = v0; D.v1 = v1; D.v2 = v2; D.color = color; D.ff = ff; D.proj = proj;
 	D.qc = &D.ctl->lane[0];
 	cudaMemcpyAsync(proj, cfg->projection, 64, cudaMemcpyHostToDevice, c->stream);
-	cudaMemsetAsync(D.keys, 0xFF, (size_t)kslots * D.RES * 8, c->stream);
+	cudaMemsetAsync(D.keys, 0xFF, (size_t)kbufs * D.RES * 8, c->stream);
 	cudaMemsetAsync(D.items, 0, (size_t)D.k * D.RES * 4, c->stream);
 	cudaMemsetAsync(D.F, 0, (size_t)kslots * Pm * 4, c->stream);
 	cudaMemsetAsync(D.dB, 0, 3 * Pm * 4, c->stream);
@@ -435,22 +440,45 @@ static int enqueue_batch_multi(rad_ctx* c, bool keep_items) {
 }
 
 // ---- speculative strict progressive refinement (k == 1; rad_ctx::spec) ------------------------------------------------------
-// One batch: the `nslots` strongest patches are selected with the argmax's tie rule, their hemicubes rendered and processed
-// through the raster lanes like any batch, then spec_apply_kernel replays the one-shot-at-a-time loop over them.  The
-// launchers read c->d: the batch view (k = spec_slots) is swapped in for the duration of the enqueue.
-static int enqueue_spec_batch(rad_ctx* c, uint32_t nslots, int stop_armed) {
-	const RadDev saved = c->d;
+// The launchers read c->d: the batch view (k = the slots the context holds) is swapped in for the duration of an enqueue.
+struct SpecView {
+	rad_ctx* c; RadDev saved;
+	explicit SpecView(rad_ctx* c_) : c(c_), saved(c_->d) {
+		RadDev& S = c->d;
+		S.k = c->key_slots; S.spec = 1u; S.stop_gate = 1u; S.deal = 0u; S.small_steps = RAD_SMALL_STEPS; S.tile = RAD_TILE;
+	}
+	~SpecView() { c->d = saved; c->select_override = 0; c->cam_count = 0; c->sel_count = 0; c->sel_excl_n = 0; c->defer_join = false; }
+};
+// render ahead: the `n` strongest patches (the argmax's tie rule; patches waiting in em[excl .. +excl_n) left out) go to
+// em[base .. +n), cameras, hemicubes + ProcessHemicube through the raster lanes.  defer: the lanes are left running
+// (rad_join_lanes) so that the sequential kernel of the OTHER half overlaps them.
+static void enqueue_spec_render(rad_ctx* c, uint32_t base, uint32_t n, uint32_t excl, uint32_t excl_n, bool defer) {
 	RadDev& S = c->d;
-	S.k = c->spec_slots; S.h0 = 0; S.h1 = nslots; S.spec = 1u; S.stop_gate = 1u; S.deal = 0u;
-	S.small_steps = RAD_SMALL_STEPS; S.tile = RAD_TILE;
-	c->select_override = 2;
-	cudaMemsetAsync(S.F, 0, (size_t)nslots * S.P * 4, c->stream);                 // the slots a cut-short batch did not use are not zeroed by anybody else
-	cudaMemsetAsync(&S.ctl->spec_key[0], 0, 3 * sizeof(unsigned long long), c->stream);
+	c->select_override = 2; c->sel_base = base; c->sel_count = n; c->sel_excl = excl; c->sel_excl_n = excl_n; c->cam_base = base; c->cam_count = n;
+	S.h0 = base; S.h1 = base + n;
+	cudaMemsetAsync(S.F + (size_t)base * S.P, 0, (size_t)n * S.P * 4, c->stream);   // (slots a cut-short batch did not use are not zeroed by anybody else)
 	rad_launch_select(c);
+	c->defer_join = defer;
 	rad_launch_raster_process(c, false);
-	const int r = rad_launch_spec_apply(c, S, nslots, stop_armed);
-	c->select_override = 0;
-	c->d = saved;
+	c->defer_join = false;
+}
+static int enqueue_spec_apply(rad_ctx* c, uint32_t base, uint32_t n, int stop_armed) {
+	cudaMemsetAsync(&c->d.ctl->spec_key[0], 0, 3 * sizeof(unsigned long long), c->stream);
+	return rad_launch_spec_apply(c, c->d, base, n, stop_armed);
+}
+// one step.  Plain: select + render n slots, then replay the loop over them.  Overlapped (spec_overlap, two halves of
+// RAD_SPEC_SLOTS): half a = (t & 1) was rendered during the previous step; the other half is selected from the state at hand
+// (without a's patches: they are about to shoot) and rendered WHILE the sequential kernel replays the loop over a.
+static int enqueue_spec_step(rad_ctx* c, uint32_t t, uint32_t n, int stop_armed) {
+	SpecView view(c);
+	if (!c->spec_overlap) {
+		enqueue_spec_render(c, 0, n, 0, 0, false);
+		return enqueue_spec_apply(c, 0, n, stop_armed);
+	}
+	const uint32_t H = RAD_SPEC_SLOTS, a = (t & 1u) * H, g = H - a;
+	enqueue_spec_render(c, g, H, a, H, true);
+	const int r = enqueue_spec_apply(c, a, H, stop_armed);
+	rad_join_lanes(c);
 	return r;
 }
 
@@ -462,20 +490,25 @@ static int shoot_speculative(rad_ctx* c, uint32_t n_shots, int stop_test, const 
 	RAD_CUDA_TRY(c, cudaMemsetAsync(&c->d.ctl->gate, 0, sizeof(uint32_t), c->stream));
 	RAD_CUDA_TRY(c, cudaStreamSynchronize(c->stream));                            // (target is a stack variable)
 	uint64_t launches = 0;
-	uint32_t done = 0;
-	RadControl t = ctl0;
+	uint32_t done = 0, t = 0;
+	RadControl ct = ctl0;
 	const uint32_t GB = 4, M = c->spec_slots;
+	if (c->spec_overlap) {                                                        // prologue: half 0 is rendered before the first step
+		const uint32_t l0 = c->launches;
+		{ SpecView view(c); enqueue_spec_render(c, 0, RAD_SPEC_SLOTS, 0, 0, false); }
+		launches += c->launches - l0;
+	}
 	while (done < n_shots) {
 		const uint32_t remaining = n_shots - done;
-		if (remaining >= GB * M) {
-			// a CUDA graph of GB full batches; batches behind the end of the call are gated on the device
+		if (remaining >= GB * M && (t & 1u) == 0u) {
+			// a CUDA graph of GB full steps; steps behind the end of the call are gated on the device
 			if (!c->spec_graph || c->spec_graph_stop != (uint32_t)stop_test) {
 				if (c->spec_graph) { cudaGraphExecDestroy(c->spec_graph); c->spec_graph = nullptr; }
 				cudaGraph_t g = nullptr;
 				const uint32_t l0 = c->launches;
 				RAD_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-				rad_launch_clear_keys(c);
-				for (uint32_t b = 0; b < GB; b++) if ((r = enqueue_spec_batch(c, M, stop_test))) { cudaGraph_t junk; cudaStreamEndCapture(c->stream, &junk); return r; }
+				rad_launch_clear_keys(c);                                        // a replay re-uses the captured epoch tags: every replay starts from cleared keys
+				for (uint32_t b = 0; b < GB; b++) if ((r = enqueue_spec_step(c, b, M, stop_test))) { cudaGraph_t junk; cudaStreamEndCapture(c->stream, &junk); return r; }
 				c->spec_graph_epoch_after = c->epoch;
 				RAD_CUDA_TRY(c, cudaStreamEndCapture(c->stream, &g));
 				RAD_CUDA_TRY(c, cudaGraphInstantiate(&c->spec_graph, g, 0));
@@ -486,19 +519,21 @@ static int shoot_speculative(rad_ctx* c, uint32_t n_shots, int stop_test, const 
 			RAD_CUDA_TRY(c, cudaGraphLaunch(c->spec_graph, c->stream));
 			launches += c->spec_graph_launches;
 			c->epoch = c->spec_graph_epoch_after;
+			t += GB;
 		} else {
-			uint32_t m = 8; while (m < remaining && m < M) m <<= 1;                 // a short tail renders only what it may need
+			uint32_t m = 8; while (m < remaining && m < M) m <<= 1;                 // (plain form: a short tail renders only what it may need)
 			if (m > M) m = M;
 			const uint32_t l0 = c->launches;
-			if ((r = enqueue_spec_batch(c, m, stop_test))) return r;
+			if ((r = enqueue_spec_step(c, t, m, stop_test))) return r;
 			launches += c->launches - l0;
+			t++;
 		}
-		if ((r = read_ctl(c, &t))) return r;
-		done = t.shots_done - ctl0.shots_done;
-		if (t.spec_done) break;
+		if ((r = read_ctl(c, &ct))) return r;
+		done = ct.shots_done - ctl0.shots_done;
+		if (ct.spec_done) break;
 	}
 	c->selkey_valid = false; c->cam_valid = false;
-	*launches_out = launches; *ctl_out = t;
+	*launches_out = launches; *ctl_out = ct;
 	return RAD_OK;
 }
 

@@ -43,6 +43,7 @@ struct __align__(16) RadSmallQuad {
 #define RAD_XB_DATA 4096           // byte offset of the dB planes inside an exchange buffer
 #define RAD_XB_FLAG2 2048          // byte offset of the second flag row (two-shot exchange: reduced slices ready)
 #define RAD_MAX_LANES 8            // concurrent raster lanes (streams) a batch can be split into
+#define RAD_SPEC_POOL 128          // ... and the slots such a context holds: two halves, one being applied while the other is rendered
 #define RAD_SPEC_SLOTS 64          // hemicubes rendered ahead of a strict-progressive (k == 1) run, see rad_ctx::spec
 #define RAD_RING_SLOTS 64          // hemicube slots one launch of the ring path renders (per-slot work lists, see RadRing)
 struct RadQueueCtl {              // work-list counters of one raster lane
@@ -213,8 +214,13 @@ struct rad_ctx {
 	// batch (raster lanes, full GPU), and spec_apply_kernel then replays the reference's one-shot-at-a-time loop over them:
 	// argmax of the CURRENT B, transfer with the S of that moment, emitter update, stop test — exactly the k == 1 semantics.
 	// A shot whose shooter is not among the rendered ones ends the batch; the next batch is selected from the state reached.
+	uint32_t key_bufs;            // key buffers allocated (<= key_slots)
 	uint32_t key_slots;           // hemicube slots the key / F / emitter buffers hold (hemicubes, or RAD_SPEC_SLOTS for a speculative k == 1 context)
 	bool spec; uint32_t spec_slots; cudaGraphExec_t spec_graph; uint32_t spec_graph_batches, spec_graph_launches, spec_graph_stop, spec_graph_epoch_after; int spec_blocks;
+	// render-ahead overlap of the speculative path: the list of a selection goes to em[sel_base .. +sel_count), patches already
+	// waiting in em[sel_excl .. +sel_excl_n) are left out; the camera kernel covers [cam_base, +cam_count); defer_join: the raster
+	// lanes are not joined to the context's stream by rad_launch_raster_process (rad_join_lanes does it later)
+	bool spec_overlap; uint32_t sel_base, sel_count, sel_excl, sel_excl_n, cam_base, cam_count, last_lanes; bool defer_join;
 	int select_override;          // 0: cfg.select_mode; 2: top-k with the argmax's tie rule (higher id first) — the speculative path's candidate set
 	bool pdl;                     // RAD_PDL=1 (opt-in, k == 1): the kernels of a shot are chained by programmatic dependent launches
 	bool lane_delta_done;         // multi-GPU: the raster lanes of the batch being enqueued have added their dB themselves (no whole-rank kernel needed)
@@ -242,7 +248,8 @@ void rad_launch_delta(rad_ctx* c);                  // multi-GPU: local dB (whol
 void rad_launch_lane_delta(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_t s0, uint32_t n);   // multi-GPU: local dB of one raster lane's slots, added into the rank's planes
 void rad_launch_xreduce(rad_ctx* c);                // multi-GPU, fused two-shot exchange: this rank's slice of the summed dB
 void rad_launch_finish(rad_ctx* c, bool fuse_select); // multi-GPU: B += dB, emitter update
-int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t nslots, int stop_armed);   // speculative k == 1 path: the sequential part (cooperative launch)
+int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t slot_base, uint32_t nslots, int stop_armed);
+void rad_join_lanes(rad_ctx* c);                    // the raster lanes of a deferred-join batch rejoin the context's stream   // speculative k == 1 path: the sequential part (cooperative launch)
 void rad_launch_argmax(rad_ctx* c);                 // k==1: prime selkey[parity] from the current B
 void rad_launch_read_depth(rad_ctx* c, uint32_t hi, uint32_t* d_out);
 void rad_launch_tiles_view(rad_ctx* c, const RadDev& V, const RadTiles& T, cudaStream_t st, uint32_t s0, uint32_t n, bool keep_items,

@@ -32,11 +32,11 @@
 namespace {
 
 // one block per hemicube slot: lanes 0..4 build the face matrices, lane 0 takes the snapshot (camera.cuh)
-__global__ void camera_kernel(RadDev D, int sel_parity) {
+__global__ void camera_kernel(RadDev D, int sel_parity, uint32_t slot_base) {
 	__shared__ RadEmitter s_e;
 	pdl_enter();
 	if (D.stop_gate && blockIdx.x == 0 && threadIdx.x == 0 && (D.spec ? D.ctl->spec_done : D.ctl->stopped)) D.ctl->gate = 1;   // the previous batch was the last one (Main.cpp:1137,1298)
-	camera_block(D, blockIdx.x, sel_parity, &s_e);
+	camera_block(D, slot_base + blockIdx.x, sel_parity, &s_e);
 }
 
 struct CV { float x, y, z, w; };
@@ -862,7 +862,7 @@ void rad_launch_atomic_bench(rad_ctx* c, uint32_t pattern, uint32_t steps, uint3
 }
 
 void rad_launch_camera(rad_ctx* c, int sel_parity) {
-	rad_launch_pdl(c->pdl, camera_kernel, dim3(c->d.k), dim3(32), 0, c->stream, c->d, sel_parity);
+	rad_launch_pdl(c->pdl, camera_kernel, dim3(c->cam_count ? c->cam_count : c->d.k), dim3(32), 0, c->stream, c->d, sel_parity, c->cam_count ? c->cam_base : 0u);
 	c->launches++;
 }
 
@@ -1087,8 +1087,12 @@ void rad_launch_raster_process_marked(rad_ctx* c, bool keep_items, const std::fu
 			launch_chunks(c, V, st, kbase); if (mark) mark(2);
 			rad_launch_process_view(c, V, st, s0, n, kbase, keep_items); if (mark) mark(4);
 		}
-		if (L > 1) { cudaEventRecord(c->ev_lane[lane], st); cudaStreamWaitEvent(c->stream, c->ev_lane[lane], 0); }
+		if (L > 1) { cudaEventRecord(c->ev_lane[lane], st); if (!c->defer_join) cudaStreamWaitEvent(c->stream, c->ev_lane[lane], 0); }
 	}
+	c->last_lanes = L;
+}
+void rad_join_lanes(rad_ctx* c) {
+	if (c->last_lanes > 1) for (uint32_t lane = 0; lane < c->last_lanes; lane++) cudaStreamWaitEvent(c->stream, c->ev_lane[lane], 0);
 }
 void rad_launch_raster_process(rad_ctx* c, bool keep_items) { rad_launch_raster_process_marked(c, keep_items, nullptr); }
 
@@ -1104,7 +1108,7 @@ void rad_launch_resolve(rad_ctx* c, bool) {
 
 void rad_launch_clear_keys(rad_ctx* c) {
 	const RadDev& D = c->d;
-	clear_keys_kernel<<<148 * 8, 256, 0, c->stream>>>(D.keys, (size_t)c->key_slots * D.RES);   // every buffer: the epoch is shared by all of them
+	clear_keys_kernel<<<148 * 8, 256, 0, c->stream>>>(D.keys, (size_t)c->key_bufs * D.RES);   // every buffer: the epoch is shared by all of them
 	c->launches++;
 	c->keys_dirty = false;
 	c->epoch = 254;

@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(1024) select_reference_kernel(RadDev D) {
 // chunks' winners are the next level's input; the block that finishes LAST on a level with <= 2048 / keep chunks
 // merges them and writes the emitter list — one launch for 16 k patches, two for 1 M.  Exact and deterministic.
 constexpr int kTopChunk = 2048, kTopThreads = 1024;
+struct TopkSpec { uint32_t count, slot_base, excl_base, excl_n; };   // speculative path (mode 2): list length and destination, slots whose patches are left out
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
 	return ((unsigned long long)__shfl_xor_sync(FULL, (unsigned)(v >> 32), m) << 32) | __shfl_xor_sync(FULL, (unsigned)v, m);
@@ -268,11 +269,16 @@ __device__ __forceinline__ void block_topk(unsigned long long& a0, unsigned long
 // run take the fast path (the fresh scene's 99 equal light patches are the other two).
 template <bool FIRST>
 __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const unsigned long long* __restrict__ in, uint32_t n_in,
-                                                                  unsigned long long* __restrict__ out, int keep, int finish, int ref_mode) {
+                                                                  unsigned long long* __restrict__ out, int keep, int finish, int ref_mode, TopkSpec sp) {
 	__shared__ unsigned long long s[kTopChunk];
 	__shared__ bool s_last;
+	__shared__ uint32_t s_excl[RAD_SPEC_SLOTS];
 	const int t = threadIdx.x;
 	unsigned long long a[2];
+	if (FIRST && ref_mode == 2 && sp.excl_n) {      // patches already rendered ahead (the half about to be applied) are not candidates
+		if ((uint32_t)t < RAD_SPEC_SLOTS) s_excl[t] = ((uint32_t)t < sp.excl_n && D.em[sp.excl_base + t].valid) ? D.em[sp.excl_base + t].id : 0xFFFFFFFFu;
+		__syncthreads();
+	}
 	const uint32_t e0b = (FIRST && ref_mode == 1) ? __float_as_uint(len2(D.rad[0], D.rad[D.P], D.rad[2 * (size_t)D.P])) : 0u;
 	#pragma unroll
 	for (int r = 0; r < 2; r++) {
@@ -281,7 +287,11 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 		if (i < n_in) {
 			if constexpr (FIRST) {
 				const uint32_t eb = __float_as_uint(len2(D.rad[i], D.rad[D.P + i], D.rad[2 * (size_t)D.P + i]));
-				const bool in_s = ref_mode != 1 || eb >= e0b;                         // (positive floats order like their bits)
+				bool in_s = ref_mode != 1 || eb >= e0b;                         // (positive floats order like their bits)
+				if (ref_mode == 2 && sp.excl_n && eb != 0) {
+					#pragma unroll 8
+					for (uint32_t j = 0; j < RAD_SPEC_SLOTS; j++) in_s = in_s && s_excl[j] != i;
+				}
 				if (eb != 0 && eb < 0x7F800000u && in_s) key = ((unsigned long long)eb << 32) | (ref_mode == 2 ? i : 0xFFFFFFFFu - i);   // 2: ties -> higher id first, the argmax's rule
 			} else key = in[i];
 		}
@@ -323,6 +333,13 @@ __global__ void __launch_bounds__(kTopThreads) topk_level_kernel(RadDev D, const
 			D.em[t].id = a[0] ? 0xFFFFFFFFu - (uint32_t)(a[0] & 0xFFFFFFFFull) : 0u;
 			D.em[t].valid = (a[0] || isseed) ? 1u : 0u;
 			D.em[t].order = (uint32_t)t;
+		}
+		return;
+	}
+	if (ref_mode == 2) {                           // speculative path: `count` entries into em[slot_base ..)
+		if ((uint32_t)t < sp.count) {
+			RadEmitter* e = D.em + sp.slot_base + t;
+			e->id = a[0] ? (uint32_t)(a[0] & 0xFFFFFFFFull) : 0u; e->valid = a[0] ? 1u : 0u; e->order = (uint32_t)t;
 		}
 		return;
 	}
@@ -581,14 +598,14 @@ __global__ void __launch_bounds__(256) lane_delta_kernel(RadDev D) {
 // is not among the rendered slots ends the batch (the caller selects the next batch from the state reached); the first shot
 // of a batch always hits, its shooter is slot 0 by construction.
 template <int PPT>
-__global__ void __launch_bounds__(1024, 1) spec_apply_kernel(RadDev D, uint32_t nslots, int stop_armed) {
+__global__ void __launch_bounds__(1024, 1) spec_apply_kernel(RadDev D, uint32_t slot_base, uint32_t nslots, int stop_armed) {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	__shared__ uint32_t s_id[RAD_SPEC_SLOTS], s_used[RAD_SPEC_SLOTS];
 	__shared__ unsigned long long s_key;
 	__shared__ int s_slot;
 	if (D.ctl->gate) return;                    // (grid-uniform: latched by the camera kernel of this batch)
 	const uint32_t P = D.P, tid = threadIdx.x, stride = gridDim.x * 1024u, i0 = blockIdx.x * 1024u + tid;
-	if (tid < RAD_SPEC_SLOTS) { s_id[tid] = (tid < nslots && D.em[tid].valid) ? D.em[tid].id : 0xFFFFFFFFu; s_used[tid] = 0u; }
+	if (tid < RAD_SPEC_SLOTS) { s_id[tid] = (tid < nslots && D.em[slot_base + tid].valid) ? D.em[slot_base + tid].id : 0xFFFFFFFFu; s_used[tid] = 0u; }
 	float bx[PPT], by[PPT], bz[PPT];
 	#pragma unroll
 	for (int j = 0; j < PPT; j++) {
@@ -638,7 +655,7 @@ __global__ void __launch_bounds__(1024, 1) spec_apply_kernel(RadDev D, uint32_t 
 		if (slot < 0) { missed = 1; break; }        // not rendered ahead: the batch ends here
 		const float4 Sv = __ldcg(D.spec_cand + rk * 256u + (shooter >> 10) % gridDim.x);     // the owner block's candidate IS the winner
 		const float c0 = __ldg(D.color + shooter), c1 = __ldg(D.color + P + shooter), c2 = __ldg(D.color + 2 * (size_t)P + shooter);
-		const float* __restrict__ F = D.F + (size_t)slot * P;
+		const float* __restrict__ F = D.F + (size_t)(slot_base + (uint32_t)slot) * P;
 		#pragma unroll
 		for (int j = 0; j < PPT; j++) {
 			const uint32_t i = i0 + (uint32_t)j * stride;
@@ -679,7 +696,7 @@ __global__ void __launch_bounds__(1024, 1) spec_apply_kernel(RadDev D, uint32_t 
 // into all 16 CTAs' tables, double-buffered by shot parity — and meet at the hardware cluster barrier instead of a grid
 // barrier through global memory.  Everything else is spec_apply_kernel.
 template <int PPT>
-__global__ void __launch_bounds__(1024, 1) spec_apply_cluster_kernel(RadDev D, uint32_t nslots, int stop_armed) {
+__global__ void __launch_bounds__(1024, 1) spec_apply_cluster_kernel(RadDev D, uint32_t slot_base, uint32_t nslots, int stop_armed) {
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster();
 	__shared__ uint32_t s_id[RAD_SPEC_SLOTS], s_used[RAD_SPEC_SLOTS];
@@ -690,7 +707,7 @@ __global__ void __launch_bounds__(1024, 1) spec_apply_cluster_kernel(RadDev D, u
 	__shared__ float4 c_S[2][16];
 	if (D.ctl->gate) return;                    // (uniform over the cluster)
 	const uint32_t P = D.P, tid = threadIdx.x, NB = cluster.num_blocks(), rank = cluster.block_rank(), stride = NB * 1024u, i0 = rank * 1024u + tid;
-	if (tid < RAD_SPEC_SLOTS) { s_id[tid] = (tid < nslots && D.em[tid].valid) ? D.em[tid].id : 0xFFFFFFFFu; s_used[tid] = 0u; }
+	if (tid < RAD_SPEC_SLOTS) { s_id[tid] = (tid < nslots && D.em[slot_base + tid].valid) ? D.em[slot_base + tid].id : 0xFFFFFFFFu; s_used[tid] = 0u; }
 	float bx[PPT], by[PPT], bz[PPT];
 	#pragma unroll
 	for (int j = 0; j < PPT; j++) {
@@ -743,7 +760,7 @@ __global__ void __launch_bounds__(1024, 1) spec_apply_cluster_kernel(RadDev D, u
 		if (slot < 0) { missed = 1; break; }
 		const float4 Sv = c_S[par][owner];
 		const float c0 = __ldg(D.color + shooter), c1 = __ldg(D.color + P + shooter), c2 = __ldg(D.color + 2 * (size_t)P + shooter);
-		const float* __restrict__ F = D.F + (size_t)slot * P;
+		const float* __restrict__ F = D.F + (size_t)(slot_base + (uint32_t)slot) * P;
 		#pragma unroll
 		for (int j = 0; j < PPT; j++) {
 			const uint32_t i = i0 + (uint32_t)j * stride;
@@ -803,8 +820,10 @@ void rad_launch_select(rad_ctx* c) {
 	} else {
 		const bool ref = c->cfg.select_mode == RAD_SELECT_REFERENCE && c->select_override == 0;
 		const int mode = c->select_override ? c->select_override : (ref ? 1 : 0);
+		TopkSpec sp = { D.k, 0u, 0u, 0u };
+		if (mode == 2) { sp.count = c->sel_count ? c->sel_count : D.k; sp.slot_base = c->sel_base; sp.excl_base = c->sel_excl; sp.excl_n = c->sel_excl_n; }
 		int keep = 64;
-		while ((uint32_t)keep < D.k + (ref ? 1u : 0u)) keep <<= 1;             // reference list: one entry beyond its end (tie check)
+		while ((uint32_t)keep < (mode == 2 ? sp.count : D.k) + (ref ? 1u : 0u)) keep <<= 1;             // reference list: one entry beyond its end (tie check)
 		uint32_t n = D.P;
 		const unsigned long long* in = nullptr;
 		unsigned long long* out = D.cand0;
@@ -812,8 +831,8 @@ void rad_launch_select(rad_ctx* c) {
 		for (;;) {
 			const uint32_t nb = (n + kTopChunk - 1) / kTopChunk;
 			const int fin = nb * (uint32_t)keep <= (uint32_t)kTopChunk;       // the level's last block can finish the selection
-			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, mode);
-			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, mode);
+			if (first) topk_level_kernel<true><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, mode, sp);
+			else topk_level_kernel<false><<<nb, kTopThreads, 0, c->stream>>>(D, in, n, out, keep, fin, mode, sp);
 			c->launches++;
 			if (fin) break;
 			n = nb * keep; in = out; out = out == D.cand0 ? D.cand1 : D.cand0; first = false;
@@ -856,7 +875,7 @@ void rad_launch_lane_delta(rad_ctx* c, const RadDev& V, cudaStream_t st, uint32_
 	c->lane_delta_done = true;
 }
 // the grid covers every patch: blocks of 1024 threads, one per SM at most (co-resident: the kernel has a grid barrier per shot)
-int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t nslots, int stop_armed) {
+int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t slot_base, uint32_t nslots, int stop_armed) {
 	int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->cfg.device);
 	uint32_t nb = (S.P + 1023u) / 1024u;
 	if (nb > (uint32_t)nsm) nb = (uint32_t)nsm;
@@ -885,7 +904,7 @@ int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t nslots, int stop
 		cat[0].id = cudaLaunchAttributeClusterDimension; cat[0].val.clusterDim.x = 16; cat[0].val.clusterDim.y = 1; cat[0].val.clusterDim.z = 1;
 		ccfg.attrs = cat; ccfg.numAttrs = 1;
 		RadDev Dc = S;
-		void* cargs[3] = { (void*)&Dc, (void*)&nslots, (void*)&stop_armed };
+		void* cargs[4] = { (void*)&Dc, (void*)&slot_base, (void*)&nslots, (void*)&stop_armed };
 		const cudaError_t ce = cudaLaunchKernelExC(&ccfg, cfn, cargs);
 		if (ce == cudaSuccess) { c->launches++; return RAD_OK; }
 		cudaGetLastError();                      // (a device that cannot place the cluster: the grid form below)
@@ -900,7 +919,7 @@ int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t nslots, int stop
 	at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
 	cfg.attrs = at; cfg.numAttrs = 1;
 	RadDev D = S;
-	void* args[3] = { (void*)&D, (void*)&nslots, (void*)&stop_armed };
+	void* args[4] = { (void*)&D, (void*)&slot_base, (void*)&nslots, (void*)&stop_armed };
 	const cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
 	c->launches++;
 	if (e != cudaSuccess) { c->err = std::string("spec_apply_kernel launch: ") + cudaGetErrorString(e); return RAD_E_CUDA; }
