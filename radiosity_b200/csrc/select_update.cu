@@ -691,6 +691,87 @@ __global__ void __launch_bounds__(1024, 1) spec_apply_kernel(RadDev D, uint32_t 
 	}
 }
 
+// Small scenes (P <= 148 x 512): one patch per thread, blocks of 512 threads, and everything a shot needs staged ON CHIP before
+// the loop starts — the F entry of the thread's patch for every rendered slot (64 x 512 floats of shared memory), the slots'
+// emitter colours and self form factors — so that a shot's dependent chain is block reduction -> barrier -> slot look-up ->
+// update, with no L2 round trip behind the barrier.  Otherwise spec_apply_kernel<1>.
+__global__ void __launch_bounds__(512, 1) spec_apply_smem_kernel(RadDev D, uint32_t slot_base, uint32_t nslots, int stop_armed) {
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	extern __shared__ float sF[];                 // [nslots][512]
+	__shared__ uint32_t s_id[RAD_SPEC_SLOTS], s_used[RAD_SPEC_SLOTS];
+	__shared__ float s_col[RAD_SPEC_SLOTS][3], s_fself[RAD_SPEC_SLOTS];
+	__shared__ unsigned long long s_key;
+	__shared__ int s_slot;
+	if (D.ctl->gate) return;
+	const uint32_t P = D.P, tid = threadIdx.x, i = blockIdx.x * 512u + tid;
+	const bool live = i < P;
+	if (tid < RAD_SPEC_SLOTS) {
+		const bool v = tid < nslots && D.em[slot_base + tid].valid;
+		const uint32_t id = v ? D.em[slot_base + tid].id : 0xFFFFFFFFu;
+		s_id[tid] = id; s_used[tid] = 0u;
+		s_col[tid][0] = v ? __ldg(D.color + id) : 0.0f; s_col[tid][1] = v ? __ldg(D.color + P + id) : 0.0f; s_col[tid][2] = v ? __ldg(D.color + 2 * (size_t)P + id) : 0.0f;
+		s_fself[tid] = v ? __ldcg(D.F + (size_t)(slot_base + tid) * P + id) : 0.0f;
+	}
+	for (uint32_t sl = 0; sl < nslots; sl++) sF[sl * 512u + tid] = live ? __ldcg(D.F + (size_t)(slot_base + sl) * P + i) : 0.0f;
+	float bx = 0.0f, by = 0.0f, bz = 0.0f;
+	if (live) { bx = D.rad[i]; by = D.rad[P + i]; bz = D.rad[2 * (size_t)P + i]; }
+	const uint32_t target = D.ctl->spec_target, done0 = D.ctl->shots_done;
+	const float rho = D.reflectivity;
+	uint32_t count = 0; int ended = 0, missed = 0;
+	__syncthreads();
+	for (uint32_t shot = 0; done0 + count < target; shot++) {
+		const unsigned long long mine = live ? energy_key_last(len2(bx, by, bz), i) : 0ull;
+		const unsigned long long blockbest = block_max(mine);
+		const uint32_t rk = shot % 3u;
+		if (tid == 0) {
+			s_key = blockbest;
+			if (blockbest) atomicMax(&D.ctl->spec_key[rk], blockbest);
+			if (blockIdx.x == 0) D.ctl->spec_key[(shot + 1u) % 3u] = 0ull;
+		}
+		__syncthreads();
+		if (mine != 0ull && mine == s_key) D.spec_cand[rk * 256u + blockIdx.x] = make_float4(bx, by, bz, 0.0f);
+		grid.sync();
+		const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&D.ctl->spec_key[rk]);
+		if (key == 0ull) {
+			count = target - done0; ended = 1;
+			if (blockIdx.x == 0 && tid == 0) { D.ctl->last_energy_len = 0.0f; D.ctl->stopped = 1; }
+			break;
+		}
+		const uint32_t shooter = (uint32_t)(key & 0xFFFFFFFFull);
+		if (tid == 0) s_slot = -1;
+		__syncthreads();
+		if (tid < nslots && s_id[tid] == shooter && !s_used[tid]) s_slot = (int)tid;
+		__syncthreads();
+		const int slot = s_slot;
+		if (slot < 0) { missed = 1; break; }
+		const float4 Sv = __ldcg(D.spec_cand + rk * 256u + (shooter >> 9));      // the owner block's candidate IS the winner
+		const float c0 = s_col[slot][0], c1 = s_col[slot][1], c2 = s_col[slot][2];
+		if (live) {
+			const float f = sF[(uint32_t)slot * 512u + tid];
+			bx += ((Sv.x * f) * rho) * c0; by += ((Sv.y * f) * rho) * c1; bz += ((Sv.z * f) * rho) * c2;
+			if (i == shooter) {
+				D.illum[i] += Sv.x; D.illum[P + i] += Sv.y; D.illum[2 * (size_t)P + i] += Sv.z;
+				bx -= Sv.x; by -= Sv.y; bz -= Sv.z;
+			}
+		}
+		const float fs = s_fself[slot];
+		const float ex = Sv.x + ((Sv.x * fs) * rho) * c0, ey = Sv.y + ((Sv.y * fs) * rho) * c1, ez = Sv.z + ((Sv.z * fs) * rho) * c2;
+		const float l = sqrtf(len2(ex, ey, ez));
+		const bool stop_now = (double)l < 0.1;
+		if (blockIdx.x == 0 && tid == 0) { D.ctl->last_energy_len = l; if (stop_now) D.ctl->stopped = 1; }
+		if (tid == 0) s_used[slot] = 1u;
+		count++;
+		if (stop_armed && stop_now) { ended = 1; break; }
+		__syncthreads();
+	}
+	if (live) { D.rad[i] = bx; D.rad[P + i] = by; D.rad[2 * (size_t)P + i] = bz; }
+	if (blockIdx.x == 0 && tid == 0) {
+		D.ctl->shots_done = done0 + count; D.ctl->batches_done += count;
+		D.ctl->spec_hits += count; D.ctl->spec_misses += (uint32_t)missed;
+		if (ended || done0 + count >= target) D.ctl->spec_done = 1;
+	}
+}
+
 // Cluster form of the same loop for scenes that fit ONE thread-block cluster (P <= 16 x 1024 x PPT patches): the 16 CTAs
 // exchange their argmax candidates (key + B of that patch) through distributed shared memory — every CTA stores its candidate
 // into all 16 CTAs' tables, double-buffered by shot parity — and meet at the hardware cluster barrier instead of a grid
@@ -908,6 +989,22 @@ int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t slot_base, uint3
 		const cudaError_t ce = cudaLaunchKernelExC(&ccfg, cfn, cargs);
 		if (ce == cudaSuccess) { c->launches++; return RAD_OK; }
 		cudaGetLastError();                      // (a device that cannot place the cluster: the grid form below)
+	}
+	// small scenes: everything a shot reads staged in shared memory (RAD_SPEC_SMEM=0: the register form below)
+	static const bool use_smem = [] { const char* e = getenv("RAD_SPEC_SMEM"); return !e || atoi(e) != 0; }();
+	if (use_smem && S.P <= (uint32_t)nsm * 512u && S.P <= 256u * 512u && nslots <= RAD_SPEC_SLOTS) {
+		static bool smem_attr = false;
+		if (!smem_attr) { cudaFuncSetAttribute(spec_apply_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RAD_SPEC_SLOTS * 512 * 4); smem_attr = true; }
+		cudaLaunchConfig_t scfg = {};
+		scfg.gridDim = dim3((S.P + 511u) / 512u); scfg.blockDim = dim3(512); scfg.dynamicSmemBytes = (size_t)nslots * 512 * 4; scfg.stream = c->stream;
+		cudaLaunchAttribute sat[1];
+		sat[0].id = cudaLaunchAttributeCooperative; sat[0].val.cooperative = 1;
+		scfg.attrs = sat; scfg.numAttrs = 1;
+		RadDev Ds = S;
+		void* sargs[4] = { (void*)&Ds, (void*)&slot_base, (void*)&nslots, (void*)&stop_armed };
+		const cudaError_t se = cudaLaunchKernelExC(&scfg, (const void*)spec_apply_smem_kernel, sargs);
+		if (se == cudaSuccess) { c->launches++; return RAD_OK; }
+		cudaGetLastError();
 	}
 	const void* fn = nullptr;
 	if (ppt <= 1) fn = (const void*)spec_apply_kernel<1>; else if (ppt <= 2) fn = (const void*)spec_apply_kernel<2>; else if (ppt <= 4) fn = (const void*)spec_apply_kernel<4>;
