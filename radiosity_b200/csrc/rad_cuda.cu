@@ -147,7 +147,7 @@ int rad_create(rad_ctx** out, const rad_config* cfg) {
 	A(dalloc(D.keys, (size_t)kbufs * D.RES)); A(dalloc(D.items, (size_t)D.k * D.RES));
 	A(dalloc(D.F, (size_t)kslots * Pm)); A(dalloc(D.dB, 3 * Pm));
 	A(dalloc(D.mvp, (size_t)kslots * RAD_NFACES * 16)); A(dalloc(D.em, (size_t)kslots)); A(dalloc(D.emlite, 2 * (size_t)kslots)); A(dalloc(D.ctl, 1)); A(dalloc(D.rc, 1));
-	A(dalloc(D.spec_cand, (size_t)3 * 256));
+	A(dalloc(D.spec_cand, (size_t)3 * 256)); A(dalloc(D.spec_steps, (size_t)RAD_SPEC_SLOTS));
 	A(dalloc(D.q_tri, (size_t)D.q_tri_cap)); A(dalloc(D.q_ent, (size_t)D.q_ent_cap)); A(dalloc(D.q_sm, (size_t)D.q_sm_cap)); A(dalloc(D.pairs, (size_t)D.pairs_cap)); A(dalloc(D.nb, 8 * Pm)); A(dalloc(D.shade_e, 3 * Pm));
 	A(dalloc(D.ework, Pm < RAD_MAX_HEMICUBES ? (size_t)RAD_MAX_HEMICUBES : Pm)); A(dalloc(D.cand0, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(D.cand1, ((Pm + 2047) / 2048) * (size_t)RAD_MAX_HEMICUBES)); A(dalloc(proj, 16));
 	if (c->tile_mode) {
@@ -197,7 +197,7 @@ int rad_destroy(rad_ctx* c) {
 	RadDev& D = c->d;
 	cudaFree((void*)D.v0); cudaFree((void*)D.v1); cudaFree((void*)D.v2); cudaFree((void*)D.color);
 	cudaFree(D.rad); cudaFree(D.illum); cudaFree((void*)D.ff); cudaFree(D.keys); cudaFree(D.items);
-	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.emlite); cudaFree(D.ctl); cudaFree(D.rc); cudaFree(D.spec_cand);
+	cudaFree(D.F); cudaFree(D.dB); cudaFree(D.mvp); cudaFree(D.em); cudaFree(D.emlite); cudaFree(D.ctl); cudaFree(D.rc); cudaFree(D.spec_cand); cudaFree(D.spec_steps);
 	cudaFree(D.q_tri); cudaFree(D.q_ent); cudaFree(D.q_sm); cudaFree(D.pairs); cudaFree(D.nb); cudaFree(D.shade_e); cudaFree(D.ework); cudaFree(D.cand0); cudaFree(D.cand1); cudaFree((void*)D.proj);
 	if (c->tl.cnt) cudaFree(c->tl.cnt);
 	if (c->tl.base) cudaFree(c->tl.base);

@@ -54,6 +54,13 @@ struct RadQueueCtl {              // work-list counters of one raster lane
 	uint32_t parked;              // records parked by the lane's last batch (statistics)
 	uint32_t pad[3];
 };
+struct RadSpecStep {              // one simulated shot of the speculative k == 1 path (spec_sim_kernel -> spec_verify_kernel / spec_commit_kernel)
+	unsigned long long key;       // the shooter's argmax key (energy bits << 32 | id) right before the shot
+	uint32_t slot, id;            // rendered-ahead slot and patch
+	float S[3], c[3];             // its B at that moment, its colour
+	float len;                    // |B| of the emitter after the transfer, before the subtraction (the stop test's lastEnergy)
+	float pad;
+};
 struct RadControl {               // small device-resident control block
 	unsigned long long selkey[2]; // k==1 selection: (E bits << 32 | id), ping-pong by batch parity
 	unsigned long long spec_key[3];   // speculative k == 1 path: the grid's argmax key of shot s in spec_key[s % 3]
@@ -68,6 +75,9 @@ struct RadControl {               // small device-resident control block
 	uint32_t ticket;              // blocks finished ("last block merges" pattern of the selection / update kernels)
 	uint32_t spec_target;         // speculative k == 1 path: shots_done at which the call ends
 	uint32_t spec_done;           // ... reached (or the stop test fired while armed): the batches still enqueued do nothing
+	uint32_t spec_count_sim;      // shots spec_sim_kernel could simulate over the rendered-ahead set
+	uint32_t spec_jstar;          // ... of which the first spec_jstar are what the strict loop does (spec_verify_kernel: no patch outside overtakes before)
+	uint32_t spec_alldark;        // nothing carries energy: the remaining shots are the reference's no-op shots of patch 0
 	uint32_t spec_hits, spec_misses;   // statistics: shots served from a rendered-ahead hemicube / batches cut short by a shooter outside the set
 	uint32_t ref_fast;            // RAD_SELECT_REFERENCE, k > 1: the tie-free fast path has written the emitter list of this batch
 	uint32_t ring_abort;          // ring path watchdog: a wait inside raster_ring_kernel timed out (never expected; the call fails instead of hanging)
@@ -134,6 +144,7 @@ struct RadDev {                   // device pointers + sizes, passed by value to
 	RadEmitter* em;               // [k]
 	float4* emlite;               // [k][2] what the update kernel needs of an emitter: (S, valid | order << 1), (colour, id)
 	RadControl* ctl;
+	RadSpecStep* spec_steps;      // [RAD_SPEC_SLOTS] the simulated shots of the batch in flight
 	float4* spec_cand;            // [3][blocks] (argmax key, B of that patch) of every block of spec_apply_kernel, by shot % 3
 	RadRingCtl* rc;               // ring path: per-slot work-list counters + stage hand-over (see RadRingCtl)
 	RadQueueCtl* qc;              // this launch's lane counters (= &ctl->lane[lane])

@@ -772,6 +772,117 @@ __global__ void __launch_bounds__(512, 1) spec_apply_smem_kernel(RadDev D, uint3
 	}
 }
 
+// ---- the sequential part without a barrier per shot: simulate, verify, commit ------------------------------------------
+// While the shooters come from the rendered-ahead set, the strict loop's decisions depend on the set's OWN radiosities only:
+// member m receives ((S F[s][id_m]) rho) c from the shot of slot s, a 64 x 64 matrix.  spec_sim_kernel replays the loop over
+// the members alone — one block, no grid barrier — and records every shot (slot, S, colour, the shooter's argmax key, the stop
+// test's lastEnergy); it stops at the call's end, at the stop test, or when the strongest member is one whose hemicube is
+// already spent.  spec_verify_kernel then walks every patch through the recorded shots with the loop's own arithmetic and
+// finds the first shot before which a patch OUTSIDE the simulation would have been the argmax (key > the recorded key:
+// largest energy, last index among equals) — up to there the simulation IS the strict loop — and spec_commit_kernel applies
+// exactly those shots.  Same shots, same floats as one shot at a time; 3 launches instead of a grid barrier per shot.
+__global__ void __launch_bounds__(64) spec_sim_kernel(RadDev D, uint32_t slot_base, uint32_t nslots, int stop_armed) {
+	__shared__ float G[RAD_SPEC_SLOTS][RAD_SPEC_SLOTS + 1];      // G[s][m] = F of slot s at member m's patch
+	__shared__ unsigned long long s_k[2];
+	__shared__ int s_w, s_stop;
+	__shared__ float s_S[3], s_c[3];
+	if (D.ctl->gate) return;
+	const uint32_t P = D.P, m = threadIdx.x;
+	const bool valid = m < nslots && D.em[slot_base + m].valid != 0 && D.em[slot_base + m].id < P;
+	const uint32_t id = valid ? D.em[slot_base + m].id : 0u;
+	float bx = 0.0f, by = 0.0f, bz = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+	if (valid) {
+		bx = D.rad[id]; by = D.rad[P + id]; bz = D.rad[2 * (size_t)P + id];
+		c0 = D.color[id]; c1 = D.color[P + id]; c2 = D.color[2 * (size_t)P + id];
+	}
+	for (uint32_t sl = 0; sl < RAD_SPEC_SLOTS; sl++) G[sl][m] = (valid && sl < nslots) ? __ldcg(D.F + (size_t)(slot_base + sl) * P + id) : 0.0f;
+	const uint32_t target = D.ctl->spec_target, done0 = D.ctl->shots_done;
+	const uint32_t R = target > done0 ? target - done0 : 0u;
+	const float rho = D.reflectivity;
+	if (m == 0) s_stop = 0;
+	const int nvalid = __syncthreads_count(valid);
+	if (nvalid == 0) {                              // the set was the strongest of ALL patches: nothing carries energy
+		if (m == 0) { D.ctl->spec_count_sim = 0u; D.ctl->spec_jstar = 0u; D.ctl->spec_alldark = 1u; }
+		return;
+	}
+	bool used = false;
+	uint32_t j = 0;
+	while (j < R && j < RAD_SPEC_SLOTS) {
+		const unsigned long long key = valid ? energy_key_last(len2(bx, by, bz), id) : 0ull;
+		const unsigned long long kw = warp_max(key);
+		if ((m & 31u) == 0u) s_k[m >> 5] = kw;
+		if (m == 0) s_w = -1;
+		__syncthreads();
+		const unsigned long long K = s_k[0] > s_k[1] ? s_k[0] : s_k[1];
+		if (K == 0ull) break;                       // the members have nothing left: the next batch decides
+		if (key == K && !used) { s_w = (int)m; s_S[0] = bx; s_S[1] = by; s_S[2] = bz; s_c[0] = c0; s_c[1] = c1; s_c[2] = c2; }
+		__syncthreads();
+		const int w = s_w;
+		if (w < 0) break;                           // the strongest member's hemicube is spent
+		const float S0 = s_S[0], S1 = s_S[1], S2 = s_S[2], w0 = s_c[0], w1 = s_c[1], w2 = s_c[2];
+		const float f = G[w][m];
+		if (valid) { bx += ((S0 * f) * rho) * w0; by += ((S1 * f) * rho) * w1; bz += ((S2 * f) * rho) * w2; }
+		if ((int)m == w) {
+			const float l = sqrtf(len2(bx, by, bz));   // lastEnergy: after the transfer, before the subtraction (Main.cpp:1292)
+			RadSpecStep st; st.key = K; st.slot = m; st.id = id; st.S[0] = S0; st.S[1] = S1; st.S[2] = S2; st.c[0] = w0; st.c[1] = w1; st.c[2] = w2; st.len = l; st.pad = 0.0f;
+			D.spec_steps[j] = st;
+			bx -= S0; by -= S1; bz -= S2;
+			used = true;
+			if ((double)l < 0.1) s_stop = 1;
+		}
+		j++;
+		__syncthreads();
+		if (stop_armed && s_stop) break;
+	}
+	if (m == 0) { D.ctl->spec_count_sim = j; D.ctl->spec_jstar = j; D.ctl->spec_alldark = 0u; }
+}
+
+// the patch's radiosity after the first n recorded shots, with the strict loop's own arithmetic; verify: the first shot
+// before which this patch would have been the argmax instead (atomicMin into spec_jstar)
+template <bool VERIFY>
+__global__ void __launch_bounds__(256) spec_walk_kernel(RadDev D, uint32_t slot_base, int stop_armed) {
+	__shared__ RadSpecStep s_st[RAD_SPEC_SLOTS];
+	if (D.ctl->gate) return;
+	const uint32_t P = D.P;
+	const uint32_t nsim = D.ctl->spec_count_sim;
+	const uint32_t n = VERIFY ? nsim : min(nsim, D.ctl->spec_jstar);
+	if (!VERIFY && blockIdx.x == 0 && threadIdx.x == 0) {       // the batch's bookkeeping
+		const uint32_t target = D.ctl->spec_target, done0 = D.ctl->shots_done;
+		if (D.ctl->spec_alldark) {                  // the remaining shots are no-op shots of patch 0 that still count (Main.cpp:1161 with S = 0)
+			D.ctl->batches_done += target - done0; D.ctl->shots_done = target;
+			D.ctl->last_energy_len = 0.0f; D.ctl->stopped = 1; D.ctl->spec_done = 1;
+		} else {
+			int low = 0;
+			for (uint32_t j = 0; j < n; j++) low |= (double)D.spec_steps[j].len < 0.1;
+			if (n) D.ctl->last_energy_len = D.spec_steps[n - 1].len;
+			if (low) D.ctl->stopped = 1;
+			D.ctl->shots_done = done0 + n; D.ctl->batches_done += n;
+			D.ctl->spec_hits += n; D.ctl->spec_misses += (n < target - done0) ? 1u : 0u;
+			if (done0 + n >= target || (stop_armed && low)) D.ctl->spec_done = 1;
+		}
+	}
+	if (n == 0) return;
+	for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) s_st[t] = D.spec_steps[t];
+	__syncthreads();
+	const float rho = D.reflectivity;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+		float bx = D.rad[i], by = D.rad[P + i], bz = D.rad[2 * (size_t)P + i];
+		for (uint32_t j = 0; j < n; j++) {
+			const RadSpecStep& st = s_st[j];
+			if (VERIFY) {
+				if (energy_key_last(len2(bx, by, bz), i) > st.key) { atomicMin(&D.ctl->spec_jstar, j); break; }
+			}
+			const float f = __ldcg(D.F + (size_t)(slot_base + st.slot) * P + i);
+			bx += ((st.S[0] * f) * rho) * st.c[0]; by += ((st.S[1] * f) * rho) * st.c[1]; bz += ((st.S[2] * f) * rho) * st.c[2];
+			if (i == st.id) {
+				if (!VERIFY) { D.illum[i] += st.S[0]; D.illum[P + i] += st.S[1]; D.illum[2 * (size_t)P + i] += st.S[2]; }
+				bx -= st.S[0]; by -= st.S[1]; bz -= st.S[2];
+			}
+		}
+		if (!VERIFY) { D.rad[i] = bx; D.rad[P + i] = by; D.rad[2 * (size_t)P + i] = bz; }
+	}
+}
+
 // Cluster form of the same loop for scenes that fit ONE thread-block cluster (P <= 16 x 1024 x PPT patches): the 16 CTAs
 // exchange their argmax candidates (key + B of that patch) through distributed shared memory — every CTA stores its candidate
 // into all 16 CTAs' tables, double-buffered by shot parity — and meet at the hardware cluster barrier instead of a grid
@@ -989,6 +1100,16 @@ int rad_launch_spec_apply(rad_ctx* c, const RadDev& S, uint32_t slot_base, uint3
 		const cudaError_t ce = cudaLaunchKernelExC(&ccfg, cfn, cargs);
 		if (ce == cudaSuccess) { c->launches++; return RAD_OK; }
 		cudaGetLastError();                      // (a device that cannot place the cluster: the grid form below)
+	}
+	// default: simulate over the set's own 64 x 64 transfers, verify against all patches, commit (no barrier per shot);
+	// RAD_SPEC_SIM=0: the cooperative one-barrier-per-shot kernels below
+	static const bool use_sim = [] { const char* e = getenv("RAD_SPEC_SIM"); return !e || atoi(e) != 0; }();
+	if (use_sim && nslots <= RAD_SPEC_SLOTS) {
+		spec_sim_kernel<<<1, 64, 0, c->stream>>>(S, slot_base, nslots, stop_armed);
+		spec_walk_kernel<true><<<patch_grid(S.P, 256), 256, 0, c->stream>>>(S, slot_base, stop_armed);
+		spec_walk_kernel<false><<<patch_grid(S.P, 256), 256, 0, c->stream>>>(S, slot_base, stop_armed);
+		c->launches += 3;
+		return RAD_OK;
 	}
 	// small scenes: everything a shot reads staged in shared memory (RAD_SPEC_SMEM=0: the register form below)
 	static const bool use_smem = [] { const char* e = getenv("RAD_SPEC_SMEM"); return !e || atoi(e) != 0; }();
